@@ -1,0 +1,33 @@
+# Builds the product library (CUDA, sm_100a only) and the oracle's C restatement (CPU checker).
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CUDA_LIB  ?= /usr/local/cuda/lib64
+PKG       := homogenization.jl_b200
+CSRC      := $(PKG)/csrc
+LIB       := $(PKG)/libhmg_b200.so
+NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
+             -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude
+SRCS      := $(CSRC)/api.cu $(CSRC)/kernels.cu $(CSRC)/reference.cpp $(CSRC)/topology.cpp $(CSRC)/introspect.cpp
+HDRS      := include/hmg.h $(CSRC)/hmg_host.hpp $(CSRC)/kernels.cuh $(CSRC)/lattice.hpp
+OBJS      := $(patsubst $(CSRC)/%,build/%.o,$(SRCS))
+
+all: $(LIB) oracle
+
+$(LIB): $(OBJS)
+	$(NVCC) -shared -o $@ $(OBJS) -L$(CUDA_LIB) -lcusolver -lcublas -lnccl \
+	    -Xlinker -rpath=$(CUDA_LIB)
+
+build/%.cu.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
+
+build/%.cpp.o: $(CSRC)/%.cpp $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@
+
+oracle:
+	@if [ -f oracle/c/Makefile ]; then $(MAKE) -C oracle/c; fi
+
+clean:
+	rm -rf build $(LIB)
+
+.PHONY: all oracle clean

@@ -1,0 +1,763 @@
+// C ABI of libhmg_b200 (see include/hmg.h): context, state vectors, orchestration of the V-cycle.
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include "../../include/hmg.h"
+#include "hmg_host.hpp"
+#include "kernels.cuh"
+
+using namespace hmg;
+
+namespace {
+
+thread_local std::string g_err;
+
+#define CUDA_OK(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            throw Error(std::string("hmg: CUDA error: ") + cudaGetErrorString(e_) + " in " #call); \
+    } while (0)
+#define CUSOLVER_OK(call)                                                                    \
+    do {                                                                                     \
+        cusolverStatus_t s_ = (call);                                                        \
+        if (s_ != CUSOLVER_STATUS_SUCCESS)                                                   \
+            throw Error(std::string("hmg: cuSOLVER error ") + std::to_string((int)s_) + " in " #call); \
+    } while (0)
+
+struct LevelDev {
+    LevelView view{};
+    int32_t* hier2lat = nullptr;
+    double* vec[HMG_NVEC] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+}  // namespace
+
+struct hmg_ctx {
+    int dim = 0, nlevels = 0, device = 0;
+    int rank = 0, nranks = 1;
+    int64_t ne = 0, ne_global = 0, nn = 0;
+    double lambda = 1.0;
+    cudaStream_t stream = nullptr;
+    RefElement ref;
+    Topology topo;
+    std::vector<int64_t> elems;          // local elements, 0-based, (dim+1) x ne
+    std::vector<double> nodes;           // dim x nn
+    std::vector<int64_t> local_to_global;
+    std::vector<LevelDev> lv;
+    TopoView tview{};
+    double* elem_coef = nullptr;
+    uint16_t* cmask = nullptr;
+    int32_t* node_first = nullptr;
+    int32_t* elems32 = nullptr;
+    Reducer red{};
+    std::vector<void*> allocs;
+    // coarse level
+    int64_t n_interior = 0;
+    int64_t* interior_idx = nullptr;
+    double* Ainv = nullptr;
+    double *ubase = nullptr, *bint = nullptr, *xint = nullptr;
+    // staging
+    double* staging = nullptr;
+    size_t staging_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+
+    template <class T> T* dalloc(size_t n, bool zero = true) {
+        void* p = nullptr;
+        if (n == 0) n = 1;
+        CUDA_OK(cudaMalloc(&p, n * sizeof(T)));
+        allocs.push_back(p);
+        if (zero) CUDA_OK(cudaMemsetAsync(p, 0, n * sizeof(T), stream));
+        return reinterpret_cast<T*>(p);
+    }
+    template <class T> T* dupload(const std::vector<T>& h) {
+        T* p = dalloc<T>(h.size(), false);
+        if (!h.empty()) CUDA_OK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));   // h may be a temporary
+        return p;
+    }
+    void dfree(void* p) {
+        auto it = std::find(allocs.begin(), allocs.end(), p);
+        if (it != allocs.end()) { cudaFree(p); allocs.erase(it); }
+    }
+    LevelDev& level(int l) {
+        HMG_CHECK(l >= 1 && l <= nlevels, "level out of range");
+        return lv[l - 1];
+    }
+    double* vecp(int l, int which) {
+        HMG_CHECK(which >= 0 && which < HMG_NVEC, "unknown state vector id");
+        LevelDev& L = level(l);
+        if (!L.vec[which]) L.vec[which] = dalloc<double>((size_t)L.view.ld * ne);   // scratch vectors are lazy
+        return L.vec[which];
+    }
+    int64_t nstored(int l) { return (int64_t)level(l).view.ld * ne; }
+};
+
+namespace {
+
+void check_launch(hmg_ctx* c, int n) {
+    c->launches += n;
+    CUDA_OK(cudaGetLastError());
+}
+
+void upload_operator(hmg_ctx* c, const double* sigma) {
+    const int cs = c->dim == 3 ? 8 : 4;
+    std::vector<double> coef;
+    element_coefficients(c->dim, c->ne, c->nodes.data(), c->elems.data(), sigma, coef, cs);
+    if (!c->elem_coef) c->elem_coef = c->dalloc<double>(coef.size(), false);
+    CUDA_OK(cudaMemcpyAsync(c->elem_coef, coef.data(), coef.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+}
+
+hmg_ctx* create_impl(int dim, int nlevels, int64_t ne, int64_t nn, const double* base_nodes,
+                     const int64_t* base_elems, const double* sigma, double lambda, int device) {
+    HMG_CHECK(base_nodes && base_elems && sigma, "null input array");
+    HMG_CHECK(ne > 0 && nn > 0, "empty base mesh");
+    int ndev = 0;
+    cudaError_t de = cudaGetDeviceCount(&ndev);
+    if (de != cudaSuccess || ndev == 0)
+        throw Error("hmg: no CUDA device available -- this library has no CPU fallback");
+    HMG_CHECK(device >= 0 && device < ndev, "device index out of range");
+    CUDA_OK(cudaSetDevice(device));
+    std::unique_ptr<hmg_ctx> c(new hmg_ctx);
+    c->dim = dim;
+    c->nlevels = nlevels;
+    c->device = device;
+    c->ne = c->ne_global = ne;
+    c->nn = nn;
+    c->lambda = lambda;
+    CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreate(&c->ev0));
+    CUDA_OK(cudaEventCreate(&c->ev1));
+
+    const int nv = dim + 1;
+    c->elems.resize((size_t)ne * nv);
+    for (size_t q = 0; q < c->elems.size(); ++q) c->elems[q] = base_elems[q] - 1;   // Julia is 1-based
+    c->nodes.assign(base_nodes, base_nodes + (size_t)nn * dim);
+    c->local_to_global.resize(ne);
+    for (int64_t e = 0; e < ne; ++e) c->local_to_global[e] = e;
+
+    c->ref = build_reference(dim, nlevels);
+    c->topo = build_topology(dim, ne, nn, c->elems.data());
+
+    // per-level tables and state vectors
+    c->lv.resize(nlevels);
+    for (int l = 1; l <= nlevels; ++l) {
+        const RefLevel& R = c->ref.lv[l - 1];
+        LevelDev& L = c->lv[l - 1];
+        LevelView& V = L.view;
+        V.m = R.m; V.nf = R.nf; V.ld = R.ld;
+        V.n_interior = (int)R.interior.size();
+        V.n_boundary = (int)R.boundary.size();
+        V.npf = dim == 3 ? (int)R.face_bary.size() : 0;
+        V.npe = R.m - 1;
+        V.nodeinfo = c->dupload(R.nodeinfo);
+        V.interior = c->dupload(R.interior);
+        V.boundary = c->dupload(R.boundary);
+        V.G = c->dupload(R.G);
+        V.face_bary = c->dupload(R.face_bary);
+        for (int v = 0; v < 4; ++v) V.vpos[v] = v < nv ? R.hier2lat[v] : 0;
+        L.hier2lat = c->dupload(R.hier2lat);
+        for (int w = 0; w <= HMG_AP; ++w) L.vec[w] = c->dalloc<double>((size_t)V.ld * ne);
+    }
+    // topology
+    const Topology& T = c->topo;
+    c->tview.nfaces = T.faces.ncells();
+    c->tview.nedges = T.edges.ncells();
+    c->tview.nverts = T.verts.ncells();
+    c->tview.face_off = c->dupload(T.faces.offset);
+    c->tview.face_own = c->dupload(T.faces.owner);
+    c->tview.edge_off = c->dupload(T.edges.offset);
+    c->tview.edge_own = c->dupload(T.edges.owner);
+    c->tview.vert_off = c->dupload(T.verts.offset);
+    c->tview.vert_own = c->dupload(T.verts.owner);
+    c->cmask = c->dupload(T.cmask);
+    c->node_first = c->dupload(T.node_first);
+    std::vector<int32_t> e32(c->elems.begin(), c->elems.end());
+    c->elems32 = c->dupload(e32);
+    upload_operator(c.get(), sigma);
+    // reductions
+    c->red.max_blocks = 148 * 8;
+    c->red.partials = c->dalloc<double>(c->red.max_blocks);
+    c->red.scalars = c->dalloc<double>(S_COUNT);
+    c->red.ticket = c->dalloc<unsigned int>(1);
+    c->ubase = c->dalloc<double>(nn);
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return c.release();
+}
+
+// ---- building blocks ---------------------------------------------------------------------
+void do_apply(hmg_ctx* c, int l, int mode, double alpha, const double* x, double* y, const double* b) {
+    ApplyArgs a;
+    a.L = c->level(l).view;
+    a.ne = c->ne;
+    a.elem_coef = c->elem_coef;
+    a.cmask = c->cmask;
+    a.x = x; a.y = y; a.b = b;
+    a.alpha = alpha; a.lambda = c->lambda;
+    a.mode = mode;
+    check_launch(c, launch_apply(c->dim, a, c->stream));
+}
+void do_broadcast(hmg_ctx* c, int l, double* x) {
+    check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->stream));
+}
+void do_local_residual(hmg_ctx* c, int l) {
+    do_apply(c, l, APPLY_RESIDUAL, 1.0, c->vecp(l, HMG_X), c->vecp(l, HMG_R), c->vecp(l, HMG_B));
+}
+void do_smoothing(hmg_ctx* c, int l, int steps) {
+    const int64_t n = c->nstored(l);
+    double *x = c->vecp(l, HMG_X), *r = c->vecp(l, HMG_R), *p = c->vecp(l, HMG_P), *Ap = c->vecp(l, HMG_AP);
+    do_local_residual(c, l);
+    do_broadcast(c, l, r);
+    CUDA_OK(cudaMemcpyAsync(p, r, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    c->launches++;
+    check_launch(c, launch_dot(c->red, r, r, n, POST_RHO, 0, c->stream));
+    for (int i = 0; i < steps; ++i) {
+        do_apply(c, l, APPLY_AX, 1.0, p, Ap, nullptr);
+        do_broadcast(c, l, Ap);
+        check_launch(c, launch_dot(c->red, p, Ap, n, POST_PAP, 0, c->stream));
+        check_launch(c, launch_cg_update(c->red, x, p, r, Ap, n, c->stream));
+        check_launch(c, launch_p_update(c->red, p, r, n, c->stream));
+    }
+}
+void do_coarse_solve(hmg_ctx* c) {
+    HMG_CHECK(c->Ainv != nullptr, "coarse matrix not set: call hmg_set_coarse_matrix or hmg_assemble_coarse first");
+    LevelDev& L1 = c->level(1);
+    do_broadcast(c, 1, c->vecp(1, HMG_B));
+    check_launch(c, launch_copy_to_base(L1.view, c->nn, c->node_first, c->vecp(1, HMG_B), c->ubase, c->stream));
+    check_launch(c, launch_gather(c->interior_idx, c->n_interior, c->ubase, c->bint, c->stream));
+    check_launch(c, launch_symv_full(c->Ainv, c->n_interior, c->bint, c->xint, c->stream));
+    check_launch(c, launch_fill(c->ubase, 0.0, c->nn, c->stream));
+    check_launch(c, launch_scatter(c->interior_idx, c->n_interior, c->xint, c->ubase, c->stream));
+    check_launch(c, launch_distribute(c->dim, L1.view, c->ne, c->elems32, c->ubase, c->vecp(1, HMG_X), c->stream));
+}
+void do_vcycle(hmg_ctx* c, int k, int steps) {
+    if (k == 1) { do_coarse_solve(c); return; }
+    do_smoothing(c, k, steps);
+    do_local_residual(c, k);
+    check_launch(c, launch_restrict(c->dim, c->level(k).view, c->level(k - 1).view, c->ne, c->vecp(k, HMG_R),
+                                    c->vecp(k - 1, HMG_B), c->stream));
+    check_launch(c, launch_fill(c->vecp(k - 1, HMG_X), 0.0, c->nstored(k - 1), c->stream));
+    do_vcycle(c, k - 1, 2);   // the reference does not forward `steps` (src/multigrid.jl:109)
+    check_launch(c, launch_interp_add(c->dim, c->level(k).view, c->level(k - 1).view, c->ne, c->vecp(k, HMG_X),
+                                      c->vecp(k - 1, HMG_X), c->stream));
+    do_smoothing(c, k, steps);
+}
+double read_scalar(hmg_ctx* c, int slot) {
+    double v = 0.0;
+    CUDA_OK(cudaMemcpyAsync(&v, c->red.scalars + slot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return v;
+}
+void ensure_staging(hmg_ctx* c, size_t bytes) {
+    if (c->staging_bytes >= bytes) return;
+    if (c->staging) c->dfree(c->staging);
+    c->staging = c->dalloc<double>(bytes / sizeof(double), false);
+    c->staging_bytes = bytes;
+}
+
+void set_coarse_dense(hmg_ctx* c, int64_t n, const std::vector<int64_t>& colptr, const std::vector<int64_t>& rowval,
+                      const std::vector<double>& nzval, const std::vector<int64_t>& interior0) {
+    // dense Cholesky inverse on the device: A^-1 is formed once, every V-cycle applies it with one
+    // bandwidth-bound symmetric matrix-vector product (replaces CHOLMOD's F \ b, src/multigrid.jl:84)
+    if (c->Ainv) { c->dfree(c->Ainv); c->Ainv = nullptr; }
+    if (c->interior_idx) { c->dfree(c->interior_idx); c->interior_idx = nullptr; }
+    if (c->bint) { c->dfree(c->bint); c->bint = nullptr; }
+    if (c->xint) { c->dfree(c->xint); c->xint = nullptr; }
+    c->n_interior = n;
+    c->interior_idx = c->dupload(interior0);
+    c->bint = c->dalloc<double>(n);
+    c->xint = c->dalloc<double>(n);
+    c->Ainv = c->dalloc<double>((size_t)n * n);
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    // scatter the CSC entries column by column through a bounded host buffer
+    {
+        const int64_t chunk_cols = std::max<int64_t>(1, (int64_t)(64 << 20) / (n * 8));
+        std::vector<double> buf;
+        for (int64_t c0 = 0; c0 < n; c0 += chunk_cols) {
+            const int64_t nc = std::min(chunk_cols, n - c0);
+            buf.assign((size_t)nc * n, 0.0);
+            for (int64_t j = 0; j < nc; ++j)
+                for (int64_t q = colptr[c0 + j]; q < colptr[c0 + j + 1]; ++q) buf[(size_t)j * n + rowval[q]] += nzval[q];
+            CUDA_OK(cudaMemcpy(c->Ainv + (size_t)c0 * n, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
+    cusolverDnHandle_t h;
+    CUSOLVER_OK(cusolverDnCreate(&h));
+    CUSOLVER_OK(cusolverDnSetStream(h, c->stream));
+    int lwork1 = 0, lwork2 = 0;
+    CUSOLVER_OK(cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_LOWER, (int)n, c->Ainv, (int)n, &lwork1));
+    CUSOLVER_OK(cusolverDnDpotri_bufferSize(h, CUBLAS_FILL_MODE_LOWER, (int)n, c->Ainv, (int)n, &lwork2));
+    const int lwork = std::max(lwork1, lwork2);
+    double* work = c->dalloc<double>(lwork, false);
+    int* info = c->dalloc<int>(1);
+    CUSOLVER_OK(cusolverDnDpotrf(h, CUBLAS_FILL_MODE_LOWER, (int)n, c->Ainv, (int)n, work, lwork, info));
+    int hinfo = 0;
+    CUDA_OK(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    HMG_CHECK(hinfo == 0, "coarse matrix is not positive definite (potrf failed)");
+    CUSOLVER_OK(cusolverDnDpotri(h, CUBLAS_FILL_MODE_LOWER, (int)n, c->Ainv, (int)n, work, lwork, info));
+    CUDA_OK(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    HMG_CHECK(hinfo == 0, "potri failed on the coarse matrix");
+    check_launch(c, launch_symmetrize_lower(c->Ainv, n, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    cusolverDnDestroy(h);
+    c->dfree(work);
+    c->dfree(info);
+}
+
+}  // namespace
+
+#define HMG_API_BEGIN try {
+#define HMG_API_END                                  \
+    return 0;                                        \
+    }                                                \
+    catch (const std::exception& ex) {               \
+        g_err = ex.what();                           \
+        return 1;                                    \
+    }                                                \
+    catch (...) {                                    \
+        g_err = "hmg: unknown error";                \
+        return 1;                                    \
+    }
+#define NEED_CTX(c) HMG_CHECK((c) != nullptr, "null context")
+
+extern "C" {
+
+const char* hmg_last_error(void) { return g_err.c_str(); }
+int hmg_version(void) { return 100; }
+
+int hmg_create(int dim, int nlevels, int64_t ne, int64_t nn, const double* base_nodes, const int64_t* base_elems,
+               const double* sigma, double lambda, int device, hmg_ctx** out) {
+    HMG_API_BEGIN
+    HMG_CHECK(out != nullptr, "null output pointer");
+    *out = nullptr;
+    *out = create_impl(dim, nlevels, ne, nn, base_nodes, base_elems, sigma, lambda, device);
+    HMG_API_END
+}
+
+int hmg_create_partitioned(int, int, int64_t, int64_t, const double*, const int64_t*, const double*, double, int, int,
+                           int, const int32_t*, const void*, hmg_ctx** out) {
+    HMG_API_BEGIN
+    if (out) *out = nullptr;
+    throw Error("hmg: partitioned contexts are not available in this build");
+    HMG_API_END
+}
+int hmg_nccl_unique_id(void*) {
+    HMG_API_BEGIN
+    throw Error("hmg: partitioned contexts are not available in this build");
+    HMG_API_END
+}
+
+int hmg_destroy(hmg_ctx* c) {
+    HMG_API_BEGIN
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    HMG_API_END
+}
+
+int64_t hmg_nf(const hmg_ctx* c, int level) {
+    if (!c || level < 1 || level > c->nlevels) return -1;
+    return c->lv[level - 1].view.nf;
+}
+int64_t hmg_ne_local(const hmg_ctx* c) { return c ? c->ne : -1; }
+int64_t hmg_ld(const hmg_ctx* c, int level) {
+    if (!c || level < 1 || level > c->nlevels) return -1;
+    return c->lv[level - 1].view.ld;
+}
+int hmg_local_elements(const hmg_ctx* c, int64_t* out) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    for (int64_t e = 0; e < c->ne; ++e) out[e] = c->local_to_global[e] + 1;
+    HMG_API_END
+}
+
+int hmg_set_lambda(hmg_ctx* c, double lambda) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    c->lambda = lambda;
+    HMG_API_END
+}
+int hmg_set_sigma(hmg_ctx* c, const double* sigma) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    HMG_CHECK(sigma != nullptr, "null sigma");
+    CUDA_OK(cudaSetDevice(c->device));
+    upload_operator(c, sigma);
+    HMG_API_END
+}
+
+int hmg_upload(hmg_ctx* c, int level, int which, const double* host, int64_t ld_host) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    LevelDev& L = c->level(level);
+    const int nf = L.view.nf;
+    HMG_CHECK(host != nullptr && ld_host >= nf, "bad host matrix");
+    double* dst = c->vecp(level, which);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(c->ne, (int64_t)(256 << 20) / (nf * 8)));
+    ensure_staging(c, (size_t)chunk * nf * 8);
+    for (int64_t c0 = 0; c0 < c->ne; c0 += chunk) {
+        const int64_t nc = std::min(chunk, c->ne - c0);
+        CUDA_OK(cudaMemcpy2DAsync(c->staging, (size_t)nf * 8, host + c0 * ld_host, (size_t)ld_host * 8, (size_t)nf * 8,
+                                  (size_t)nc, cudaMemcpyHostToDevice, c->stream));
+        check_launch(c, launch_permute_in(L.view, L.hier2lat, c->staging, nf, dst + c0 * L.view.ld, nc, c->stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    HMG_API_END
+}
+
+int hmg_download(hmg_ctx* c, int level, int which, double* host, int64_t ld_host) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    LevelDev& L = c->level(level);
+    const int nf = L.view.nf;
+    HMG_CHECK(host != nullptr && ld_host >= nf, "bad host matrix");
+    const double* src = c->vecp(level, which);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(c->ne, (int64_t)(256 << 20) / (nf * 8)));
+    ensure_staging(c, (size_t)chunk * nf * 8);
+    for (int64_t c0 = 0; c0 < c->ne; c0 += chunk) {
+        const int64_t nc = std::min(chunk, c->ne - c0);
+        check_launch(c, launch_permute_out(L.view, L.hier2lat, src + c0 * L.view.ld, c->staging, nf, nc, c->stream));
+        CUDA_OK(cudaMemcpy2DAsync(host + c0 * ld_host, (size_t)ld_host * 8, c->staging, (size_t)nf * 8, (size_t)nf * 8,
+                                  (size_t)nc, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+    HMG_API_END
+}
+
+int hmg_fill(hmg_ctx* c, int level, int which, double value) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    if (value == 0.0) {
+        check_launch(c, launch_fill(c->vecp(level, which), 0.0, c->nstored(level), c->stream));
+    } else {
+        // pads must stay zero: fill column by column
+        LevelDev& L = c->level(level);
+        double* v = c->vecp(level, which);
+        for (int64_t e = 0; e < c->ne; ++e) check_launch(c, launch_fill(v + e * L.view.ld, value, L.view.nf, c->stream));
+    }
+    HMG_API_END
+}
+int hmg_copy(hmg_ctx* c, int level, int dst, int src) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaMemcpyAsync(c->vecp(level, dst), c->vecp(level, src), c->nstored(level) * sizeof(double),
+                            cudaMemcpyDeviceToDevice, c->stream));
+    HMG_API_END
+}
+int hmg_axpy(hmg_ctx* c, int level, double alpha, int x, int y) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    check_launch(c, launch_axpy(alpha, c->vecp(level, x), c->vecp(level, y), c->nstored(level), c->stream));
+    HMG_API_END
+}
+int hmg_dot(hmg_ctx* c, int level, int a, int b, double* out) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    check_launch(c, launch_dot(c->red, c->vecp(level, a), c->vecp(level, b), c->nstored(level), POST_STORE, S_TMP, c->stream));
+    *out = read_scalar(c, S_TMP);
+    HMG_API_END
+}
+
+int hmg_mul(hmg_ctx* c, int level, double alpha, int x, int y) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    HMG_CHECK(x != y, "mul!: x and y must be different vectors");
+    do_apply(c, level, APPLY_MULADD, alpha, c->vecp(level, x), c->vecp(level, y), nullptr);
+    HMG_API_END
+}
+int hmg_apply_global(hmg_ctx* c, int level, int x, int y) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    HMG_CHECK(x != y, "apply: x and y must be different vectors");
+    do_apply(c, level, APPLY_AX, 1.0, c->vecp(level, x), c->vecp(level, y), nullptr);
+    do_broadcast(c, level, c->vecp(level, y));
+    HMG_API_END
+}
+int hmg_apply_constraint(hmg_ctx* c, int level, int which) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    check_launch(c, launch_apply_constraint(c->dim, c->level(level).view, c->ne, c->cmask, c->vecp(level, which), c->stream));
+    HMG_API_END
+}
+int hmg_broadcast_interfaces(hmg_ctx* c, int level, int which) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    do_broadcast(c, level, c->vecp(level, which));
+    HMG_API_END
+}
+int hmg_zero_out_all_but_one(hmg_ctx* c, int level, int which) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    check_launch(c, launch_zero_all_but_one(c->dim, c->level(level).view, c->tview, c->vecp(level, which), c->stream));
+    HMG_API_END
+}
+int hmg_local_residual(hmg_ctx* c, int level) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    do_local_residual(c, level);
+    HMG_API_END
+}
+int hmg_restrict(hmg_ctx* c, int k) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    HMG_CHECK(k >= 2 && k <= c->nlevels, "restrict: level must be in 2..nlevels");
+    check_launch(c, launch_restrict(c->dim, c->level(k).view, c->level(k - 1).view, c->ne, c->vecp(k, HMG_R),
+                                    c->vecp(k - 1, HMG_B), c->stream));
+    HMG_API_END
+}
+int hmg_interpolate_add(hmg_ctx* c, int k) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    HMG_CHECK(k >= 2 && k <= c->nlevels, "interpolate: level must be in 2..nlevels");
+    check_launch(c, launch_interp_add(c->dim, c->level(k).view, c->level(k - 1).view, c->ne, c->vecp(k, HMG_X),
+                                      c->vecp(k - 1, HMG_X), c->stream));
+    HMG_API_END
+}
+int hmg_smoothing_steps(hmg_ctx* c, int level, int steps) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    HMG_CHECK(steps >= 0, "negative number of smoothing steps");
+    do_smoothing(c, level, steps);
+    HMG_API_END
+}
+
+int hmg_set_coarse_matrix(hmg_ctx* c, int64_t n, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                          const int64_t* interior_nodes) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    HMG_CHECK(n > 0 && colptr && rowval && nzval && interior_nodes, "bad coarse matrix");
+    HMG_CHECK(n < 46000, "coarse problem too large for the dense coarse solver");
+    std::vector<int64_t> cp(colptr, colptr + n + 1), in0(interior_nodes, interior_nodes + n);
+    for (auto& v : cp) v -= 1;
+    for (auto& v : in0) { v -= 1; HMG_CHECK(v >= 0 && v < c->nn, "interior node out of range"); }
+    std::vector<int64_t> rv(rowval, rowval + cp[n]);
+    for (auto& v : rv) { v -= 1; HMG_CHECK(v >= 0 && v < n, "coarse matrix row out of range"); }
+    std::vector<double> nz(nzval, nzval + cp[n]);
+    set_coarse_dense(c, n, cp, rv, nz, in0);
+    HMG_API_END
+}
+
+int hmg_assemble_coarse(hmg_ctx* c) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    // P1 assembly of lambda*M + K(sigma) on the base mesh, restricted to the interior nodes
+    const int dim = c->dim, nv = dim + 1, cs = dim == 3 ? 8 : 4, nc = dim == 3 ? 7 : 4;
+    std::vector<double> coef((size_t)c->ne * cs);
+    CUDA_OK(cudaMemcpy(coef.data(), c->elem_coef, coef.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    const std::vector<int64_t>& interior = c->topo.interior_nodes;
+    const int64_t n = (int64_t)interior.size();
+    HMG_CHECK(n > 0, "base mesh has no interior nodes");
+    HMG_CHECK(n < 46000, "coarse problem too large for the dense coarse solver");
+    std::vector<int64_t> pos(c->nn, -1);
+    for (int64_t q = 0; q < n; ++q) pos[interior[q]] = q;
+    const double fact = dim == 3 ? 6.0 : 2.0;
+    const double gref[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    std::vector<std::map<int64_t, double>> cols(n);
+    for (int64_t e = 0; e < c->ne; ++e) {
+        const double* ec = &coef[(size_t)e * cs];
+        double P[3][3];
+        int q = 0;
+        for (int k = 0; k < dim; ++k)
+            for (int l = k; l < dim; ++l, ++q) P[k][l] = P[l][k] = ec[q];
+        const double detJ = ec[nc - 1];
+        for (int a = 0; a < nv; ++a) {
+            const int64_t ra = pos[c->elems[e * nv + a]];
+            if (ra < 0) continue;
+            for (int b = 0; b < nv; ++b) {
+                const int64_t rb = pos[c->elems[e * nv + b]];
+                if (rb < 0) continue;
+                double s = 0.0;
+                for (int k = 0; k < dim; ++k)
+                    for (int l = 0; l < dim; ++l) s += gref[a][k] * P[k][l] * gref[b][l];
+                const double mass = detJ * (a == b ? 2.0 : 1.0) / (fact * (dim + 1) * (dim + 2));
+                cols[rb][ra] += s / fact + c->lambda * mass;
+            }
+        }
+    }
+    std::vector<int64_t> cp(n + 1, 0), rv;
+    std::vector<double> nz;
+    for (int64_t j = 0; j < n; ++j) {
+        for (const auto& kv : cols[j]) { rv.push_back(kv.first); nz.push_back(kv.second); }
+        cp[j + 1] = (int64_t)rv.size();
+    }
+    set_coarse_dense(c, n, cp, rv, nz, interior);
+    HMG_API_END
+}
+
+int hmg_copy_to_base(hmg_ctx* c, int which, double* u_host) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    check_launch(c, launch_copy_to_base(c->level(1).view, c->nn, c->node_first, c->vecp(1, which), c->ubase, c->stream));
+    CUDA_OK(cudaMemcpyAsync(u_host, c->ubase, c->nn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    HMG_API_END
+}
+int hmg_distribute(hmg_ctx* c, int which, const double* u_host) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaMemcpyAsync(c->ubase, u_host, c->nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    check_launch(c, launch_distribute(c->dim, c->level(1).view, c->ne, c->elems32, c->ubase, c->vecp(1, which), c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    HMG_API_END
+}
+
+static void vcycle_with_norm(hmg_ctx* c, int top, int steps, bool want_norm, int slot) {
+    do_vcycle(c, top, steps);
+    if (want_norm) {
+        double* r = c->vecp(top, HMG_R);
+        check_launch(c, launch_zero_all_but_one(c->dim, c->level(top).view, c->tview, r, c->stream));
+        check_launch(c, launch_dot(c->red, r, r, c->nstored(top), POST_STORE, slot, c->stream));
+    }
+}
+
+int hmg_vcycle(hmg_ctx* c, int top_level, int steps, double* out_resnorm) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    HMG_CHECK(top_level >= 1 && top_level <= c->nlevels, "level out of range");
+    vcycle_with_norm(c, top_level, steps, out_resnorm != nullptr, S_NRM);
+    if (out_resnorm) *out_resnorm = std::sqrt(read_scalar(c, S_NRM));
+    HMG_API_END
+}
+int hmg_vcycles(hmg_ctx* c, int top_level, int steps, int ncycles, double* resnorms) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    HMG_CHECK(top_level >= 1 && top_level <= c->nlevels, "level out of range");
+    HMG_CHECK(ncycles >= 0, "negative cycle count");
+    double* dn = nullptr;
+    if (resnorms) dn = c->dalloc<double>(ncycles);
+    for (int i = 0; i < ncycles; ++i) {
+        vcycle_with_norm(c, top_level, steps, resnorms != nullptr, S_NRM);
+        if (resnorms)
+            CUDA_OK(cudaMemcpyAsync(dn + i, c->red.scalars + S_NRM, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (resnorms) {
+        CUDA_OK(cudaMemcpyAsync(resnorms, dn, ncycles * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < ncycles; ++i) resnorms[i] = std::sqrt(resnorms[i]);
+        c->dfree(dn);
+    }
+    HMG_API_END
+}
+
+int hmg_rhs_axi_grad(hmg_ctx*, const double*, int) {
+    HMG_API_BEGIN
+    throw Error("hmg: hmg_rhs_axi_grad is not implemented yet");
+    HMG_API_END
+}
+int hmg_integrate_first_term(hmg_ctx*, int, const double*, int64_t, double*) {
+    HMG_API_BEGIN
+    throw Error("hmg: hmg_integrate_first_term is not implemented yet");
+    HMG_API_END
+}
+int hmg_integrate_terms(hmg_ctx*, int, int, int64_t, double*) {
+    HMG_API_BEGIN
+    throw Error("hmg: hmg_integrate_terms is not implemented yet");
+    HMG_API_END
+}
+int hmg_integrate_area(hmg_ctx*, int64_t, double*) {
+    HMG_API_BEGIN
+    throw Error("hmg: hmg_integrate_area is not implemented yet");
+    HMG_API_END
+}
+int hmg_next_rhs(hmg_ctx*, int, int) {
+    HMG_API_BEGIN
+    throw Error("hmg: hmg_next_rhs is not implemented yet");
+    HMG_API_END
+}
+
+int hmg_synchronize(hmg_ctx* c) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    HMG_API_END
+}
+
+int hmg_time_op(hmg_ctx* c, int op, int level, int steps, int reps, float* ms_out) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    HMG_CHECK(reps > 0 && ms_out, "bad arguments");
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; ++i) {
+        if (op == 0) {
+            do_apply(c, level, APPLY_AX, 1.0, c->vecp(level, HMG_P), c->vecp(level, HMG_AP), nullptr);
+            do_broadcast(c, level, c->vecp(level, HMG_AP));
+        } else if (op == 1) {
+            do_vcycle(c, level, steps);
+        } else if (op == 2) {
+            do_apply(c, level, APPLY_MULADD, 1.0, c->vecp(level, HMG_P), c->vecp(level, HMG_AP), nullptr);
+        } else if (op == 3) {
+            do_apply(c, level, APPLY_AX, 1.0, c->vecp(level, HMG_P), c->vecp(level, HMG_AP), nullptr);
+        } else if (op == 4) {
+            do_broadcast(c, level, c->vecp(level, HMG_AP));
+        } else {
+            throw Error("hmg: unknown op for hmg_time_op");
+        }
+    }
+    CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+    CUDA_OK(cudaEventSynchronize(c->ev1));
+    CUDA_OK(cudaEventElapsedTime(ms_out, c->ev0, c->ev1));
+    HMG_API_END
+}
+
+int64_t hmg_launch_count(const hmg_ctx* c) { return c ? c->launches : -1; }
+void* hmg_device_ptr(hmg_ctx* c, int level, int which) {
+    try {
+        if (!c) return nullptr;
+        cudaSetDevice(c->device);
+        return c->vecp(level, which);
+    } catch (const std::exception& ex) {
+        g_err = ex.what();
+        return nullptr;
+    }
+}
+int hmg_hier_to_lattice(const hmg_ctx* c, int level, int32_t* out) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    HMG_CHECK(level >= 1 && level <= c->nlevels && out, "bad arguments");
+    const auto& h = c->ref.lv[level - 1].hier2lat;
+    std::copy(h.begin(), h.end(), out);
+    HMG_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+// Host-side setup structures of libhmg_b200 (plain C++17, no CUDA types).
+//
+// The reference builds, per level, dim^2 sparse matrices ops[k,l] and a mass matrix on the
+// refined reference simplex (src/build_local_operators.jl:51-141) in a *hierarchical* node
+// order (src/multilevel_reference.jl:41-61).  This library never stores those matrices: the
+// refined reference simplex is a uniform simplicial lattice, so the operator of one coarse
+// element is a constant-coefficient stencil (15-point in 3D, 7-point in 2D) whose truncation
+// on the simplex boundary depends only on WHICH reference faces a node lies on (its "class").
+// Everything here is integer-exact; the structural assumptions are verified at setup and the
+// library refuses to run if one does not hold.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace hmg {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+#define HMG_CHECK(cond, msg)                                                      \
+    do {                                                                          \
+        if (!(cond)) throw ::hmg::Error(std::string("hmg: ") + (msg) + " [" #cond "]"); \
+    } while (0)
+
+// ---- lattice helpers -----------------------------------------------------------------
+inline int tri(int q) { return (q + 1) * (q + 2) / 2; }            // #points of a 2-simplex lattice
+inline int tot3(int q) { return (q + 1) * (q + 2) * (q + 3) / 6; } // #points of a 3-simplex lattice
+// packed (lexicographic, last coordinate fastest) index of a lattice point
+inline int pack2(int m, int i, int j) { return tri(m) - tri(m - i) + j; }
+inline int pack3(int m, int i, int j, int k) {
+    int n1 = m - i;
+    return tot3(m) - tot3(n1) + tri(n1) - tri(n1 - j) + k;
+}
+
+// stencil directions (index 0 = centre); the set is verified against the assembled stencil
+constexpr int NDIR3 = 15, NDIR2 = 7;
+extern const int DIRS3[NDIR3][3];
+extern const int DIRS2[NDIR2][2];
+// symmetric tensor components: 3D (00,01,02,11,12,22) + mass = 7; 2D (00,01,11) + mass = 4
+constexpr int NC3 = 7, NC2 = 4;
+constexpr int NCLS3 = 16, NCLS2 = 8;   // class = bitmask of reference faces the node lies on
+
+struct RefLevel {
+    int m = 0;     // lattice size 2^(level-1)
+    int nf = 0;    // nodes of the refined reference element
+    int ld = 0;    // padded leading dimension on the device
+    std::vector<int32_t> hier2lat;   // hierarchical row -> packed lattice index
+    std::vector<uint32_t> nodeinfo;  // per packed index: i | j<<8 | k<<16 | class<<24
+    std::vector<uint32_t> interior;  // interior nodes (class 0), packed p | i<<14 | j<<22
+    std::vector<uint32_t> boundary;  // boundary nodes sorted by class, p | class<<14 ; (i,j,k) via nodeinfo
+    std::vector<double> G;           // [ncls][ndir][nc] stencil table, scale factors folded in
+    std::vector<uint16_t> face_bary; // 3D: interior nodes of a face, barycentric a | b<<8
+    double mass_total = 0.0;         // sum of all entries of the reference mass matrix
+};
+
+struct RefElement {
+    int dim = 0, nlevels = 0;
+    int ndir = 0, nc = 0, ncls = 0;
+    std::vector<RefLevel> lv;        // lv[l-1] = level l
+};
+
+RefElement build_reference(int dim, int nlevels);
+
+// ---- base-mesh topology ---------------------------------------------------------------
+struct CellMap {                     // CSR cell -> (element, local id), owners ascending
+    std::vector<int64_t> offset;     // ncells + 1
+    std::vector<int32_t> owner;      // element * 8 + local id
+    std::vector<int64_t> cell_key;   // first global vertex id of the cell (diagnostics / partition)
+    int64_t ncells() const { return offset.empty() ? 0 : (int64_t)offset.size() - 1; }
+};
+
+struct Topology {
+    int dim = 0;
+    int64_t ne = 0, nn = 0;
+    CellMap faces, edges, verts;         // interface cells (>= 2 owners), src/interface.jl:65-117
+    std::vector<int32_t> node_first;     // per base node: first owner (element*8+local), -1 if unused
+    std::vector<int64_t> nodeown_off;    // all_nodes CSR (src/interface.jl:82-88)
+    std::vector<int32_t> nodeown;
+    std::vector<uint16_t> cmask;         // per element: bit c set <=> class c is on the domain boundary
+    std::vector<uint8_t> node_boundary;  // per base node: 1 if on the domain boundary
+    std::vector<int64_t> interior_nodes; // complement (sorted), src/grid.jl:176-202
+    // cut cells (multi-GPU): filled by the partitioner
+};
+
+// elems: (dim+1) x ne, 0-based, sorted per element
+Topology build_topology(int dim, int64_t ne, int64_t nn, const int64_t* elems);
+
+// class bitmask of the reference-face set containing a local cell
+int class_of_face(int lf);              // 3D face 0..3
+int class_of_edge(int dim, int le);     // edge local id
+int class_of_vertex(int dim, int lv);
+
+// per element geometry: coef[e][c] = |J| * P_c (c < nc-1), coef[e][nc-1] = |J| with
+// P = J^-1 diag(sigma) J^-T (src/apply_local_operators.jl:101-105, src/cell_values.jl:104-127)
+void element_coefficients(int dim, int64_t ne, const double* nodes /*dim x nn*/,
+                          const int64_t* elems /*0-based*/, const double* sigma /*dim x ne*/,
+                          std::vector<double>& coef /*ne x stride*/, int stride);
+
+}  // namespace hmg

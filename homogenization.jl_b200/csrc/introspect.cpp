@@ -1,0 +1,187 @@
+// Host-only verification entry points (no GPU needed, nothing here computes on behalf of the
+// product path).  They expose the tables the kernels consume, expanded through the SAME index
+// functions the kernels use (lattice.hpp), so that the CPU test-suite can compare them with the
+// oracle's explicit sparse operators and interface maps.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hmg.h"
+#include "hmg_host.hpp"
+#include "lattice.hpp"
+
+using namespace hmg;
+
+namespace {
+thread_local std::string g_host_err;
+const RefLevel& get_level(const RefElement& ref, int level) {
+    HMG_CHECK(level >= 1 && level <= ref.nlevels, "level out of range");
+    return ref.lv[level - 1];
+}
+template <int DIM>
+void local_matrix_t(const RefElement& ref, const RefLevel& L, const double* coef, double* dense) {
+    using D = Dims<DIM>;
+    const int nf = L.nf;
+    std::vector<int> l2h(nf);
+    for (int h = 0; h < nf; ++h) l2h[L.hier2lat[h]] = h;
+    std::memset(dense, 0, sizeof(double) * nf * nf);
+    for (int p = 0; p < nf; ++p) {
+        const uint32_t info = L.nodeinfo[p];
+        const int i = info & 255, j = (info >> 8) & 255, k = (info >> 16) & 255, cls = info >> 24;
+        int off[D::NDIR];
+        neighbour_offsets<DIM>(L.m, i, j, off);
+        for (int d = 0; d < D::NDIR; ++d) {
+            if (!neighbour_inside<DIM>(L.m, i, j, k, d)) continue;
+            double s = 0.0;
+            for (int c = 0; c < D::NC; ++c) s += coef[c] * L.G[((size_t)cls * D::NDIR + d) * D::NC + c];
+            const int q = p + off[d];
+            HMG_CHECK(q >= 0 && q < nf, "neighbour offset leaves the element");
+            dense[(size_t)l2h[q] * nf + l2h[p]] = s;   // column-major, row = p, col = q
+        }
+    }
+    (void)ref;
+}
+template <int DIM>
+void transfer_matrix_t(const RefLevel& Lf, const RefLevel& Lc, double* dense) {
+    std::vector<int> l2h_f(Lf.nf), l2h_c(Lc.nf);
+    for (int h = 0; h < Lf.nf; ++h) l2h_f[Lf.hier2lat[h]] = h;
+    for (int h = 0; h < Lc.nf; ++h) l2h_c[Lc.hier2lat[h]] = h;
+    std::memset(dense, 0, sizeof(double) * Lf.nf * Lc.nf);
+    for (int p = 0; p < Lf.nf; ++p) {
+        const uint32_t info = Lf.nodeinfo[p];
+        const int i = info & 255, j = (info >> 8) & 255, k = (info >> 16) & 255;
+        int pa, pb;
+        const int n = interp_parents<DIM>(Lc.m, i, j, k, pa, pb);
+        if (n == 1) dense[(size_t)l2h_c[pa] * Lf.nf + l2h_f[p]] = 1.0;
+        else {
+            dense[(size_t)l2h_c[pa] * Lf.nf + l2h_f[p]] += 0.5;
+            dense[(size_t)l2h_c[pb] * Lf.nf + l2h_f[p]] += 0.5;
+        }
+    }
+}
+}  // namespace
+
+#define HOST_BEGIN try {
+#define HOST_END                                     \
+    return 0;                                        \
+    }                                                \
+    catch (const std::exception& ex) {               \
+        g_host_err = ex.what();                      \
+        return 1;                                    \
+    }
+
+extern "C" {
+
+const char* hmg_host_last_error(void) { return g_host_err.c_str(); }
+
+// sizes[8] = m, nf, ld, n_interior, n_boundary, npf, ndir, nc ; hier2lat[nf] / G[ncls*ndir*nc] may be NULL
+int hmg_host_reference(int dim, int nlevels, int level, int64_t* sizes, int32_t* hier2lat, double* G,
+                       double* mass_total) {
+    HOST_BEGIN
+    RefElement ref = build_reference(dim, nlevels);
+    const RefLevel& L = get_level(ref, level);
+    if (sizes) {
+        sizes[0] = L.m; sizes[1] = L.nf; sizes[2] = L.ld; sizes[3] = (int64_t)L.interior.size();
+        sizes[4] = (int64_t)L.boundary.size(); sizes[5] = (int64_t)L.face_bary.size();
+        sizes[6] = ref.ndir; sizes[7] = ref.nc;
+    }
+    if (hier2lat) std::copy(L.hier2lat.begin(), L.hier2lat.end(), hier2lat);
+    if (G) std::copy(L.G.begin(), L.G.end(), G);
+    if (mass_total) *mass_total = L.mass_total;
+    HOST_END
+}
+
+// dense nf x nf (column-major, hierarchical order) matrix of  sum_c coef[c] * (stencil table c)
+int hmg_host_local_matrix(int dim, int nlevels, int level, const double* coef, double* dense) {
+    HOST_BEGIN
+    RefElement ref = build_reference(dim, nlevels);
+    const RefLevel& L = get_level(ref, level);
+    if (dim == 3) local_matrix_t<3>(ref, L, coef, dense);
+    else local_matrix_t<2>(ref, L, coef, dense);
+    HOST_END
+}
+
+// dense nf(level) x nf(level-1) interpolation matrix, hierarchical order, column-major
+int hmg_host_transfer_matrix(int dim, int nlevels, int level_fine, double* dense) {
+    HOST_BEGIN
+    RefElement ref = build_reference(dim, nlevels);
+    HMG_CHECK(level_fine >= 2, "level_fine must be >= 2");
+    const RefLevel& Lf = get_level(ref, level_fine);
+    const RefLevel& Lc = get_level(ref, level_fine - 1);
+    if (dim == 3) transfer_matrix_t<3>(Lf, Lc, dense);
+    else transfer_matrix_t<2>(Lf, Lc, dense);
+    HOST_END
+}
+
+// hierarchical row of the q-th paired node of a local face (kind 0) / edge (1) / vertex (2)
+int hmg_host_interface_rows(int dim, int nlevels, int level, int kind, int lid, int32_t* rows, int64_t* count) {
+    HOST_BEGIN
+    RefElement ref = build_reference(dim, nlevels);
+    const RefLevel& L = get_level(ref, level);
+    std::vector<int> l2h(L.nf);
+    for (int h = 0; h < L.nf; ++h) l2h[L.hier2lat[h]] = h;
+    const int n = kind == 0 ? (int)L.face_bary.size() : kind == 1 ? L.m - 1 : 1;
+    if (count) *count = n;
+    if (rows)
+        for (int t = 0; t < n; ++t) {
+            const unsigned ab = kind == 0 ? L.face_bary[t] : 0;
+            const int q = kind == 1 ? t + 1 : 0;
+            const int p = dim == 3 ? interface_node<3>(L.m, kind, lid, q, ab) : interface_node<2>(L.m, kind, lid, q, ab);
+            rows[t] = l2h[p];
+        }
+    HOST_END
+}
+
+// kind 0 faces, 1 edges, 2 interface vertices, 3 all nodes.  Two-pass: arrays may be NULL.
+int hmg_host_topology(int dim, int64_t ne, int64_t nn, const int64_t* elems1, int kind, int64_t* ncells,
+                      int64_t* nentries, int64_t* offset, int64_t* element, int64_t* local_id) {
+    HOST_BEGIN
+    std::vector<int64_t> el((size_t)ne * (dim + 1));
+    for (size_t q = 0; q < el.size(); ++q) el[q] = elems1[q] - 1;
+    Topology T = build_topology(dim, ne, nn, el.data());
+    const std::vector<int64_t>* off;
+    const std::vector<int32_t>* own;
+    if (kind == 3) { off = &T.nodeown_off; own = &T.nodeown; }
+    else {
+        const CellMap& m = kind == 0 ? T.faces : kind == 1 ? T.edges : T.verts;
+        off = &m.offset; own = &m.owner;
+    }
+    if (ncells) *ncells = off->empty() ? 0 : (int64_t)off->size() - 1;
+    if (nentries) *nentries = (int64_t)own->size();
+    if (offset) std::copy(off->begin(), off->end(), offset);
+    if (element) for (size_t q = 0; q < own->size(); ++q) element[q] = (*own)[q] >> 3;
+    if (local_id) for (size_t q = 0; q < own->size(); ++q) local_id[q] = (*own)[q] & 7;
+    HOST_END
+}
+
+// cmask[ne] (bit c set <=> node class c of that element lies on the domain boundary),
+// interior[nn] flags (1 = interior node)
+int hmg_host_boundary(int dim, int64_t ne, int64_t nn, const int64_t* elems1, uint16_t* cmask, uint8_t* interior) {
+    HOST_BEGIN
+    std::vector<int64_t> el((size_t)ne * (dim + 1));
+    for (size_t q = 0; q < el.size(); ++q) el[q] = elems1[q] - 1;
+    Topology T = build_topology(dim, ne, nn, el.data());
+    if (cmask) std::copy(T.cmask.begin(), T.cmask.end(), cmask);
+    if (interior) for (int64_t n = 0; n < nn; ++n) interior[n] = T.node_boundary[n] ? 0 : 1;
+    HOST_END
+}
+
+// class bitmask of a local face / edge / vertex
+int hmg_host_class_of(int dim, int kind, int lid) {
+    return kind == 0 ? class_of_face(lid) : kind == 1 ? class_of_edge(dim, lid) : class_of_vertex(dim, lid);
+}
+
+// coef[ne][stride] = |J| P (symmetric components) , |J|
+int hmg_host_element_coefficients(int dim, int64_t ne, int64_t nn, const double* nodes, const int64_t* elems1,
+                                  const double* sigma, double* coef, int stride) {
+    HOST_BEGIN
+    (void)nn;
+    std::vector<int64_t> el((size_t)ne * (dim + 1));
+    for (size_t q = 0; q < el.size(); ++q) el[q] = elems1[q] - 1;
+    std::vector<double> c;
+    element_coefficients(dim, ne, nodes, el.data(), sigma, c, stride);
+    std::copy(c.begin(), c.end(), coef);
+    HOST_END
+}
+
+}  // extern "C"

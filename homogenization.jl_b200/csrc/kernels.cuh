@@ -1,0 +1,73 @@
+// Device-side parameter blocks and launcher declarations of libhmg_b200 (sm_100a only).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace hmg {
+
+// ---- per-level device view -------------------------------------------------------------
+struct LevelView {
+    int m, nf, ld;
+    int n_interior, n_boundary, npf, npe;
+    const uint32_t* nodeinfo;   // [nf]   i | j<<8 | k<<16 | class<<24   (lattice order)
+    const uint32_t* interior;   // [n_interior] p | i<<14 | j<<22
+    const uint32_t* boundary;   // [n_boundary] p | class<<14   (sorted by class)
+    const double* G;            // [ncls][ndir][nc]
+    const uint16_t* face_bary;  // [npf] a | b<<8
+    int vpos[4];                // packed lattice index of the reference vertices
+};
+
+struct TopoView {
+    int64_t nfaces, nedges, nverts;
+    const int64_t *face_off, *edge_off, *vert_off;
+    const int32_t *face_own, *edge_own, *vert_own;   // element*8 + local id
+};
+
+enum ApplyMode { APPLY_AX = 0, APPLY_RESIDUAL = 1, APPLY_MULADD = 2 };
+
+struct ApplyArgs {
+    LevelView L;
+    int64_t ne;
+    const double* elem_coef;   // [ne][CS]
+    const uint16_t* cmask;     // [ne]
+    const double* x;           // input  (ld x ne)
+    double* y;                 // output
+    const double* b;           // rhs for APPLY_RESIDUAL
+    double alpha, lambda;
+    int mode;
+};
+
+// scalar slots on the device (no host round trip inside a V-cycle)
+enum Scalar { S_RHO = 0, S_PAP = 1, S_ALPHA = 2, S_RSQR = 3, S_BETA = 4, S_TMP = 5, S_NRM = 6, S_COUNT = 16 };
+enum PostOp { POST_STORE = 0, POST_RHO = 1, POST_PAP = 2, POST_RSQR = 3 };
+
+struct Reducer {
+    double* partials;     // [max_blocks]
+    double* scalars;      // [S_COUNT]
+    unsigned int* ticket; // last-block-done counter (self-resetting)
+    int max_blocks;
+};
+
+// launchers (all asynchronous on `st`); return the number of kernels launched
+int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st);
+int launch_interface_sum(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
+int launch_zero_all_but_one(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
+int launch_apply_constraint(int dim, const LevelView& L, int64_t ne, const uint16_t* cmask, double* x, cudaStream_t st);
+int launch_restrict(int dim, const LevelView& Lf, const LevelView& Lc, int64_t ne, const double* rf, double* bc, cudaStream_t st);
+int launch_interp_add(int dim, const LevelView& Lf, const LevelView& Lc, int64_t ne, double* xf, const double* xc, cudaStream_t st);
+int launch_dot(const Reducer& R, const double* a, const double* b, int64_t n, int post, int slot, cudaStream_t st);
+int launch_cg_update(const Reducer& R, double* x, const double* p, double* r, const double* Ap, int64_t n, cudaStream_t st);
+int launch_p_update(const Reducer& R, double* p, const double* r, int64_t n, cudaStream_t st);
+int launch_axpy(double alpha, const double* x, double* y, int64_t n, cudaStream_t st);
+int launch_fill(double* x, double v, int64_t n, cudaStream_t st);
+int launch_permute_in(const LevelView& L, const int32_t* hier2lat, const double* staged, int64_t ld_staged, double* dst, int64_t ncols, cudaStream_t st);
+int launch_permute_out(const LevelView& L, const int32_t* hier2lat, const double* src, double* staged, int64_t ld_staged, int64_t ncols, cudaStream_t st);
+// level 1 <-> base vector
+int launch_copy_to_base(const LevelView& L1, int64_t nn, const int32_t* node_first, const double* v, double* u, cudaStream_t st);
+int launch_distribute(int dim, const LevelView& L1, int64_t ne, const int32_t* elems, const double* u, double* v, cudaStream_t st);
+int launch_gather(const int64_t* idx, int64_t n, const double* src, double* dst, cudaStream_t st);
+int launch_scatter(const int64_t* idx, int64_t n, const double* src, double* dst, cudaStream_t st);
+int launch_symmetrize_lower(double* A, int64_t n, cudaStream_t st);
+int launch_symv_full(const double* A, int64_t n, const double* x, double* y, cudaStream_t st);
+
+}  // namespace hmg

@@ -1,0 +1,125 @@
+// Lattice index arithmetic shared by the kernels and the host-side verification code.
+//
+// The refined reference simplex of level l is the set of integer points (i, j[, k]) >= 0 with
+// i + j [+ k] <= m, m = 2^(l-1) (reference vertex 1 = origin, vertex 2 = m e_1, ...).  Nodes are
+// stored in lexicographic order, last coordinate fastest ("packed" index).  The operator couples a
+// node with its neighbours along 7 (3D) / 3 (2D) lattice directions and their opposites.
+#pragma once
+#ifdef __CUDACC__
+#define HMG_HD __host__ __device__ __forceinline__
+#else
+#define HMG_HD inline
+#endif
+
+namespace hmg {
+
+HMG_HD int lat_tri(int q) { return (q + 1) * (q + 2) / 2; }
+HMG_HD int lat_tot3(int q) { return (q + 1) * (q + 2) * (q + 3) / 6; }
+HMG_HD int lat_pack2(int m, int i, int j) { return lat_tri(m) - lat_tri(m - i) + j; }
+HMG_HD int lat_pack3(int m, int i, int j, int k) {
+    const int n1 = m - i;
+    return lat_tot3(m) - lat_tot3(n1) + lat_tri(n1) - lat_tri(n1 - j) + k;
+}
+
+template <int DIM> struct Dims;
+template <> struct Dims<3> { static constexpr int NDIR = 15, NC = 7, NCLS = 16, CS = 8; };
+template <> struct Dims<2> { static constexpr int NDIR = 7, NC = 4, NCLS = 8, CS = 4; };
+
+// direction d of the stencil (0 = centre); must match DIRS3 / DIRS2 of reference.cpp
+HMG_HD void lat_dir3(int d, int& di, int& dj, int& dk) {
+    // packed as 2-bit fields (value + 1) to stay in registers / immediates
+    const int I[15] = {0, 1, -1, 0, 0, 0, 0, -1, 1, -1, 1, 0, 0, 1, -1};
+    const int J[15] = {0, 0, 0, 1, -1, 0, 0, 1, -1, 0, 0, -1, 1, -1, 1};
+    const int K[15] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 1, -1};
+    di = I[d]; dj = J[d]; dk = K[d];
+}
+HMG_HD void lat_dir2(int d, int& di, int& dj) {
+    const int I[7] = {0, 1, -1, 0, 0, -1, 1};
+    const int J[7] = {0, 0, 0, 1, -1, 1, -1};
+    di = I[d]; dj = J[d];
+}
+
+// packed-index offsets of the stencil neighbours of node (i, j, *) at lattice size m
+template <int DIM> HMG_HD void neighbour_offsets(int m, int i, int j, int* off);
+template <> HMG_HD void neighbour_offsets<3>(int m, int i, int j, int* off) {
+    const int n1 = m - i;
+    const int A = n1 - j + 1;                       // length of row (i, j)
+    const int U = (n1 + 1) * (n1 + 2) / 2 - j;      // (i+1, j, k) - (i, j, k)
+    const int V = U + n1 + 2;                       // (i, j, k) - (i-1, j, k)
+    off[0] = 0;           off[1] = U;       off[2] = -V;
+    off[3] = A;           off[4] = -(A + 1); off[5] = 1;       off[6] = -1;
+    off[7] = A + 1 - V;   off[8] = U - A;   off[9] = 1 - V;   off[10] = U - 1;
+    off[11] = -A;         off[12] = A - 1;  off[13] = U - A + 1; off[14] = A - V;
+}
+template <> HMG_HD void neighbour_offsets<2>(int m, int i, int, int* off) {
+    const int B = m - i + 1;                        // length of row i
+    off[0] = 0; off[1] = B; off[2] = -(B + 1); off[3] = 1; off[4] = -1; off[5] = -B; off[6] = B - 1;
+}
+
+template <int DIM> HMG_HD bool neighbour_inside(int m, int i, int j, int k, int d) {
+    int di, dj, dk = 0;
+    if (DIM == 3) lat_dir3(d, di, dj, dk); else lat_dir2(d, di, dj);
+    const int ni = i + di, nj = j + dj, nk = k + dk;
+    return ni >= 0 && nj >= 0 && nk >= 0 && ni + nj + nk <= m;
+}
+
+// local vertex ids of the reference faces / edges (src/grid.jl:89-91, 0-based)
+HMG_HD void face_vertices(int lf, int* v) {
+    const int F[4][3] = {{0, 1, 2}, {0, 1, 3}, {0, 2, 3}, {1, 2, 3}};
+    v[0] = F[lf][0]; v[1] = F[lf][1]; v[2] = F[lf][2];
+}
+template <int DIM> HMG_HD void edge_vertices(int le, int* v) {
+    const int E3[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+    const int E2[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+    v[0] = DIM == 3 ? E3[le][0] : E2[le][0];
+    v[1] = DIM == 3 ? E3[le][1] : E2[le][1];
+}
+
+// packed index of the node with barycentric weights w[0..n) on the local vertices lv[0..n)
+template <int DIM> HMG_HD int bary_to_packed(int m, const int* lv, const int* w, int n) {
+    int lam[4] = {0, 0, 0, 0};
+    for (int q = 0; q < 3; ++q)
+        if (q < n) lam[lv[q]] = w[q];
+    return DIM == 3 ? lat_pack3(m, lam[1], lam[2], lam[3]) : lat_pack2(m, lam[1], lam[2]);
+}
+
+// kind 0 = face (q indexes face_bary: a | b<<8), 1 = edge (q = weight on the 2nd vertex), 2 = vertex
+template <int DIM> HMG_HD int interface_node(int m, int kind, int lid, int q, unsigned ab) {
+    int lv[3] = {0, 0, 0}, w[3] = {0, 0, 0}, n;
+    if (kind == 0) {
+        face_vertices(lid, lv);
+        w[0] = ab & 255; w[1] = ab >> 8; w[2] = m - w[0] - w[1]; n = 3;
+    } else if (kind == 1) {
+        edge_vertices<DIM>(lid, lv);
+        w[0] = m - q; w[1] = q; n = 2;
+    } else {
+        lv[0] = lid; w[0] = m; n = 1;
+    }
+    return bary_to_packed<DIM>(m, lv, w, n);
+}
+
+// interpolation parents of fine node (i, j, k): returns 1 (coincides with a coarse node) or 2
+// (midpoint of two coarse nodes, weights 1/2); pa/pb are packed indices on the coarse lattice mc.
+// The parity -> direction table is verified against the edge graph in reference.cpp.
+template <int DIM> HMG_HD int interp_parents(int mc, int i, int j, int k, int& pa, int& pb) {
+    if (DIM == 3) {
+        const int par = (i & 1) * 4 + (j & 1) * 2 + (k & 1);
+        if (par == 0) { pa = pb = lat_pack3(mc, i >> 1, j >> 1, k >> 1); return 1; }
+        const int dtab[8] = {0, 5, 3, 11, 1, 9, 7, 13};
+        int di, dj, dk;
+        lat_dir3(dtab[par], di, dj, dk);
+        pa = lat_pack3(mc, (i + di) >> 1, (j + dj) >> 1, (k + dk) >> 1);
+        pb = lat_pack3(mc, (i - di) >> 1, (j - dj) >> 1, (k - dk) >> 1);
+        return 2;
+    }
+    const int par = (i & 1) * 2 + (j & 1);
+    if (par == 0) { pa = pb = lat_pack2(mc, i >> 1, j >> 1); return 1; }
+    const int dtab[4] = {0, 3, 1, 5};
+    int di, dj;
+    lat_dir2(dtab[par], di, dj);
+    pa = lat_pack2(mc, (i + di) >> 1, (j + dj) >> 1);
+    pb = lat_pack2(mc, (i - di) >> 1, (j - dj) >> 1);
+    return 2;
+}
+
+}  // namespace hmg

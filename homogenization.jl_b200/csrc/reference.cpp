@@ -1,0 +1,333 @@
+// Refined reference simplex: hierarchical numbering -> lattice numbering, stencil tables.
+//
+// What the reference does (cited, not copied): refined_element() repeatedly applies red (2D) /
+// Bey (3D) refinement to the reference simplex and appends one midpoint node per edge in
+// edge-graph order (src/multilevel_reference.jl:41-61, src/sparse_graph.jl:20-48,
+// src/tri/refine.jl:5-43, src/tet/refine.jl:5-54); the local operators are assembled on those
+// meshes (src/build_local_operators.jl:51-141).  Here the same refinement is run in exact integer
+// lattice coordinates, only to (1) learn the hierarchical->lattice permutation, (2) assemble the
+// per-class integer stencil tables, (3) verify the structural facts the kernels rely on.
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdlib>
+#include <numeric>
+
+#include "hmg_host.hpp"
+
+namespace hmg {
+
+const int DIRS3[NDIR3][3] = {{0, 0, 0},  {1, 0, 0},  {-1, 0, 0}, {0, 1, 0},  {0, -1, 0},
+                             {0, 0, 1},  {0, 0, -1}, {-1, 1, 0}, {1, -1, 0}, {-1, 0, 1},
+                             {1, 0, -1}, {0, -1, 1}, {0, 1, -1}, {1, -1, 1}, {-1, 1, -1}};
+const int DIRS2[NDIR2][2] = {{0, 0}, {1, 0}, {-1, 0}, {0, 1}, {0, -1}, {-1, 1}, {1, -1}};
+
+namespace {
+
+using I3 = std::array<int, 3>;
+using I4 = std::array<int, 4>;
+
+struct IntMesh {
+    std::vector<I3> nodes;   // integer coordinates scaled by M = 2^(nlevels-1); z = 0 in 2D
+    std::vector<I4> elems;   // vertex ids (4th unused in 2D)
+};
+
+struct Edges {               // sorted unique (from < to) pairs; index = midpoint numbering
+    std::vector<std::pair<int, int>> e;
+    int index(int a, int b) const {
+        if (a > b) std::swap(a, b);
+        auto it = std::lower_bound(e.begin(), e.end(), std::make_pair(a, b));
+        HMG_CHECK(it != e.end() && *it == std::make_pair(a, b), "edge not found in edge graph");
+        return (int)(it - e.begin());
+    }
+};
+
+Edges edge_graph(const IntMesh& mesh, int nv) {
+    Edges g;
+    g.e.reserve(mesh.elems.size() * 6);
+    for (const auto& el : mesh.elems)
+        for (int i = 0; i < nv; ++i)
+            for (int j = i + 1; j < nv; ++j)
+                g.e.emplace_back(std::min(el[i], el[j]), std::max(el[i], el[j]));
+    std::sort(g.e.begin(), g.e.end());
+    g.e.erase(std::unique(g.e.begin(), g.e.end()), g.e.end());
+    return g;
+}
+
+IntMesh refine(const IntMesh& mesh, const Edges& g, int dim) {
+    IntMesh out;
+    const int nn = (int)mesh.nodes.size();
+    out.nodes = mesh.nodes;
+    out.nodes.reserve(nn + g.e.size());
+    for (const auto& pr : g.e) {
+        const I3 &a = mesh.nodes[pr.first], &b = mesh.nodes[pr.second];
+        I3 mid;
+        for (int d = 0; d < 3; ++d) {
+            HMG_CHECK(((a[d] + b[d]) & 1) == 0, "midpoint is not a lattice point");
+            mid[d] = (a[d] + b[d]) / 2;
+        }
+        out.nodes.push_back(mid);
+    }
+    if (dim == 2) {
+        out.elems.reserve(mesh.elems.size() * 4);
+        for (const auto& t : mesh.elems) {
+            int a = g.index(t[0], t[1]) + nn, b = g.index(t[0], t[2]) + nn, c = g.index(t[1], t[2]) + nn;
+            int kids[4][3] = {{t[0], a, b}, {t[1], c, a}, {t[2], b, c}, {a, c, b}};
+            for (auto& k : kids) {
+                std::sort(k, k + 3);            // children are index-sorted on creation (2D only)
+                out.elems.push_back({k[0], k[1], k[2], -1});
+            }
+        }
+    } else {
+        static const int bey[8][4] = {{0, 4, 5, 6}, {4, 1, 7, 8}, {5, 7, 2, 9}, {6, 8, 9, 3},
+                                      {4, 5, 6, 8}, {4, 5, 7, 8}, {5, 6, 8, 9}, {5, 7, 8, 9}};
+        out.elems.reserve(mesh.elems.size() * 8);
+        for (const auto& t : mesh.elems) {
+            int parts[10] = {t[0], t[1], t[2], t[3]};
+            int idx = 4;
+            for (int i = 0; i < 4; ++i)
+                for (int j = i + 1; j < 4; ++j) parts[idx++] = g.index(t[i], t[j]) + nn;
+            for (const auto& q : bey) out.elems.push_back({parts[q[0]], parts[q[1]], parts[q[2]], parts[q[3]]});
+        }
+    }
+    return out;
+}
+
+int dir_index(int dim, int di, int dj, int dk) {
+    if (dim == 3) {
+        for (int d = 0; d < NDIR3; ++d)
+            if (DIRS3[d][0] == di && DIRS3[d][1] == dj && DIRS3[d][2] == dk) return d;
+    } else {
+        for (int d = 0; d < NDIR2; ++d)
+            if (DIRS2[d][0] == di && DIRS2[d][1] == dj && dk == 0) return d;
+    }
+    return -1;
+}
+
+int node_class(int dim, int m, int i, int j, int k) {
+    if (dim == 3) return (k == 0 ? 1 : 0) | (j == 0 ? 2 : 0) | (i == 0 ? 4 : 0) | (i + j + k == m ? 8 : 0);
+    return (j == 0 ? 1 : 0) | (i == 0 ? 2 : 0) | (i + j == m ? 4 : 0);
+}
+
+// gradient (in lattice units) of the barycentric coordinates of a unimodular lattice simplex
+void lattice_gradients(int dim, const I3* v, int g[4][3]) {
+    long E[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 1}};
+    for (int c = 0; c < dim; ++c)
+        for (int r = 0; r < dim; ++r) E[r][c] = v[c + 1][r] - v[0][r];
+    long inv[3][3];
+    long det;
+    if (dim == 2) {
+        det = E[0][0] * E[1][1] - E[0][1] * E[1][0];
+        inv[0][0] = E[1][1]; inv[0][1] = -E[0][1];
+        inv[1][0] = -E[1][0]; inv[1][1] = E[0][0];
+    } else {
+        det = E[0][0] * (E[1][1] * E[2][2] - E[1][2] * E[2][1]) -
+              E[0][1] * (E[1][0] * E[2][2] - E[1][2] * E[2][0]) +
+              E[0][2] * (E[1][0] * E[2][1] - E[1][1] * E[2][0]);
+        inv[0][0] = E[1][1] * E[2][2] - E[1][2] * E[2][1];
+        inv[0][1] = E[0][2] * E[2][1] - E[0][1] * E[2][2];
+        inv[0][2] = E[0][1] * E[1][2] - E[0][2] * E[1][1];
+        inv[1][0] = E[1][2] * E[2][0] - E[1][0] * E[2][2];
+        inv[1][1] = E[0][0] * E[2][2] - E[0][2] * E[2][0];
+        inv[1][2] = E[0][2] * E[1][0] - E[0][0] * E[1][2];
+        inv[2][0] = E[1][0] * E[2][1] - E[1][1] * E[2][0];
+        inv[2][1] = E[0][1] * E[2][0] - E[0][0] * E[2][1];
+        inv[2][2] = E[0][0] * E[1][1] - E[0][1] * E[1][0];
+    }
+    HMG_CHECK(det == 1 || det == -1, "fine element is not a unimodular lattice simplex");
+    for (int d = 0; d < 3; ++d) g[0][d] = 0;
+    for (int a = 1; a <= dim; ++a)
+        for (int d = 0; d < dim; ++d) {
+            g[a][d] = (int)(inv[a - 1][d] * det);   // divide by det = multiply by det (det = +-1)
+            g[0][d] -= g[a][d];
+        }
+    for (int a = 0; a <= dim; ++a)
+        for (int d = dim; d < 3; ++d) g[a][d] = 0;
+}
+
+}  // namespace
+
+RefElement build_reference(int dim, int nlevels) {
+    HMG_CHECK(dim == 2 || dim == 3, "dim must be 2 or 3");
+    HMG_CHECK(nlevels >= 1, "need at least one level");
+    HMG_CHECK(dim == 3 ? nlevels <= 6 : nlevels <= 8,
+              "too many levels: at most 6 (3D) / 8 (2D) grids are supported");
+    RefElement ref;
+    ref.dim = dim;
+    ref.nlevels = nlevels;
+    ref.ndir = dim == 3 ? NDIR3 : NDIR2;
+    ref.nc = dim == 3 ? NC3 : NC2;
+    ref.ncls = dim == 3 ? NCLS3 : NCLS2;
+    const int nv = dim + 1;
+    const int M = 1 << (nlevels - 1);
+
+    IntMesh mesh;
+    mesh.nodes.push_back({0, 0, 0});
+    mesh.nodes.push_back({M, 0, 0});
+    mesh.nodes.push_back({0, M, 0});
+    if (dim == 3) mesh.nodes.push_back({0, 0, M});
+    mesh.elems.push_back(dim == 3 ? I4{0, 1, 2, 3} : I4{0, 1, 2, -1});
+
+    // parity pattern of a new node -> direction towards its two parents (verified below)
+    auto parity_dir = [&](int pi, int pj, int pk) -> int {
+        if (dim == 3) {
+            static const int tab[8] = {0, 5, 3, 11, 1, 9, 7, 13};   // index = pi*4 + pj*2 + pk
+            return tab[pi * 4 + pj * 2 + pk];
+        }
+        static const int tab2[4] = {0, 3, 1, 5};                    // index = pi*2 + pj
+        return tab2[pi * 2 + pj];
+    };
+
+    ref.lv.resize(nlevels);
+    for (int l = 1; l <= nlevels; ++l) {
+        RefLevel& L = ref.lv[l - 1];
+        const int m = 1 << (l - 1);
+        const int s = M / m;
+        L.m = m;
+        L.nf = (int)mesh.nodes.size();
+        HMG_CHECK(L.nf == (dim == 3 ? tot3(m) : tri(m)), "unexpected node count of the refined element");
+        HMG_CHECK(L.nf < (1 << 14), "reference element too large for the packed node lists");
+        L.ld = L.nf >= 64 ? (L.nf + 15) / 16 * 16 : (L.nf + 1) / 2 * 2;
+
+        auto lat = [&](int n) -> I3 {
+            const I3& c = mesh.nodes[n];
+            return {c[0] / s, c[1] / s, c[2] / s};
+        };
+        auto pack = [&](const I3& c) { return dim == 3 ? pack3(m, c[0], c[1], c[2]) : pack2(m, c[0], c[1]); };
+
+        // (1) permutation hierarchical -> lattice, node info
+        L.hier2lat.resize(L.nf);
+        L.nodeinfo.assign(L.nf, 0);
+        std::vector<char> seen(L.nf, 0);
+        for (int n = 0; n < L.nf; ++n) {
+            I3 c = lat(n);
+            int p = pack(c);
+            HMG_CHECK(p >= 0 && p < L.nf && !seen[p], "hierarchical -> lattice map is not a bijection");
+            seen[p] = 1;
+            L.hier2lat[n] = p;
+            int cls = node_class(dim, m, c[0], c[1], c[2]);
+            L.nodeinfo[p] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)cls << 24);
+        }
+        for (int p = 0; p < L.nf; ++p) {
+            uint32_t info = L.nodeinfo[p];
+            int i = info & 255, j = (info >> 8) & 255, cls = info >> 24;
+            if (cls == 0) L.interior.push_back((uint32_t)p | ((uint32_t)i << 14) | ((uint32_t)j << 22));
+        }
+        for (int cls = 1; cls < ref.ncls; ++cls)
+            for (int p = 0; p < L.nf; ++p)
+                if ((int)(L.nodeinfo[p] >> 24) == cls) L.boundary.push_back((uint32_t)p | ((uint32_t)cls << 14));
+
+        // (2) integer stencil: acc[p][dir][c]
+        const int ndir = ref.ndir, nc = ref.nc;
+        std::vector<int> acc((size_t)L.nf * ndir * nc, 0);
+        for (const auto& el : mesh.elems) {
+            I3 v[4];
+            for (int a = 0; a < nv; ++a) v[a] = lat(el[a]);
+            int g[4][3];
+            lattice_gradients(dim, v, g);
+            for (int a = 0; a < nv; ++a) {
+                int pa = pack(v[a]);
+                for (int b = 0; b < nv; ++b) {
+                    int d = dir_index(dim, v[b][0] - v[a][0], v[b][1] - v[a][1], v[b][2] - v[a][2]);
+                    HMG_CHECK(d >= 0, "fine-element edge is not one of the stencil directions");
+                    int* dst = &acc[((size_t)pa * ndir + d) * nc];
+                    int c = 0;
+                    for (int k = 0; k < dim; ++k)
+                        for (int q = k; q < dim; ++q, ++c)
+                            dst[c] += g[a][k] * g[b][q] + (k != q ? g[a][q] * g[b][k] : 0);
+                    dst[c] += (a == b ? 2 : 1);
+                }
+            }
+        }
+        // class invariance + table
+        double fact = dim == 3 ? 6.0 : 2.0;
+        double s_stiff = dim == 3 ? 1.0 / (fact * m) : 1.0 / fact;
+        double s_mass = 1.0 / (fact * std::pow((double)m, dim) * (dim + 1) * (dim + 2));
+        L.G.assign((size_t)ref.ncls * ndir * nc, 0.0);
+        std::vector<int> rep(ref.ncls, -1);
+        L.mass_total = 0.0;
+        long mass_int = 0;
+        for (int p = 0; p < L.nf; ++p) {
+            int cls = L.nodeinfo[p] >> 24;
+            const int* row = &acc[(size_t)p * ndir * nc];
+            for (int d = 0; d < ndir; ++d) mass_int += row[d * nc + nc - 1];
+            if (rep[cls] < 0) {
+                rep[cls] = p;
+                for (int d = 0; d < ndir; ++d)
+                    for (int c = 0; c < nc; ++c)
+                        L.G[((size_t)cls * ndir + d) * nc + c] = row[d * nc + c] * (c == nc - 1 ? s_mass : s_stiff);
+            } else {
+                const int* r0 = &acc[(size_t)rep[cls] * ndir * nc];
+                HMG_CHECK(std::equal(row, row + ndir * nc, r0), "stencil is not invariant within a node class");
+            }
+        }
+        L.mass_total = mass_int * s_mass;
+
+        // (3) pairing rule: on every reference face / edge the ascending hierarchical order is the
+        // same sequence of barycentric coordinates (src/implicit_fine_grid.jl:232-234 pairs k-th with k-th)
+        auto bary = [&](int n) -> I4 {
+            I3 c = lat(n);
+            return {m - c[0] - c[1] - c[2], c[0], c[1], dim == 3 ? c[2] : 0};
+        };
+        if (dim == 3) {
+            static const int F[4][3] = {{0, 1, 2}, {0, 1, 3}, {0, 2, 3}, {1, 2, 3}};
+            std::vector<std::array<int, 3>> first;
+            for (int f = 0; f < 4; ++f) {
+                int opp = 6 - F[f][0] - F[f][1] - F[f][2];
+                std::vector<std::array<int, 3>> seq;
+                for (int n = 0; n < L.nf; ++n) {
+                    I4 b = bary(n);
+                    if (b[opp] == 0 && b[F[f][0]] > 0 && b[F[f][1]] > 0 && b[F[f][2]] > 0)
+                        seq.push_back({b[F[f][0]], b[F[f][1]], b[F[f][2]]});
+                }
+                if (f == 0) first = seq;
+                HMG_CHECK(seq == first, "face-interior numbering is not consistent across reference faces");
+            }
+            for (const auto& t : first) L.face_bary.push_back((uint16_t)(t[0] | (t[1] << 8)));
+            HMG_CHECK((int)L.face_bary.size() == (m - 1) * (m - 2) / 2, "unexpected face-interior count");
+        }
+        {
+            const int ne_loc = dim == 3 ? 6 : 3;
+            static const int E3[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+            static const int E2[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+            std::vector<int> first_seq;
+            for (int e = 0; e < ne_loc; ++e) {
+                int a = dim == 3 ? E3[e][0] : E2[e][0], b = dim == 3 ? E3[e][1] : E2[e][1];
+                std::vector<int> seq;   // weight on the edge's second vertex, ascending hierarchical row
+                for (int n = 0; n < L.nf; ++n) {
+                    I4 bc = bary(n);
+                    if (bc[a] > 0 && bc[b] > 0 && bc[a] + bc[b] == m) seq.push_back(bc[b]);
+                }
+                if (e == 0) first_seq = seq;
+                HMG_CHECK(seq == first_seq, "edge-interior numbering is not consistent across reference edges");
+                HMG_CHECK((int)seq.size() == m - 1, "unexpected edge-interior count");
+            }
+            for (int v = 0; v < nv; ++v) HMG_CHECK(bary(v)[v] == m, "corner nodes are not the first rows");
+        }
+
+        if (l == nlevels) break;
+        // (4) refine, and verify the interpolation structure used by the transfer kernels:
+        // every new node is the midpoint of node +- dir(parity) in the finer lattice
+        // (src/interpolation.jl:7-50 builds P from the same edge graph)
+        Edges g = edge_graph(mesh, nv);
+        IntMesh finer = refine(mesh, g, dim);
+        const int s2 = s / 2;
+        for (size_t q = 0; q < g.e.size(); ++q) {
+            const I3& c = finer.nodes[mesh.nodes.size() + q];
+            I3 f = {c[0] / s2, c[1] / s2, c[2] / s2};
+            int d = parity_dir(f[0] & 1, f[1] & 1, f[2] & 1);
+            HMG_CHECK(d > 0, "new node has even lattice coordinates");
+            const int* dv = dim == 3 ? DIRS3[d] : DIRS2[d];
+            I3 pa = {f[0] + dv[0], f[1] + dv[1], dim == 3 ? f[2] + dv[2] : 0};
+            I3 pb = {f[0] - dv[0], f[1] - dv[1], dim == 3 ? f[2] - dv[2] : 0};
+            const I3 &A = mesh.nodes[g.e[q].first], &B = mesh.nodes[g.e[q].second];
+            I3 a2 = {A[0] / s2, A[1] / s2, A[2] / s2}, b2 = {B[0] / s2, B[1] / s2, B[2] / s2};
+            HMG_CHECK((pa == a2 && pb == b2) || (pa == b2 && pb == a2),
+                      "interpolation parents do not follow the parity rule");
+        }
+        mesh = std::move(finer);
+    }
+    return ref;
+}
+
+}  // namespace hmg

@@ -1,0 +1,196 @@
+// Base-mesh topology: interface cells with their owners, domain-boundary classes, all-nodes map,
+// per-element geometry.  Built once on the host (O(Ne log Ne)), uploaded by the context.
+//
+// Semantics follow src/interface.jl:65-117 (interfaces: cells shared by >= 2 elements, owners in
+// ascending element index), src/interface.jl:207-284 (boundary faces -> their edges -> their nodes,
+// each with ALL owners), src/grid.jl:176-202 (interior nodes) -- implemented with comparison sorts
+// on packed keys instead of the reference's radix-sort pipeline.
+#include <algorithm>
+#include <array>
+#include <cmath>
+
+#include "hmg_host.hpp"
+
+namespace hmg {
+
+int class_of_face(int lf) { return 1 << lf; }
+int class_of_vertex(int dim, int lv) { return dim == 3 ? (15 & ~(8 >> lv)) : (7 & ~(4 >> lv)); }
+int class_of_edge(int dim, int le) {
+    if (dim == 2) return 1 << le;
+    static const int E3[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+    int mask = 0;
+    for (int v = 0; v < 4; ++v)
+        if (v != E3[le][0] && v != E3[le][1]) mask |= 8 >> v;
+    return mask;
+}
+
+namespace {
+
+struct Entry {
+    std::array<int64_t, 3> key;
+    int32_t elem;
+    int8_t lid;
+    bool operator<(const Entry& o) const {
+        if (key != o.key) return key < o.key;
+        return elem < o.elem;    // ascending element index inside a cell (stable radix sort in the reference)
+    }
+};
+
+template <class F>   // F(group_begin, group_end)
+void for_groups(const std::vector<Entry>& v, F f) {
+    size_t i = 0;
+    while (i < v.size()) {
+        size_t j = i + 1;
+        while (j < v.size() && v[j].key == v[i].key) ++j;
+        f(i, j);
+        i = j;
+    }
+}
+
+CellMap interface_map(const std::vector<Entry>& v) {
+    CellMap m;
+    m.offset.push_back(0);
+    for_groups(v, [&](size_t i, size_t j) {
+        if (j - i < 2) return;                       // remove_singletons!
+        for (size_t q = i; q < j; ++q) m.owner.push_back(v[q].elem * 8 + v[q].lid);
+        m.cell_key.push_back(v[i].key[0]);
+        m.offset.push_back((int64_t)m.owner.size());
+    });
+    return m;
+}
+
+}  // namespace
+
+Topology build_topology(int dim, int64_t ne, int64_t nn, const int64_t* elems) {
+    HMG_CHECK(ne < (int64_t(1) << 27), "too many coarse elements for the packed owner ids");
+    Topology T;
+    T.dim = dim;
+    T.ne = ne;
+    T.nn = nn;
+    const int nv = dim + 1;
+    for (int64_t e = 0; e < ne; ++e)
+        for (int a = 0; a < nv; ++a) {
+            int64_t v = elems[e * nv + a];
+            HMG_CHECK(v >= 0 && v < nn, "element refers to a node outside the mesh");
+            if (a) HMG_CHECK(elems[e * nv + a - 1] < v, "base elements must be sorted ascending (src/implicit_fine_grid.jl:14)");
+        }
+    static const int F3[4][3] = {{0, 1, 2}, {0, 1, 3}, {0, 2, 3}, {1, 2, 3}};
+    static const int E3[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+    static const int E2[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+    const int nedge = dim == 3 ? 6 : 3;
+
+    std::vector<Entry> verts, edges, faces;
+    verts.reserve(ne * nv);
+    edges.reserve(ne * nedge);
+    for (int64_t e = 0; e < ne; ++e) {
+        const int64_t* el = elems + e * nv;
+        for (int a = 0; a < nv; ++a) verts.push_back({{el[a], -1, -1}, (int32_t)e, (int8_t)a});
+        for (int q = 0; q < nedge; ++q) {
+            const int* pr = dim == 3 ? E3[q] : E2[q];
+            edges.push_back({{el[pr[0]], el[pr[1]], -1}, (int32_t)e, (int8_t)q});
+        }
+        if (dim == 3)
+            for (int q = 0; q < 4; ++q)
+                faces.push_back({{el[F3[q][0]], el[F3[q][1]], el[F3[q][2]]}, (int32_t)e, (int8_t)q});
+    }
+    std::sort(verts.begin(), verts.end());
+    std::sort(edges.begin(), edges.end());
+    std::sort(faces.begin(), faces.end());
+
+    T.verts = interface_map(verts);
+    T.edges = interface_map(edges);
+    T.faces = interface_map(faces);
+
+    // all_nodes map
+    T.node_first.assign(nn, -1);
+    T.nodeown_off.assign(nn + 1, 0);
+    T.nodeown.reserve(verts.size());
+    for (const auto& v : verts) T.nodeown_off[v.key[0] + 1]++;
+    for (int64_t n = 0; n < nn; ++n) T.nodeown_off[n + 1] += T.nodeown_off[n];
+    for (const auto& v : verts) {
+        if (T.node_first[v.key[0]] < 0) T.node_first[v.key[0]] = v.elem * 8 + v.lid;
+        T.nodeown.push_back(v.elem * 8 + v.lid);
+    }
+
+    // domain boundary
+    T.cmask.assign(ne, 0);
+    T.node_boundary.assign(nn, 0);
+    std::vector<std::array<int64_t, 2>> bedges;
+    if (dim == 3) {
+        for_groups(faces, [&](size_t i, size_t j) {
+            if ((j - i) % 2 == 0) return;            // remove_repeated_pairs!: a lone face is a boundary face
+            const Entry& f = faces[j - 1];
+            T.cmask[f.elem] |= (uint16_t)(1u << class_of_face(f.lid));
+            bedges.push_back({f.key[0], f.key[1]});
+            bedges.push_back({f.key[0], f.key[2]});
+            bedges.push_back({f.key[1], f.key[2]});
+        });
+        std::sort(bedges.begin(), bedges.end());
+        bedges.erase(std::unique(bedges.begin(), bedges.end()), bedges.end());
+        for_groups(edges, [&](size_t i, size_t j) {
+            std::array<int64_t, 2> k = {edges[i].key[0], edges[i].key[1]};
+            if (!std::binary_search(bedges.begin(), bedges.end(), k)) return;
+            for (size_t q = i; q < j; ++q)
+                T.cmask[edges[q].elem] |= (uint16_t)(1u << class_of_edge(3, edges[q].lid));
+        });
+    } else {
+        for_groups(edges, [&](size_t i, size_t j) {
+            if ((j - i) % 2 == 0) return;
+            const Entry& ed = edges[j - 1];
+            T.cmask[ed.elem] |= (uint16_t)(1u << class_of_edge(2, ed.lid));
+            bedges.push_back({ed.key[0], ed.key[1]});
+        });
+    }
+    for (const auto& be : bedges) T.node_boundary[be[0]] = T.node_boundary[be[1]] = 1;
+    for (const auto& v : verts)
+        if (T.node_boundary[v.key[0]]) T.cmask[v.elem] |= (uint16_t)(1u << class_of_vertex(dim, v.lid));
+    for (int64_t n = 0; n < nn; ++n)
+        if (!T.node_boundary[n]) T.interior_nodes.push_back(n);
+    return T;
+}
+
+void element_coefficients(int dim, int64_t ne, const double* nodes, const int64_t* elems,
+                          const double* sigma, std::vector<double>& coef, int stride) {
+    const int nv = dim + 1;
+    coef.assign((size_t)ne * stride, 0.0);
+    for (int64_t e = 0; e < ne; ++e) {
+        const int64_t* el = elems + e * nv;
+        double J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        for (int c = 0; c < dim; ++c)
+            for (int r = 0; r < dim; ++r) J[r][c] = nodes[el[c + 1] * dim + r] - nodes[el[0] * dim + r];
+        double det, inv[3][3];   // inv = J^-1
+        if (dim == 2) {
+            det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+            inv[0][0] = J[1][1] / det; inv[0][1] = -J[0][1] / det;
+            inv[1][0] = -J[1][0] / det; inv[1][1] = J[0][0] / det;
+        } else {
+            double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+            double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+            double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+            det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+            inv[0][0] = c00 / det;
+            inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
+            inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+            inv[1][0] = c01 / det;
+            inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+            inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+            inv[2][0] = c02 / det;
+            inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
+            inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+        }
+        HMG_CHECK(det != 0.0 && std::isfinite(det), "degenerate base element");
+        const double adet = std::fabs(det);
+        // P = J^-1 diag(sigma) J^-T :  P[k][l] = sum_r inv[k][r] sigma_r inv[l][r]
+        double* out = &coef[(size_t)e * stride];
+        int c = 0;
+        for (int k = 0; k < dim; ++k)
+            for (int l = k; l < dim; ++l, ++c) {
+                double s = 0.0;
+                for (int r = 0; r < dim; ++r) s += inv[k][r] * sigma[e * dim + r] * inv[l][r];
+                out[c] = adet * s;
+            }
+        out[c] = adet;
+    }
+}
+
+}  // namespace hmg

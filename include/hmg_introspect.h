@@ -1,0 +1,42 @@
+/*
+ * hmg_introspect.h -- host-only verification entry points of libhmg_b200.so.
+ *
+ * They need no GPU and compute nothing for the product path: they expand the tables the kernels
+ * consume (through the same index functions, csrc/lattice.hpp) so that the CPU test-suite can
+ * compare them with the oracle's explicit operators and maps.  All return 0 on success;
+ * hmg_host_last_error() describes the last failure.  Index arrays crossing this boundary are
+ * 1-based Int64 for `elems1`, 0-based for everything returned.
+ */
+#ifndef HMG_B200_INTROSPECT_H
+#define HMG_B200_INTROSPECT_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* hmg_host_last_error(void);
+/* sizes[8] = m, nf, ld, n_interior, n_boundary, npf, ndir, nc; hier2lat[nf], G[ncls*ndir*nc] may be NULL.
+ * Restates what refined_element() fixes (src/multilevel_reference.jl:41-61). */
+int hmg_host_reference(int dim, int nlevels, int level, int64_t* sizes, int32_t* hier2lat, double* G,
+                       double* mass_total);
+/* dense nf x nf column-major, hierarchical order: sum_c coef[c] * table_c, i.e. the matrix
+ * sum_kl |J| P_kl ops[k,l] + lambda |J| mass of src/apply_local_operators.jl:105-118 */
+int hmg_host_local_matrix(int dim, int nlevels, int level, const double* coef, double* dense);
+/* dense nf(level) x nf(level-1) interpolation operator (src/interpolation.jl:7-50) */
+int hmg_host_transfer_matrix(int dim, int nlevels, int level_fine, double* dense);
+/* hierarchical rows of the paired nodes of a local face (kind 0) / edge (1) / vertex (2):
+ * must equal numbering.faces_interior / edges_interior / nodes (src/multilevel_reference.jl:125-203) */
+int hmg_host_interface_rows(int dim, int nlevels, int level, int kind, int lid, int32_t* rows, int64_t* count);
+/* kind 0 faces, 1 edges, 2 interface vertices, 3 all nodes (src/interface.jl:65-117); arrays may be NULL */
+int hmg_host_topology(int dim, int64_t ne, int64_t nn, const int64_t* elems1, int kind, int64_t* ncells,
+                      int64_t* nentries, int64_t* offset, int64_t* element, int64_t* local_id);
+/* Dirichlet classes per element and interior-node flags (src/interface.jl:207-284, src/grid.jl:176-202) */
+int hmg_host_boundary(int dim, int64_t ne, int64_t nn, const int64_t* elems1, uint16_t* cmask, uint8_t* interior);
+int hmg_host_class_of(int dim, int kind, int lid);
+int hmg_host_element_coefficients(int dim, int64_t ne, int64_t nn, const double* nodes, const int64_t* elems1,
+                                  const double* sigma, double* coef, int stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,203 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on identical seeded inputs.
+
+Tolerances: A*x 1e-12 relative, residual history 1e-10 relative per cycle.
+Pure data movement (interface sums in owner order, constraint, gather/scatter) is bit-exact.
+"""
+import numpy as np
+import pytest
+
+import hmgb200 as hmg
+from parity_common import Pair, relerr
+from oracle import implicit as oi
+from oracle import operators as oo
+from oracle import multigrid as om
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(2, 5, 5), (2, 3, 7), (3, 3, 4), (3, 2, 5), (2, 4, 1), (3, 2, 2)]
+IDS = ["tri-c5-L5", "tri-c3-L7", "tet-c3-L4", "tet-c2-L5", "tri-c4-L1", "tet-c2-L2"]
+
+
+@pytest.fixture(params=CASES, ids=IDS)
+def pair(request):
+    dim, c, levels = request.param
+    p = Pair(dim, c, levels, lam=0.7)
+    yield p
+    p.close()
+
+
+def test_upload_download_roundtrip(pair):
+    for level in range(1, pair.levels + 1):
+        x = pair.rand(level)
+        assert np.array_equal(pair.g.state(level).x.set(x).get(), x)
+
+
+def test_mul_matches_oracle(pair):
+    """mul!(alpha, base, A, x, y) on every level (src/apply_local_operators.jl:85-120)."""
+    for level in range(1, pair.levels + 1):
+        x, y = pair.rand(level), pair.rand(level)
+        st = pair.g.state(level)
+        st.x.set(x)
+        st.r.set(y)
+        hmg.mul(-1.3, pair.g, st.x, st.r)
+        expect = oo.mul(-1.3, pair.obase, pair.oops[level - 1], x, y.copy(order="F"))
+        assert relerr(st.r.get(), expect) <= 1e-12, level
+
+
+def test_mass_term_is_skipped_for_zero_lambda(pair):
+    level = pair.levels
+    x = pair.rand(level)
+    st = pair.g.state(level)
+    pair.g.set_lambda(0.0)
+    pair.oops[level - 1].lam = 0.0
+    st.x.set(x)
+    st.r.fill(0.0)
+    hmg.mul(1.0, pair.g, st.x, st.r)
+    expect = oo.mul(1.0, pair.obase, pair.oops[level - 1], x, np.zeros_like(x))
+    assert relerr(st.r.get(), expect) <= 1e-12
+
+
+def test_interface_primitives_are_bit_exact(pair):
+    for level in range(1, pair.levels + 1):
+        x = pair.rand(level)
+        st = pair.g.state(level)
+        st.x.set(x)
+        hmg.broadcast_interfaces(st.x, pair.g, level)
+        expect = oi.broadcast_interfaces(x.copy(order="F"), pair.oimp, level)
+        assert np.array_equal(st.x.get(), expect), level
+        hmg.apply_constraint(st.x, level, pair.g)
+        oi.apply_constraint(expect, level, pair.constraint, pair.oimp)
+        assert np.array_equal(st.x.get(), expect), level
+        y = pair.rand(level)
+        st.r.set(y)
+        hmg.zero_out_all_but_one(st.r, pair.g, level)
+        assert np.array_equal(st.r.get(), oi.zero_out_all_but_one(y.copy(order="F"), pair.oimp, level)), level
+
+
+def test_global_product_matches_oracle(pair):
+    """Ap = broadcast(constraint(A p)) (src/multigrid.jl:58-61), the benchmarked A*x."""
+    level = pair.levels
+    p = pair.rand(level)
+    oi.broadcast_interfaces(p, pair.oimp, level)
+    oi.apply_constraint(p, level, pair.constraint, pair.oimp)
+    st = pair.g.state(level)
+    st.p.set(p)
+    hmg.apply_global(pair.g, st.p, st.Ap)
+    Ap = oo.mul(1.0, pair.obase, pair.oops[level - 1], p, np.zeros_like(p))
+    oi.apply_constraint(Ap, level, pair.constraint, pair.oimp)
+    oi.broadcast_interfaces(Ap, pair.oimp, level)
+    assert relerr(st.Ap.get(), Ap) <= 1e-12
+
+
+def test_local_residual_matches_oracle(pair):
+    level = pair.levels
+    os_ = pair.ostates[level - 1]
+    os_.x[:, :] = pair.rand(level)
+    os_.b[:, :] = pair.rand(level)
+    st = pair.g.state(level)
+    st.x.set(os_.x)
+    st.b.set(os_.b)
+    hmg.local_residual(pair.g, level)
+    oo.local_residual(pair.oimp, pair.oops[level - 1], os_, level)
+    assert relerr(st.r.get(), os_.r) <= 1e-12
+
+
+def test_transfer_operators_match_oracle(pair):
+    for k in range(2, pair.levels + 1):
+        P = pair.oimp.reference.interops[k - 2]
+        r = pair.rand(k)
+        pair.g.state(k).r.set(r)
+        hmg.restrict_to(pair.g, k)
+        assert relerr(pair.g.state(k - 1).b.get(), P.T @ r) <= 1e-14, k
+        xc, xf = pair.rand(k - 1), pair.rand(k)
+        pair.g.state(k - 1).x.set(xc)
+        pair.g.state(k).x.set(xf)
+        hmg.interpolate_and_sum_to(pair.g, k)
+        assert relerr(pair.g.state(k).x.get(), xf + P @ xc) <= 1e-14, k
+
+
+def test_level1_gather_scatter_bit_exact(pair):
+    v = pair.rand(1)
+    st = pair.g.state(1)
+    st.b.set(v)
+    u = hmg.copy_to_base(pair.g, st.b)
+    expect = oi.copy_to_base(np.zeros(pair.mesh.nnodes), v, pair.oimp)
+    assert np.array_equal(u, expect)
+    ub = pair.rng.random(pair.mesh.nnodes)
+    hmg.distribute(pair.g, st.x, ub)
+    assert np.array_equal(st.x.get(), oi.distribute(np.zeros_like(v, order="F"), ub, pair.oimp))
+
+
+def test_dot_counts_all_stored_entries(pair):
+    level = pair.levels
+    a, b = pair.rand(level), pair.rand(level)
+    st = pair.g.state(level)
+    st.p.set(a)
+    st.Ap.set(b)
+    got = hmg.dot(pair.g, st.p, st.Ap)
+    assert abs(got - om.dot(a, b)) <= 1e-12 * abs(om.dot(a, b))
+
+
+def test_smoothing_steps_match_oracle(pair):
+    level = pair.levels
+    os_ = pair.ostates[level - 1]
+    x = pair.rand(level)
+    oi.broadcast_interfaces(x, pair.oimp, level)
+    oi.apply_constraint(x, level, pair.constraint, pair.oimp)
+    os_.x[:, :] = x
+    os_.b[:, :] = pair.rand(level)
+    st = pair.g.state(level)
+    st.x.set(os_.x)
+    st.b.set(os_.b)
+    hmg.smoothing_steps(3, pair.g, level)
+    om.smoothing_steps(3, pair.oimp, pair.oops[level - 1], os_, level)
+    assert relerr(st.x.get(), os_.x) <= 1e-11
+    assert relerr(st.r.get(), os_.r) <= 1e-10
+
+
+def _vcycle_history(pair, cycles, internal_coarse):
+    L = pair.levels
+    top_o = pair.ostates[-1]
+    x = pair.rand(L)
+    oi.broadcast_interfaces(x, pair.oimp, L)
+    oi.apply_constraint(x, L, pair.constraint, pair.oimp)
+    top_o.x[:, :] = x
+    oi.local_rhs(top_o.b, pair.oimp)
+    st = pair.g.state(L)
+    st.x.set(top_o.x)
+    st.b.set(top_o.b)
+    obl, A, interior = pair.obase_level()
+    bl = hmg.BaseLevel(pair.g) if internal_coarse else hmg.BaseLevel(pair.g, A, interior)
+    hist_o, hist_g = [], []
+    for _ in range(cycles):
+        om.vcycle(pair.oimp, obl, pair.oops, pair.ostates, L, 3)
+        oi.zero_out_all_but_one(top_o.r, pair.oimp, L)
+        hist_o.append(float(np.linalg.norm(top_o.r.ravel(order="K"))))
+        hist_g.append(hmg.vcycle(pair.g, bl, L, 3, resnorm=True))
+    return np.array(hist_o), np.array(hist_g), top_o.x, st.x.get()
+
+
+@pytest.mark.parametrize("internal_coarse", [False, True], ids=["given-coarse-matrix", "assembled-coarse-matrix"])
+def test_vcycle_residual_history_matches_oracle(pair, internal_coarse):
+    """vcycle! (src/multigrid.jl:73-119) + the logged residual
+    (src/examples/homogenized_coefficients.jl:286-287): <= 1e-10 relative per cycle."""
+    if pair.levels < 2 or len(pair.obase_level()[2]) == 0:
+        pytest.skip("needs at least two grids and an interior base node")
+    ho, hg, xo, xg = _vcycle_history(pair, 5, internal_coarse)
+    assert np.all(np.abs(hg - ho) <= 1e-10 * ho), (ho, hg)
+    assert ho[-1] < 0.2 * ho[0]           # it does converge
+    assert relerr(xg, xo) <= 1e-10
+
+
+def test_batched_vcycles_equal_single_calls(pair):
+    if pair.levels < 2 or len(pair.obase_level()[2]) == 0:
+        pytest.skip("needs at least two grids and an interior base node")
+    L = pair.levels
+    st = pair.g.state(L)
+    x0, b0 = pair.rand(L), pair.rand(L)
+    bl = hmg.BaseLevel(pair.g)
+    st.x.set(x0); st.b.set(b0)
+    single = [hmg.vcycle(pair.g, bl, L, 3, resnorm=True) for _ in range(3)]
+    st.x.set(x0); st.b.set(b0)
+    batched = hmg.vcycles(pair.g, bl, L, 3, 3)
+    assert np.array_equal(np.array(single), batched)      # deterministic reductions
