@@ -1,0 +1,173 @@
+# HomogenizationB200.jl -- the reference-side binding of libhmg_b200.so (include/hmg.h).
+#
+# This file is what a maintainer of haampie/Homogenization.jl adds to route the hot path
+# (matrix-free A*x on the implicit fine grid + the multigrid V-cycle) to a B200 through `ccall`.
+# It adds METHODS to the reference's own generic functions (mul!, broadcast_interfaces!,
+# apply_constraint!, zero_out_all_but_one!, local_residual!, restrict_to!, interpolate_and_sum_to!,
+# smoothing_steps!, vcycle!) for a device matrix type, so `checkerboard_homogenization` runs
+# unchanged once its LevelStates are built with `DeviceLevelStates`.
+#
+# NOTE: Julia is not installed in the image this repository is developed in; this shim is written
+# against the reference's signatures (cited below, paths relative to the reference repository) and
+# the C ABI that the Python ctypes binding (homogenization.jl_b200/_lib.py) exercises on every test
+# run, but it has not itself been executed.
+module HomogenizationB200
+
+using Homogenization
+using Homogenization: Mesh, ImplicitFineGrid, LevelState, BaseLevel, L2PlusDivAGrad,
+                      ZeroDirichletConstraint, nelements, nnodes, refined_mesh, nlevels
+import Homogenization: broadcast_interfaces!, apply_constraint!, zero_out_all_but_one!,
+                       local_residual!, restrict_to!, interpolate_and_sum_to!, smoothing_steps!,
+                       vcycle!
+import LinearAlgebra: mul!
+using SparseArrays: SparseMatrixCSC
+using StaticArrays: SVector
+
+const libhmg = get(ENV, "HMG_B200_LIB", joinpath(@__DIR__, "..", "libhmg_b200.so"))
+
+# state vector ids of include/hmg.h (enum hmg_vec)
+const HMG_X, HMG_B, HMG_R, HMG_P, HMG_AP, HMG_V, HMG_W = Cint.(0:6)
+
+struct HmgError <: Exception
+    msg::String
+end
+
+@inline function check(status::Cint)
+    status == 0 && return nothing
+    throw(HmgError(unsafe_string(ccall((:hmg_last_error, libhmg), Cstring, ()))))
+end
+
+"""
+One context = ImplicitFineGrid + ZeroDirichletConstraint + L2PlusDivAGrad on every level + the
+LevelStates, resident on one GPU (hmg_create).  Freed by a finalizer (hmg_destroy).
+"""
+mutable struct DeviceGrid
+    ctx::Ptr{Cvoid}
+    implicit::ImplicitFineGrid
+    function DeviceGrid(implicit::ImplicitFineGrid{dim}, σs::Vector{SVector{dim,Float64}}, λ::Float64; device::Integer = 0) where {dim}
+        base = implicit.base
+        ctx = Ref{Ptr{Cvoid}}(C_NULL)
+        nodes = reinterpret(Float64, base.nodes)          # dim x nn, column-major
+        elems = reinterpret(Int64, base.elements)         # (dim+1) x ne, 1-based, sorted per element
+        sig = reinterpret(Float64, σs)                    # dim x ne
+        GC.@preserve nodes elems sig begin
+            check(ccall((:hmg_create, libhmg), Cint,
+                (Cint, Cint, Int64, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Float64, Cint, Ref{Ptr{Cvoid}}),
+                dim, nlevels(implicit), nelements(base), nnodes(base), nodes, elems, sig, λ, device, ctx))
+        end
+        g = new(ctx[], implicit)
+        finalizer(x -> (x.ctx == C_NULL || ccall((:hmg_destroy, libhmg), Cint, (Ptr{Cvoid},), x.ctx); x.ctx = C_NULL), g)
+        return g
+    end
+end
+
+"""
+An Nf(level) x Ne matrix living on the GPU: the `Tv <: AbstractMatrix{T}` of
+`LevelState{T,Tv}` (src/multigrid.jl:7).  Scalar indexing goes through a download and is meant
+for debugging only.
+"""
+struct DeviceMatrix <: AbstractMatrix{Float64}
+    grid::DeviceGrid
+    level::Cint
+    which::Cint
+end
+
+Base.size(A::DeviceMatrix) = (Int(ccall((:hmg_nf, libhmg), Int64, (Ptr{Cvoid}, Cint), A.grid.ctx, A.level)),
+                              Int(ccall((:hmg_ne_local, libhmg), Int64, (Ptr{Cvoid},), A.grid.ctx)))
+
+function Base.copyto!(dst::DeviceMatrix, src::Matrix{Float64})
+    @assert size(dst) == size(src)
+    GC.@preserve src check(ccall((:hmg_upload, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Int64),
+                                 dst.grid.ctx, dst.level, dst.which, src, size(src, 1)))
+    dst
+end
+function Base.copyto!(dst::Matrix{Float64}, src::DeviceMatrix)
+    @assert size(dst) == size(src)
+    GC.@preserve dst check(ccall((:hmg_download, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Int64),
+                                 src.grid.ctx, src.level, src.which, dst, size(dst, 1)))
+    dst
+end
+function Base.copyto!(dst::DeviceMatrix, src::DeviceMatrix)
+    @assert dst.level == src.level
+    check(ccall((:hmg_copy, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint, Cint), dst.grid.ctx, dst.level, dst.which, src.which))
+    dst
+end
+Base.Array(A::DeviceMatrix) = copyto!(Matrix{Float64}(undef, size(A)...), A)
+Base.getindex(A::DeviceMatrix, i::Int, j::Int) = Array(A)[i, j]      # debugging only
+Base.fill!(A::DeviceMatrix, v::Real) = (check(ccall((:hmg_fill, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint, Float64),
+                                                    A.grid.ctx, A.level, A.which, Float64(v))); A)
+
+"""
+    DeviceLevelStates(grid) -> Vector{LevelState{Float64,DeviceMatrix}}
+
+Replaces `LevelState(nelements(base), nnodes(mesh), Float64)` of
+src/examples/homogenized_coefficients.jl:237-240.
+"""
+DeviceLevelStates(g::DeviceGrid) = map(1:nlevels(g.implicit)) do k
+    LevelState{Float64,DeviceMatrix}((DeviceMatrix(g, k, w) for w in (HMG_X, HMG_B, HMG_R, HMG_P, HMG_AP))...)
+end
+
+# ---- device methods of the reference's generic functions -------------------------------------
+
+# mul!(α, base, A, x, y): y ← αAx + y   (src/apply_local_operators.jl:85-91)
+function mul!(α::Float64, base::Mesh, A::L2PlusDivAGrad, x::DeviceMatrix, y::DeviceMatrix)
+    check(ccall((:hmg_set_lambda, libhmg), Cint, (Ptr{Cvoid}, Float64), x.grid.ctx, A.λ))
+    check(ccall((:hmg_mul, libhmg), Cint, (Ptr{Cvoid}, Cint, Float64, Cint, Cint), x.grid.ctx, x.level, α, x.which, y.which))
+    y
+end
+
+# broadcast_interfaces!(x, implicit, level)   (src/implicit_fine_grid.jl:209)
+broadcast_interfaces!(x::DeviceMatrix, implicit::ImplicitFineGrid, level::Int) =
+    (check(ccall((:hmg_broadcast_interfaces, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint), x.grid.ctx, level, x.which)); x)
+
+# apply_constraint!(x, level, z, implicit)   (src/implicit_fine_grid.jl:94)
+apply_constraint!(x::DeviceMatrix, level::Int, z::ZeroDirichletConstraint, implicit::ImplicitFineGrid) =
+    (check(ccall((:hmg_apply_constraint, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint), x.grid.ctx, level, x.which)); x)
+
+# zero_out_all_but_one!(x, implicit, level)   (src/implicit_fine_grid.jl:334)
+zero_out_all_but_one!(x::DeviceMatrix, implicit::ImplicitFineGrid, level::Int) =
+    (check(ccall((:hmg_zero_out_all_but_one, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint), x.grid.ctx, level, x.which)); x)
+
+# local_residual!(implicit, A, curr, k)   (src/apply_local_operators.jl:18-27)
+function local_residual!(implicit::ImplicitFineGrid, A::L2PlusDivAGrad, curr::LevelState{Float64,DeviceMatrix}, k::Int)
+    check(ccall((:hmg_set_lambda, libhmg), Cint, (Ptr{Cvoid}, Float64), curr.x.grid.ctx, A.λ))
+    check(ccall((:hmg_local_residual, libhmg), Cint, (Ptr{Cvoid}, Cint), curr.x.grid.ctx, k))
+end
+
+# restrict_to!(next.b, P, curr.r) / interpolate_and_sum_to!(curr.x, P, next.x)   (src/interpolation.jl:52-74)
+restrict_to!(y::DeviceMatrix, P::SparseMatrixCSC, x::DeviceMatrix) =
+    check(ccall((:hmg_restrict, libhmg), Cint, (Ptr{Cvoid}, Cint), x.grid.ctx, x.level))
+interpolate_and_sum_to!(y::DeviceMatrix, P::SparseMatrixCSC, x::DeviceMatrix) =
+    check(ccall((:hmg_interpolate_add, libhmg), Cint, (Ptr{Cvoid}, Cint), y.grid.ctx, y.level))
+
+# smoothing_steps!(steps, implicit, ops, curr, k)   (src/multigrid.jl:46-71)
+function smoothing_steps!(steps::Integer, implicit::ImplicitFineGrid, ops::L2PlusDivAGrad, curr::LevelState{Float64,DeviceMatrix}, k::Int)
+    check(ccall((:hmg_set_lambda, libhmg), Cint, (Ptr{Cvoid}, Float64), curr.x.grid.ctx, ops.λ))
+    check(ccall((:hmg_smoothing_steps, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint), curr.x.grid.ctx, k, steps))
+end
+
+"""
+    DeviceBaseLevel(grid, A_interior, interior_nodes)
+
+Replaces `BaseLevel(Float64, cholesky(A[interior,interior]), nnodes(base), interior)`
+(src/examples/homogenized_coefficients.jl:259-261): the sparse matrix itself is handed over.
+"""
+struct DeviceBaseLevel
+    grid::DeviceGrid
+end
+function DeviceBaseLevel(g::DeviceGrid, A::SparseMatrixCSC{Float64,Int64}, interior::Vector{Int64})
+    GC.@preserve A interior check(ccall((:hmg_set_coarse_matrix, libhmg), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}),
+        g.ctx, size(A, 1), A.colptr, A.rowval, A.nzval, interior))
+    DeviceBaseLevel(g)
+end
+
+# vcycle!(implicit, base, ops, levels, k, steps)   (src/multigrid.jl:73-119): one ccall per V-cycle
+function vcycle!(implicit::ImplicitFineGrid, base::DeviceBaseLevel, ops::Vector{<:L2PlusDivAGrad},
+                 levels::Vector{LevelState{Float64,DeviceMatrix}}, k::Int, steps = 2)
+    check(ccall((:hmg_set_lambda, libhmg), Cint, (Ptr{Cvoid}, Float64), base.grid.ctx, ops[k].λ))
+    check(ccall((:hmg_vcycle, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}), base.grid.ctx, k, steps, C_NULL))
+    nothing
+end
+
+end # module
