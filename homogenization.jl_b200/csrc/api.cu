@@ -54,6 +54,7 @@ struct hmg_ctx {
     std::vector<int64_t> local_to_global;
     std::vector<LevelDev> lv;
     TopoView tview{};
+    FuseView fview{};
     double* elem_coef = nullptr;
     uint16_t* cmask = nullptr;
     int32_t* node_first = nullptr;
@@ -165,6 +166,13 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne, int64_t nn, const double*
         V.boundary = c->dupload(R.boundary);
         V.G = c->dupload(R.G);
         V.face_bary = c->dupload(R.face_bary);
+        V.iface_idx = c->dupload(R.iface_idx);
+        V.interp_tab = c->dupload(R.interp_tab);
+        V.restrict_tab = c->dupload(R.restrict_tab);
+        V.tasks = c->dupload(R.tasks);
+        V.task_cls = c->dupload(R.task_cls);
+        V.ntasks = (int)R.task_cls.size();
+        V.n_uniform = R.n_uniform_tasks;
         for (int v = 0; v < 4; ++v) V.vpos[v] = v < nv ? R.hier2lat[v] : 0;
         L.hier2lat = c->dupload(R.hier2lat);
         for (int w = 0; w <= HMG_AP; ++w) L.vec[w] = c->dalloc<double>((size_t)V.ld * ne);
@@ -180,6 +188,13 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne, int64_t nn, const double*
     c->tview.edge_own = c->dupload(T.edges.owner);
     c->tview.vert_off = c->dupload(T.verts.offset);
     c->tview.vert_own = c->dupload(T.verts.owner);
+    c->fview.nfaces = T.faces.ncells();
+    c->fview.nedges = T.edges.ncells();
+    c->fview.nverts = T.verts.ncells();
+    c->fview.cell_off = c->dupload(T.cell_off);
+    c->fview.cell_own = c->dupload(T.cell_own);
+    c->fview.elem_cells = c->dupload(T.elem_cells);
+    c->fview.arrive = c->dalloc<unsigned int>(T.cell_off.size());
     c->cmask = c->dupload(T.cmask);
     c->node_first = c->dupload(T.node_first);
     std::vector<int32_t> e32(c->elems.begin(), c->elems.end());
@@ -196,8 +211,11 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne, int64_t nn, const double*
 }
 
 // ---- building blocks ---------------------------------------------------------------------
-void do_apply(hmg_ctx* c, int l, int mode, double alpha, const double* x, double* y, const double* b) {
+void do_apply(hmg_ctx* c, int l, int mode, double alpha, const double* x, double* y, const double* b,
+              bool fused = false) {
     ApplyArgs a;
+    a.fused = fused ? 1 : 0;
+    a.F = c->fview;
     a.L = c->level(l).view;
     a.ne = c->ne;
     a.elem_coef = c->elem_coef;
@@ -216,17 +234,16 @@ void do_local_residual(hmg_ctx* c, int l) {
 void do_smoothing(hmg_ctx* c, int l, int steps) {
     const int64_t n = c->nstored(l);
     double *x = c->vecp(l, HMG_X), *r = c->vecp(l, HMG_R), *p = c->vecp(l, HMG_P), *Ap = c->vecp(l, HMG_AP);
-    do_local_residual(c, l);
-    do_broadcast(c, l, r);
-    CUDA_OK(cudaMemcpyAsync(p, r, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    c->launches++;
-    check_launch(c, launch_dot(c->red, r, r, n, POST_RHO, 0, c->stream));
+    // r = broadcast(constraint(b - A x)) in one kernel; p = r and rho = r.r in one pass
+    do_apply(c, l, APPLY_RESIDUAL, 1.0, x, r, c->vecp(l, HMG_B), true);
+    check_launch(c, launch_copy_dot(c->red, r, p, n, c->stream));
     for (int i = 0; i < steps; ++i) {
-        do_apply(c, l, APPLY_AX, 1.0, p, Ap, nullptr);
-        do_broadcast(c, l, Ap);
+        do_apply(c, l, APPLY_AX, 1.0, p, Ap, nullptr, true);          // Ap = broadcast(constraint(A p))
         check_launch(c, launch_dot(c->red, p, Ap, n, POST_PAP, 0, c->stream));
         check_launch(c, launch_cg_update(c->red, x, p, r, Ap, n, c->stream));
-        check_launch(c, launch_p_update(c->red, p, r, n, c->stream));
+        // the reference also updates p after the last step, but that value is never used
+        // (src/multigrid.jl:68; the next smoothing call starts from a fresh residual)
+        if (i + 1 < steps) check_launch(c, launch_p_update(c->red, p, r, n, c->stream));
     }
 }
 void do_coarse_solve(hmg_ctx* c) {
@@ -494,8 +511,7 @@ int hmg_apply_global(hmg_ctx* c, int level, int x, int y) {
     NEED_CTX(c);
     CUDA_OK(cudaSetDevice(c->device));
     HMG_CHECK(x != y, "apply: x and y must be different vectors");
-    do_apply(c, level, APPLY_AX, 1.0, c->vecp(level, x), c->vecp(level, y), nullptr);
-    do_broadcast(c, level, c->vecp(level, y));
+    do_apply(c, level, APPLY_AX, 1.0, c->vecp(level, x), c->vecp(level, y), nullptr, true);
     HMG_API_END
 }
 int hmg_apply_constraint(hmg_ctx* c, int level, int which) {
@@ -720,8 +736,7 @@ int hmg_time_op(hmg_ctx* c, int op, int level, int steps, int reps, float* ms_ou
     CUDA_OK(cudaEventRecord(c->ev0, c->stream));
     for (int i = 0; i < reps; ++i) {
         if (op == 0) {
-            do_apply(c, level, APPLY_AX, 1.0, c->vecp(level, HMG_P), c->vecp(level, HMG_AP), nullptr);
-            do_broadcast(c, level, c->vecp(level, HMG_AP));
+            do_apply(c, level, APPLY_AX, 1.0, c->vecp(level, HMG_P), c->vecp(level, HMG_AP), nullptr, true);
         } else if (op == 1) {
             do_vcycle(c, level, steps);
         } else if (op == 2) {

@@ -50,8 +50,20 @@ struct RefLevel {
     std::vector<uint32_t> nodeinfo;  // per packed index: i | j<<8 | k<<16 | class<<24
     std::vector<uint32_t> interior;  // interior nodes (class 0), packed p | i<<14 | j<<22
     std::vector<uint32_t> boundary;  // boundary nodes sorted by class, p | class<<14 ; (i,j,k) via nodeinfo
+    // warp tasks of the apply kernel: 32 entries (p | i<<14 | j<<22, or 0xFFFFFFFF) per task.
+    // Uniform tasks hold 32 nodes of ONE class (coefficients live in registers); the remainders of
+    // all classes are pooled into mixed tasks (class looked up per lane).  Uniform tasks come first.
+    std::vector<uint32_t> tasks;
+    std::vector<uint8_t> task_cls;   // class of a uniform task, 255 = mixed
+    int n_uniform_tasks = 0;
+    // transfer tables between this level (fine) and the next coarser one (levels >= 2):
+    std::vector<uint32_t> interp_tab;   // per fine node: coarse parents pa | pb<<16 (pa == pb: coincident)
+    std::vector<uint16_t> restrict_tab; // per coarse node: [ndir] fine indices (centre first), 0xFFFF = outside
     std::vector<double> G;           // [ncls][ndir][nc] stencil table, scale factors folded in
     std::vector<uint16_t> face_bary; // 3D: interior nodes of a face, barycentric a | b<<8
+    // packed index of the t-th paired node of every local cell: faces [4][npf] (3D), then edges
+    // [6|3][npe], then vertices [4|3]
+    std::vector<uint16_t> iface_idx;
     double mass_total = 0.0;         // sum of all entries of the reference mass matrix
 };
 
@@ -81,6 +93,12 @@ struct Topology {
     std::vector<uint16_t> cmask;         // per element: bit c set <=> class c is on the domain boundary
     std::vector<uint8_t> node_boundary;  // per base node: 1 if on the domain boundary
     std::vector<int64_t> interior_nodes; // complement (sorted), src/grid.jl:176-202
+    // unified numbering of the interface cells: faces, then edges, then vertices
+    std::vector<int64_t> cell_off;       // CSR over all interface cells
+    std::vector<int32_t> cell_own;
+    std::vector<int32_t> elem_cells;     // [ne][16]: unified cell id of the element's local faces (0..3),
+                                         // edges (4..9), vertices (10..13) in 3D; edges (0..2), vertices (3..5)
+                                         // in 2D; -1 if the cell has a single owner
     // cut cells (multi-GPU): filled by the partitioner
 };
 

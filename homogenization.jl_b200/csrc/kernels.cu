@@ -10,6 +10,8 @@
 //   K4 transfer kernels    restriction / interpolation in lattice form (src/interpolation.jl:52-74),
 //                          level-1 gather/scatter (src/implicit_fine_grid.jl:148-202).
 #include <cstdio>
+#include <cstdlib>
+#include <algorithm>
 
 #include "kernels.cuh"
 #include "lattice.hpp"
@@ -54,108 +56,212 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: local operator apply
+// K1: local operator apply (+ fused interface sum)
 // ------------------------------------------------------------------------------------------
-// blockDim = (TX, EPB): EPB consecutive coarse elements per CTA, TX threads per element.
-template <int DIM>
-__global__ void __launch_bounds__(256) apply_kernel(const ApplyArgs a) {
+// Face set a stencil direction points out of: a neighbour n+d of a node of class `cls` lies outside
+// the simplex iff (cls & out_mask(d)) != 0 (the lattice simplex is convex and d has entries in {-1,0,1}).
+template <int DIM> __host__ __device__ constexpr int out_mask(int d) {
+    if (DIM == 3) {
+        constexpr int I[15] = {0, 1, -1, 0, 0, 0, 0, -1, 1, -1, 1, 0, 0, 1, -1};
+        constexpr int J[15] = {0, 0, 0, 1, -1, 0, 0, 1, -1, 0, 0, -1, 1, -1, 1};
+        constexpr int K[15] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 1, -1};
+        return (K[d] < 0 ? 1 : 0) | (J[d] < 0 ? 2 : 0) | (I[d] < 0 ? 4 : 0) | (I[d] + J[d] + K[d] > 0 ? 8 : 0);
+    }
+    constexpr int I2[7] = {0, 1, -1, 0, 0, -1, 1};
+    constexpr int J2[7] = {0, 0, 0, 1, -1, 1, -1};
+    return (J2[d] < 0 ? 1 : 0) | (I2[d] < 0 ? 2 : 0) | (I2[d] + J2[d] > 0 ? 4 : 0);
+}
+
+template <int DIM, int D> struct StencilSum {
+    // acc += c[d] * x[p + off[d]] for every direction whose neighbour is inside (class test is
+    // warp-uniform for uniform tasks)
+    static __device__ __forceinline__ double run(const double* c, const double* xp, const int* off, int cls, double acc) {
+        acc = StencilSum<DIM, D - 1>::run(c, xp, off, cls, acc);
+        if ((cls & out_mask<DIM>(D)) == 0) acc = fma(c[D], xp[off[D]], acc);
+        return acc;
+    }
+};
+template <int DIM> struct StencilSum<DIM, 0> {
+    static __device__ __forceinline__ double run(const double* c, const double* xp, const int*, int, double acc) {
+        return fma(c[0], xp[0], acc);
+    }
+};
+
+// Persistent, double-buffered: gridDim.x CTAs loop over groups of EPB consecutive coarse elements;
+// while a group is processed, the TMA bulk copy of the CTA's next group is already in flight.
+// blockDim = (TX, EPB): TX threads (TX/32 warps) per element.
+template <int DIM, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) apply_kernel(const ApplyArgs a) {
     using D = Dims<DIM>;
+    constexpr int NCELL = DIM == 3 ? 14 : 6;
+    constexpr int NFL = DIM == 3 ? 4 : 0, NEL = DIM == 3 ? 6 : 3;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ int s_cell[8][16], s_beg[8][16], s_cnt[8][16];
     const LevelView& L = a.L;
     const int ld = L.ld;
     const int epb = blockDim.y;
-    double* xs = reinterpret_cast<double*>(smem_raw);          // [epb][ld]
-    double* coef = xs + (size_t)epb * ld;                      // [epb][NCLS][NDIR]
+    const int buf = epb * ld;
+    double* xs0 = reinterpret_cast<double*>(smem_raw);         // [2][epb][ld]
+    double* coef = xs0 + 2 * (size_t)buf;                      // [epb][NCLS][NDIR]
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    const int64_t e0 = (int64_t)blockIdx.x * epb;
-    const int nel = (int)min((int64_t)epb, a.ne - e0);
+    const int el = threadIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int64_t ngroups = (a.ne + epb - 1) / epb;
+    const int m = L.m;
+    const int mode = a.mode;
 
     if (tid == 0) {
-        mbar_init(&mbar, 1);
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
         fence_mbar_init();
     }
     __syncthreads();
-    if (tid == 0) {
-        const uint32_t bytes = (uint32_t)nel * ld * 8u;
-        mbar_expect_tx(&mbar, bytes);
-        bulk_g2s(xs, a.x + e0 * ld, bytes, &mbar);
-    }
-    // per-element stencil coefficients for every node class, while the copy is in flight
-    const int el = threadIdx.y;
-    const int64_t e = e0 + el;
-    double* ce = coef + el * (D::NCLS * D::NDIR);
-    if (el < nel) {
-        double ec[D::NC];
-#pragma unroll
-        for (int c = 0; c < D::NC; ++c) ec[c] = __ldg(a.elem_coef + e * D::CS + c);
-        ec[D::NC - 1] *= a.lambda;
-        for (int t = threadIdx.x; t < D::NCLS * D::NDIR; t += blockDim.x) {
-            const double* g = L.G + t * D::NC;
-            double s = 0.0;
-#pragma unroll
-            for (int c = 0; c < D::NC; ++c) s = fma(ec[c], __ldg(g + c), s);
-            ce[t] = s;
-        }
-    }
-    mbar_wait(&mbar, 0);
-    __syncthreads();
-    if (el >= nel) return;
+    auto issue = [&](int64_t g, int b) {
+        const int64_t e0 = g * epb;
+        const uint32_t bytes = (uint32_t)min((int64_t)epb, a.ne - e0) * ld * 8u;
+        mbar_expect_tx(&mbar[b], bytes);
+        bulk_g2s(xs0 + (size_t)b * buf, a.x + e0 * ld, bytes, &mbar[b]);
+    };
+    if (tid == 0 && (int64_t)blockIdx.x < ngroups) issue(blockIdx.x, 0);
 
-    const double* xe = xs + (size_t)el * ld;
-    double* ye = a.y + e * ld;
-    const double* be = a.b ? a.b + e * ld : nullptr;
-    const int mode = a.mode;
-    const int m = L.m;
+    int it = 0;
+    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
+        const int cur = it & 1;
+        const int64_t e0 = g * epb;
+        const int nel = (int)min((int64_t)epb, a.ne - e0);
+        const int64_t e = e0 + el;
+        // prefetch the next group: the other buffer was released by the barrier ending the last iteration
+        if (tid == 0 && g + gridDim.x < ngroups) issue(g + gridDim.x, cur ^ 1);
 
-    // interior nodes: one translation-invariant stencil, coefficients in registers
-    {
-        double c[D::NDIR];
+        // per-element stencil coefficients for every node class, while the copies are in flight
+        double* ce = coef + el * (D::NCLS * D::NDIR);
+        if (el < nel) {
+            double ec[D::NC];
 #pragma unroll
-        for (int d = 0; d < D::NDIR; ++d) c[d] = ce[d];
-        for (int q = threadIdx.x; q < L.n_interior; q += blockDim.x) {
-            const uint32_t u = __ldg(L.interior + q);
-            const int p = u & 0x3fff, i = (u >> 14) & 255, j = (u >> 22) & 255;
-            int off[D::NDIR];
-            neighbour_offsets<DIM>(m, i, j, off);
-            const double* xp = xe + p;
-            double acc = 0.0;
+            for (int c = 0; c < D::NC; ++c) ec[c] = __ldg(a.elem_coef + e * D::CS + c);
+            ec[D::NC - 1] *= a.lambda;
+            for (int t = threadIdx.x; t < D::NCLS * D::NDIR; t += blockDim.x) {
+                const double* gt = L.G + t * D::NC;
+                double s = 0.0;
 #pragma unroll
-            for (int d = 0; d < D::NDIR; ++d) acc = fma(c[d], xp[off[d]], acc);
-            if (mode == APPLY_AX) ye[p] = acc;
-            else if (mode == APPLY_RESIDUAL) ye[p] = be[p] - acc;
-            else ye[p] += a.alpha * acc;
-        }
-    }
-    // boundary nodes: truncated stencils by class; Dirichlet classes are zeroed
-    {
-        const unsigned cm = a.cmask[e];
-        for (int q = threadIdx.x; q < L.n_boundary; q += blockDim.x) {
-            const uint32_t u = __ldg(L.boundary + q);
-            const int p = u & 0x3fff, cls = u >> 14;
-            const uint32_t info = __ldg(L.nodeinfo + p);
-            const int i = info & 255, j = (info >> 8) & 255, k = (info >> 16) & 255;
-            int off[D::NDIR];
-            neighbour_offsets<DIM>(m, i, j, off);
-            const double* cc = ce + cls * D::NDIR;
-            const double* xp = xe + p;
-            double acc = 0.0;
-#pragma unroll
-            for (int d = 0; d < D::NDIR; ++d) {
-                const double xv = neighbour_inside<DIM>(m, i, j, k, d) ? xp[off[d]] : 0.0;
-                acc = fma(cc[d], xv, acc);
+                for (int c = 0; c < D::NC; ++c) s = fma(ec[c], __ldg(gt + c), s);
+                ce[t] = s;
             }
-            const bool fixed = (cm >> cls) & 1u;
-            if (mode == APPLY_AX) ye[p] = fixed ? 0.0 : acc;
-            else if (mode == APPLY_RESIDUAL) ye[p] = fixed ? 0.0 : be[p] - acc;
-            else ye[p] += a.alpha * acc;
         }
+        mbar_wait(&mbar[cur], (uint32_t)((it >> 1) & 1));
+        __syncthreads();
+
+        if (el < nel) {
+            const double* xe = xs0 + (size_t)cur * buf + (size_t)el * ld;
+            double* ye = a.y + e * ld;
+            const double* be = a.b ? a.b + e * ld : nullptr;
+            const unsigned cm = a.cmask[e];
+            // uniform tasks: 32 nodes of one class, coefficients in registers; contiguous ranges per warp
+            {
+                const int t0 = (int)(((long)L.n_uniform * warp) / nwarps), t1 = (int)(((long)L.n_uniform * (warp + 1)) / nwarps);
+                int curc = -1;
+                double c[D::NDIR];
+                bool fixed = false;
+                for (int t = t0; t < t1; ++t) {
+                    const int cls = L.task_cls[t];
+                    if (cls != curc) {
+#pragma unroll
+                        for (int d = 0; d < D::NDIR; ++d) c[d] = ce[cls * D::NDIR + d];
+                        fixed = (cm >> cls) & 1u;
+                        curc = cls;
+                    }
+                    const uint32_t u = __ldg(L.tasks + t * 32 + lane);
+                    const int p = u & 0x3fff, i = (u >> 14) & 255, j = (u >> 22) & 255;
+                    int off[D::NDIR];
+                    neighbour_offsets<DIM>(m, i, j, off);
+                    const double acc = StencilSum<DIM, D::NDIR - 1>::run(c, xe + p, off, cls, 0.0);
+                    if (mode == APPLY_AX) ye[p] = fixed ? 0.0 : acc;
+                    else if (mode == APPLY_RESIDUAL) ye[p] = fixed ? 0.0 : be[p] - acc;
+                    else ye[p] += a.alpha * acc;
+                }
+            }
+            // mixed tasks (class remainders): class and coefficients per lane
+            for (int t = L.n_uniform + warp; t < L.ntasks; t += nwarps) {
+                const uint32_t u = __ldg(L.tasks + t * 32 + lane);
+                if (u == 0xFFFFFFFFu) continue;
+                const int p = u & 0x3fff, i = (u >> 14) & 255, j = (u >> 22) & 255;
+                const int cls = __ldg(L.nodeinfo + p) >> 24;
+                int off[D::NDIR];
+                neighbour_offsets<DIM>(m, i, j, off);
+                const double acc = StencilSum<DIM, D::NDIR - 1>::run(ce + cls * D::NDIR, xe + p, off, cls, 0.0);
+                const bool fixed = (cm >> cls) & 1u;
+                if (mode == APPLY_AX) ye[p] = fixed ? 0.0 : acc;
+                else if (mode == APPLY_RESIDUAL) ye[p] = fixed ? 0.0 : be[p] - acc;
+                else ye[p] += a.alpha * acc;
+            }
+        }
+
+        if (a.fused) {
+            // ---- fused interface sum: the last CTA to arrive at a shared cell sums the owners' partial
+            // results in ascending owner order and writes the sum to every owner.  No waiting anywhere.
+            __threadfence();                 // publish this thread's partial results device-wide
+            __syncthreads();
+            if (el < nel && threadIdx.x < NCELL) {
+                const int cell = a.F.elem_cells[e * 16 + threadIdx.x];
+                int mine = -1, bo = 0, cn = 0;
+                if (cell >= 0) {
+                    const int64_t b0 = a.F.cell_off[cell];
+                    cn = (int)(a.F.cell_off[cell + 1] - b0);
+                    bo = (int)b0;
+                    const unsigned old = atomicAdd(a.F.arrive + cell, 1u);
+                    if (old + 1u == (unsigned)cn) {
+                        mine = cell;
+                        a.F.arrive[cell] = 0u;   // nobody else touches this counter before the next launch
+                    }
+                }
+                s_cell[el][threadIdx.x] = mine;
+                s_beg[el][threadIdx.x] = bo;
+                s_cnt[el][threadIdx.x] = cn;
+            }
+            __syncthreads();
+            if (el < nel) {
+                __threadfence();
+                const int npf = L.npf, npe = L.npe;
+                int total = 0;
+#pragma unroll
+                for (int c = 0; c < NCELL; ++c)
+                    total += s_cell[el][c] >= 0 ? (c < NFL ? npf : (c < NFL + NEL ? npe : 1)) : 0;
+                for (int w = threadIdx.x; w < total; w += blockDim.x) {
+                    // locate the (cell, node) item in the flat list of the cells finished by this element
+                    int c = 0, t = w, npc = 0, base = 0;
+#pragma unroll
+                    for (int q = 0; q < NCELL; ++q) {
+                        const int n = q < NFL ? npf : (q < NFL + NEL ? npe : 1);
+                        const int cnt = s_cell[el][q] >= 0 ? n : 0;
+                        if (t >= 0 && t < cnt && npc == 0) {
+                            c = q; npc = n;
+                            base = q < NFL ? 0 : (q < NFL + NEL ? NFL * npf : NFL * npf + NEL * npe);
+                        }
+                        if (npc == 0) t -= cnt;
+                    }
+                    const int b0 = s_beg[el][c], cn = s_cnt[el][c];
+                    const uint16_t* tab = L.iface_idx + base + t;
+                    double sum = 0.0;
+                    for (int o = 0; o < cn; ++o) {
+                        const int32_t id = __ldg(a.F.cell_own + b0 + o);
+                        sum += __ldcg(a.y + (int64_t)(id >> 3) * ld + __ldg(tab + (id & 7) * npc));
+                    }
+                    for (int o = 0; o < cn; ++o) {
+                        const int32_t id = __ldg(a.F.cell_own + b0 + o);
+                        __stcg(a.y + (int64_t)(id >> 3) * ld + __ldg(tab + (id & 7) * npc), sum);
+                    }
+                }
+            }
+        }
+        __syncthreads();   // everyone is done with this buffer and the coefficient table
     }
 }
 
 static void apply_block_shape(const LevelView& L, int& tx, int& epb) {
-    // threads per element ~ nodes/4, rounded to a warp multiple; fill the CTA (256 threads) with elements
-    if (L.nf >= 768) { tx = 256; epb = 1; }
+    // threads per element ~ nodes/4..16, a warp multiple; fill the CTA with elements on small levels
+    if (L.nf >= 4096) { tx = 512; epb = 1; }
+    else if (L.nf >= 768) { tx = 256; epb = 1; }
     else if (L.nf >= 384) { tx = 128; epb = 2; }
     else if (L.nf >= 128) { tx = 64; epb = 4; }
     else { tx = 32; epb = 8; }
@@ -166,15 +272,33 @@ static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
     using D = Dims<DIM>;
     int tx, epb;
     apply_block_shape(a.L, tx, epb);
-    size_t smem = (size_t)epb * (a.L.ld + D::NCLS * D::NDIR) * sizeof(double);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(apply_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
+    const size_t smem = (size_t)epb * (2 * a.L.ld + D::NCLS * D::NDIR) * sizeof(double);
+    // register budget: 64/thread (more resident CTAs) by default, 85/thread with HMG_APPLY_REGS=85
+    static const bool wide = [] { const char* v = getenv("HMG_APPLY_REGS"); return v && atoi(v) > 64; }();
+    const bool big = tx * epb > 256;
+    auto kern = big ? (wide ? apply_kernel<DIM, 512, 1> : apply_kernel<DIM, 512, 2>)
+                    : (wide ? apply_kernel<DIM, 256, 3> : apply_kernel<DIM, 256, 4>);
+    static size_t configured[4] = {0, 0, 0, 0};
+    const int ki = (big ? 1 : 0) + (wide ? 2 : 0);
+    if (smem > configured[ki]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[ki] = smem;
     }
+    // persistent grid: as many CTAs as fit on the device at once
+    static int cached_key = -1, cached_blocks = 0, sms = 0;
+    const int key = tx * 64 + epb * 4096 * 64 + (int)(smem / 64) % 64 + a.L.ld;
+    if (key != cached_key) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_blocks, kern, tx * epb, smem);
+        if (cached_blocks < 1) cached_blocks = 1;
+        cached_key = key;
+    }
+    const int64_t ngroups = (a.ne + epb - 1) / epb;
     dim3 block(tx, epb);
-    dim3 grid((unsigned)((a.ne + epb - 1) / epb));
-    apply_kernel<DIM><<<grid, block, smem, st>>>(a);
+    dim3 grid((unsigned)std::min<int64_t>(ngroups, (int64_t)sms * cached_blocks));
+    kern<<<grid, block, smem, st>>>(a);
     return 1;
 }
 
@@ -270,57 +394,56 @@ int launch_apply_constraint(int, const LevelView& L, int64_t ne, const uint16_t*
 // ------------------------------------------------------------------------------------------
 // K4: restriction / interpolation (column-local, lattice form)
 // ------------------------------------------------------------------------------------------
-template <int DIM>
-__global__ void __launch_bounds__(256) restrict_kernel(const LevelView Lf, const LevelView Lc, int64_t ne,
+// table-driven, one CTA per group of elements, 32-bit index arithmetic
+template <int NDIR>
+__global__ void __launch_bounds__(256) restrict_kernel(const LevelView Lf, const LevelView Lc, int64_t ne, int epb,
                                                        const double* __restrict__ rf, double* __restrict__ bc) {
-    using D = Dims<DIM>;
-    const int64_t total = ne * Lc.nf;
-    const int mf = Lf.m;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t e = t / Lc.nf;
-        const int pc = (int)(t - e * Lc.nf);
-        const uint32_t info = Lc.nodeinfo[pc];
-        const int i = 2 * (info & 255), j = 2 * ((info >> 8) & 255), k = 2 * ((info >> 16) & 255);
-        const int pf = DIM == 3 ? d_pack3(mf, i, j, k) : d_pack2(mf, i, j);
-        int off[D::NDIR];
-        neighbour_offsets<DIM>(mf, i, j, off);
-        const double* r = rf + e * Lf.ld + pf;
+    const int64_t e0 = (int64_t)blockIdx.x * epb;
+    const int nel = (int)min((int64_t)epb, ne - e0);
+    const int nfc = Lc.nf, total = nel * nfc;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int el = idx / nfc, pc = idx - el * nfc;
+        const uint16_t* tab = Lf.restrict_tab + pc * NDIR;
+        const double* r = rf + (e0 + el) * Lf.ld;
         double s = 0.0;
 #pragma unroll
-        for (int d = 1; d < D::NDIR; ++d) {
-            if (neighbour_inside<DIM>(mf, i, j, k, d)) s += r[off[d]];
+        for (int d = 1; d < NDIR; ++d) {
+            const unsigned q = __ldg(tab + d);
+            if (q != 0xFFFFu) s += r[q];
         }
-        bc[e * Lc.ld + pc] = r[0] + 0.5 * s;
+        bc[(e0 + el) * Lc.ld + pc] = r[__ldg(tab)] + 0.5 * s;
     }
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(256) interp_kernel(const LevelView Lf, const LevelView Lc, int64_t ne,
+__global__ void __launch_bounds__(256) interp_kernel(const LevelView Lf, const LevelView Lc, int64_t ne, int epb,
                                                      double* __restrict__ xf, const double* __restrict__ xc) {
-    const int64_t total = ne * Lf.nf;
-    const int mc = Lc.m;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t e = t / Lf.nf;
-        const int p = (int)(t - e * Lf.nf);
-        const uint32_t info = Lf.nodeinfo[p];
-        const int i = info & 255, j = (info >> 8) & 255, k = (info >> 16) & 255;
-        const double* c = xc + e * Lc.ld;
-        int pa, pb;
-        const double add = interp_parents<DIM>(mc, i, j, k, pa, pb) == 1 ? c[pa] : 0.5 * c[pa] + 0.5 * c[pb];
-        xf[e * Lf.ld + p] += add;
+    const int64_t e0 = (int64_t)blockIdx.x * epb;
+    const int nel = (int)min((int64_t)epb, ne - e0);
+    const int nff = Lf.nf, total = nel * nff;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int el = idx / nff, p = idx - el * nff;
+        const unsigned u = __ldg(Lf.interp_tab + p);
+        const double* c = xc + (e0 + el) * Lc.ld;
+        xf[(e0 + el) * Lf.ld + p] += 0.5 * c[u & 0xFFFFu] + 0.5 * c[u >> 16];
     }
 }
 
+static int elements_per_block(int nf) {
+    int epb = 4096 / (nf > 0 ? nf : 1);
+    return epb < 1 ? 1 : (epb > 64 ? 64 : epb);
+}
 int launch_restrict(int dim, const LevelView& Lf, const LevelView& Lc, int64_t ne, const double* rf, double* bc, cudaStream_t st) {
     if (ne == 0) return 0;
-    if (dim == 3) restrict_kernel<3><<<grid_for(ne * Lc.nf, 256), 256, 0, st>>>(Lf, Lc, ne, rf, bc);
-    else restrict_kernel<2><<<grid_for(ne * Lc.nf, 256), 256, 0, st>>>(Lf, Lc, ne, rf, bc);
+    const int epb = elements_per_block(Lc.nf);
+    const unsigned grid = (unsigned)((ne + epb - 1) / epb);
+    if (dim == 3) restrict_kernel<15><<<grid, 256, 0, st>>>(Lf, Lc, ne, epb, rf, bc);
+    else restrict_kernel<7><<<grid, 256, 0, st>>>(Lf, Lc, ne, epb, rf, bc);
     return 1;
 }
-int launch_interp_add(int dim, const LevelView& Lf, const LevelView& Lc, int64_t ne, double* xf, const double* xc, cudaStream_t st) {
+int launch_interp_add(int, const LevelView& Lf, const LevelView& Lc, int64_t ne, double* xf, const double* xc, cudaStream_t st) {
     if (ne == 0) return 0;
-    if (dim == 3) interp_kernel<3><<<grid_for(ne * Lf.nf, 256), 256, 0, st>>>(Lf, Lc, ne, xf, xc);
-    else interp_kernel<2><<<grid_for(ne * Lf.nf, 256), 256, 0, st>>>(Lf, Lc, ne, xf, xc);
+    const int epb = elements_per_block(Lf.nf);
+    interp_kernel<<<(unsigned)((ne + epb - 1) / epb), 256, 0, st>>>(Lf, Lc, ne, epb, xf, xc);
     return 1;
 }
 
@@ -385,6 +508,21 @@ __global__ void __launch_bounds__(256) dot_kernel(const Reducer R, const double*
     block_reduce_finish(s, R, post, slot);
 }
 
+// p = r ; rho = dot(r, r)   (src/multigrid.jl:53-54)
+__global__ void __launch_bounds__(256) copy_dot_kernel(const Reducer R, const double* __restrict__ r, double* __restrict__ p, int64_t n) {
+    double s = 0.0;
+    const int64_t n2 = n >> 1;
+    const double2* r2 = reinterpret_cast<const double2*>(r);
+    double2* p2 = reinterpret_cast<double2*>(p);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n2; t += (int64_t)gridDim.x * blockDim.x) {
+        const double2 v = r2[t];
+        p2[t] = v;
+        s = fma(v.x, v.x, s);
+        s = fma(v.y, v.y, s);
+    }
+    block_reduce_finish(s, R, POST_RHO, 0);
+}
+
 // x += alpha p ; r -= alpha Ap ; rsqr = dot(r, r) -> beta, rho   (src/multigrid.jl:64-68)
 __global__ void __launch_bounds__(256) cg_update_kernel(const Reducer R, double* __restrict__ x, const double* __restrict__ p,
                                                         double* __restrict__ r, const double* __restrict__ Ap, int64_t n) {
@@ -433,6 +571,10 @@ static const int kVecBlocks = 148 * 8;
 
 int launch_dot(const Reducer& R, const double* a, const double* b, int64_t n, int post, int slot, cudaStream_t st) {
     dot_kernel<<<grid_for(n / 2 + 1, 256, R.max_blocks), 256, 0, st>>>(R, a, b, n, post, slot);
+    return 1;
+}
+int launch_copy_dot(const Reducer& R, const double* r, double* p, int64_t n, cudaStream_t st) {
+    copy_dot_kernel<<<grid_for(n / 2 + 1, 256, R.max_blocks), 256, 0, st>>>(R, r, p, n);
     return 1;
 }
 int launch_cg_update(const Reducer& R, double* x, const double* p, double* r, const double* Ap, int64_t n, cudaStream_t st) {

@@ -14,7 +14,22 @@ struct LevelView {
     const uint32_t* boundary;   // [n_boundary] p | class<<14   (sorted by class)
     const double* G;            // [ncls][ndir][nc]
     const uint16_t* face_bary;  // [npf] a | b<<8
+    const uint16_t* iface_idx;  // paired-node packed indices: faces [4][npf], edges [6|3][npe], vertices
+    const uint32_t* interp_tab; // [nf] coarse parents pa | pb<<16 (levels >= 2)
+    const uint16_t* restrict_tab; // [nf(level-1)][ndir] fine indices, 0xFFFF = outside
+    const uint32_t* tasks;      // [ntasks][32] p | i<<14 | j<<22, 0xFFFFFFFF = empty lane
+    const uint8_t* task_cls;    // [ntasks] class of a uniform task, 255 = mixed
+    int ntasks, n_uniform;
     int vpos[4];                // packed lattice index of the reference vertices
+};
+
+// unified interface-cell tables for the fused apply + interface sum ("last arriver" per cell)
+struct FuseView {
+    int64_t nfaces, nedges, nverts;   // cell id ranges: [0,nfaces) faces, then edges, then vertices
+    const int64_t* cell_off;          // CSR over all cells
+    const int32_t* cell_own;          // element*8 + local id, ascending element
+    const int32_t* elem_cells;        // [ne][16], -1 = not shared
+    unsigned int* arrive;             // [ncells] arrival counters, zero between launches
 };
 
 struct TopoView {
@@ -35,6 +50,8 @@ struct ApplyArgs {
     const double* b;           // rhs for APPLY_RESIDUAL
     double alpha, lambda;
     int mode;
+    int fused;                 // 1: sum the interfaces inside the kernel (y becomes globally summed)
+    FuseView F;
 };
 
 // scalar slots on the device (no host round trip inside a V-cycle)
@@ -56,6 +73,7 @@ int launch_apply_constraint(int dim, const LevelView& L, int64_t ne, const uint1
 int launch_restrict(int dim, const LevelView& Lf, const LevelView& Lc, int64_t ne, const double* rf, double* bc, cudaStream_t st);
 int launch_interp_add(int dim, const LevelView& Lf, const LevelView& Lc, int64_t ne, double* xf, const double* xc, cudaStream_t st);
 int launch_dot(const Reducer& R, const double* a, const double* b, int64_t n, int post, int slot, cudaStream_t st);
+int launch_copy_dot(const Reducer& R, const double* r, double* p, int64_t n, cudaStream_t st);
 int launch_cg_update(const Reducer& R, double* x, const double* p, double* r, const double* Ap, int64_t n, cudaStream_t st);
 int launch_p_update(const Reducer& R, double* p, const double* r, int64_t n, cudaStream_t st);
 int launch_axpy(double alpha, const double* x, double* y, int64_t n, cudaStream_t st);

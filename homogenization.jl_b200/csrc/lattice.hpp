@@ -83,19 +83,32 @@ template <int DIM> HMG_HD int bary_to_packed(int m, const int* lv, const int* w,
     return DIM == 3 ? lat_pack3(m, lam[1], lam[2], lam[3]) : lat_pack2(m, lam[1], lam[2]);
 }
 
-// kind 0 = face (q indexes face_bary: a | b<<8), 1 = edge (q = weight on the 2nd vertex), 2 = vertex
+// kind 0 = face (ab = barycentric weights a | b<<8 on the face's first two vertices), 1 = edge
+// (q = weight on the edge's second vertex), 2 = vertex.  Written without indexed local arrays:
+// lattice coordinates (i, j, k) are the barycentric weights of local vertices 1, 2, 3.
 template <int DIM> HMG_HD int interface_node(int m, int kind, int lid, int q, unsigned ab) {
-    int lv[3] = {0, 0, 0}, w[3] = {0, 0, 0}, n;
-    if (kind == 0) {
-        face_vertices(lid, lv);
-        w[0] = ab & 255; w[1] = ab >> 8; w[2] = m - w[0] - w[1]; n = 3;
+    int i = 0, j = 0, k = 0;
+    if (kind == 0) {            // faces (0,1,2) (0,1,3) (0,2,3) (1,2,3)
+        const int w0 = ab & 255, w1 = ab >> 8, w2 = m - w0 - w1;
+        i = lid == 0 ? w1 : (lid == 1 ? w1 : (lid == 2 ? 0 : w0));
+        j = lid == 0 ? w2 : (lid == 1 ? 0 : w1);
+        k = lid == 0 ? 0 : w2;
     } else if (kind == 1) {
-        edge_vertices<DIM>(lid, lv);
-        w[0] = m - q; w[1] = q; n = 2;
+        const int w0 = m - q, w1 = q;
+        if (DIM == 3) {         // edges (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+            i = lid == 0 ? w1 : ((lid == 3 || lid == 4) ? w0 : 0);
+            j = lid == 1 ? w1 : (lid == 3 ? w1 : (lid == 5 ? w0 : 0));
+            k = lid == 2 ? w1 : ((lid == 4 || lid == 5) ? w1 : 0);
+        } else {                // edges (0,1) (0,2) (1,2)
+            i = lid == 0 ? w1 : (lid == 2 ? w0 : 0);
+            j = lid == 0 ? 0 : w1;
+        }
     } else {
-        lv[0] = lid; w[0] = m; n = 1;
+        i = lid == 1 ? m : 0;
+        j = lid == 2 ? m : 0;
+        k = lid == 3 ? m : 0;
     }
-    return bary_to_packed<DIM>(m, lv, w, n);
+    return DIM == 3 ? lat_pack3(m, i, j, k) : lat_pack2(m, i, j);
 }
 
 // interpolation parents of fine node (i, j, k): returns 1 (coincides with a coarse node) or 2

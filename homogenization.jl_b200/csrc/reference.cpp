@@ -14,6 +14,7 @@
 #include <numeric>
 
 #include "hmg_host.hpp"
+#include "lattice.hpp"
 
 namespace hmg {
 
@@ -217,6 +218,30 @@ RefElement build_reference(int dim, int nlevels) {
             for (int p = 0; p < L.nf; ++p)
                 if ((int)(L.nodeinfo[p] >> 24) == cls) L.boundary.push_back((uint32_t)p | ((uint32_t)cls << 14));
 
+        // warp tasks: full groups of 32 same-class nodes are uniform tasks, remainders are pooled
+        {
+            std::vector<std::vector<uint32_t>> by_cls(ref.ncls);
+            for (int p = 0; p < L.nf; ++p) {
+                uint32_t info = L.nodeinfo[p];
+                by_cls[info >> 24].push_back((uint32_t)p | ((info & 255u) << 14) | (((info >> 8) & 255u) << 22));
+            }
+            std::vector<uint32_t> pool;
+            for (int cls = 0; cls < ref.ncls; ++cls) {
+                const auto& v = by_cls[cls];
+                size_t full = v.size() / 32 * 32;
+                for (size_t q = 0; q < full; q += 32) {
+                    L.tasks.insert(L.tasks.end(), v.begin() + q, v.begin() + q + 32);
+                    L.task_cls.push_back((uint8_t)cls);
+                }
+                pool.insert(pool.end(), v.begin() + full, v.end());
+            }
+            L.n_uniform_tasks = (int)L.task_cls.size();
+            for (size_t q = 0; q < pool.size(); q += 32) {
+                for (size_t r = q; r < q + 32; ++r) L.tasks.push_back(r < pool.size() ? pool[r] : 0xFFFFFFFFu);
+                L.task_cls.push_back(255);
+            }
+        }
+
         // (2) integer stencil: acc[p][dir][c]
         const int ndir = ref.ndir, nc = ref.nc;
         std::vector<int> acc((size_t)L.nf * ndir * nc, 0);
@@ -283,7 +308,10 @@ RefElement build_reference(int dim, int nlevels) {
                 if (f == 0) first = seq;
                 HMG_CHECK(seq == first, "face-interior numbering is not consistent across reference faces");
             }
-            for (const auto& t : first) L.face_bary.push_back((uint16_t)(t[0] | (t[1] << 8)));
+            // the device enumerates face nodes lexicographically in (a, b) -- any fixed enumeration pairs
+            // the owners consistently once the sequences above agree -- for better memory locality
+            for (int a = 1; a <= m - 2; ++a)
+                for (int b = 1; a + b <= m - 1; ++b) L.face_bary.push_back((uint16_t)(a | (b << 8)));
             HMG_CHECK((int)L.face_bary.size() == (m - 1) * (m - 2) / 2, "unexpected face-interior count");
         }
         {
@@ -303,6 +331,46 @@ RefElement build_reference(int dim, int nlevels) {
                 HMG_CHECK((int)seq.size() == m - 1, "unexpected edge-interior count");
             }
             for (int v = 0; v < nv; ++v) HMG_CHECK(bary(v)[v] == m, "corner nodes are not the first rows");
+        }
+
+        // paired-node index table of the interface kernels
+        {
+            const int npf = (int)L.face_bary.size(), npe = m - 1;
+            const int nfl = dim == 3 ? 4 : 0, nel = dim == 3 ? 6 : 3;
+            for (int lf = 0; lf < nfl; ++lf)
+                for (int t = 0; t < npf; ++t)
+                    L.iface_idx.push_back((uint16_t)interface_node<3>(m, 0, lf, 0, L.face_bary[t]));
+            for (int le = 0; le < nel; ++le)
+                for (int t = 0; t < npe; ++t)
+                    L.iface_idx.push_back((uint16_t)(dim == 3 ? interface_node<3>(m, 1, le, t + 1, 0)
+                                                              : interface_node<2>(m, 1, le, t + 1, 0)));
+            for (int v = 0; v < nv; ++v)
+                L.iface_idx.push_back((uint16_t)(dim == 3 ? interface_node<3>(m, 2, v, 0, 0) : interface_node<2>(m, 2, v, 0, 0)));
+        }
+
+        // transfer tables towards the next coarser level (same index functions as everywhere else)
+        if (l >= 2) {
+            const RefLevel& C = ref.lv[l - 2];
+            L.interp_tab.resize(L.nf);
+            for (int p = 0; p < L.nf; ++p) {
+                const uint32_t info = L.nodeinfo[p];
+                const int i = info & 255, j = (info >> 8) & 255, k = (info >> 16) & 255;
+                int pa, pb;
+                if (dim == 3) interp_parents<3>(C.m, i, j, k, pa, pb); else interp_parents<2>(C.m, i, j, k, pa, pb);
+                L.interp_tab[p] = (uint32_t)pa | ((uint32_t)pb << 16);
+            }
+            L.restrict_tab.assign((size_t)C.nf * ref.ndir, 0xFFFF);
+            for (int pc = 0; pc < C.nf; ++pc) {
+                const uint32_t info = C.nodeinfo[pc];
+                const int i = 2 * (info & 255), j = 2 * ((info >> 8) & 255), k = 2 * ((info >> 16) & 255);
+                const int pf = dim == 3 ? lat_pack3(m, i, j, k) : lat_pack2(m, i, j);
+                int off[NDIR3];
+                if (dim == 3) neighbour_offsets<3>(m, i, j, off); else neighbour_offsets<2>(m, i, j, off);
+                for (int d = 0; d < ref.ndir; ++d) {
+                    const bool in = dim == 3 ? neighbour_inside<3>(m, i, j, k, d) : neighbour_inside<2>(m, i, j, k, d);
+                    if (in) L.restrict_tab[(size_t)pc * ref.ndir + d] = (uint16_t)(pf + off[d]);
+                }
+            }
         }
 
         if (l == nlevels) break;

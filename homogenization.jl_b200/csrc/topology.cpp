@@ -101,6 +101,25 @@ Topology build_topology(int dim, int64_t ne, int64_t nn, const int64_t* elems) {
     T.edges = interface_map(edges);
     T.faces = interface_map(faces);
 
+    // unified cell numbering + per-element cell table (used by the fused apply / interface kernel)
+    {
+        T.cell_off.push_back(0);
+        T.elem_cells.assign((size_t)ne * 16, -1);
+        const CellMap* maps[3] = {&T.faces, &T.edges, &T.verts};
+        const int slot0[3] = {0, dim == 3 ? 4 : 0, dim == 3 ? 10 : 3};
+        for (int kind = dim == 3 ? 0 : 1; kind < 3; ++kind) {
+            const CellMap& m = *maps[kind];
+            for (int64_t c = 0; c < m.ncells(); ++c) {
+                const int32_t id = (int32_t)(T.cell_off.size() - 1);
+                for (int64_t o = m.offset[c]; o < m.offset[c + 1]; ++o) {
+                    T.cell_own.push_back(m.owner[o]);
+                    T.elem_cells[(size_t)(m.owner[o] >> 3) * 16 + slot0[kind] + (m.owner[o] & 7)] = id;
+                }
+                T.cell_off.push_back((int64_t)T.cell_own.size());
+            }
+        }
+    }
+
     // all_nodes map
     T.node_first.assign(nn, -1);
     T.nodeown_off.assign(nn + 1, 0);

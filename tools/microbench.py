@@ -1,0 +1,48 @@
+"""Device-timed micro-benchmarks of the library operations (development helper).
+
+    python tools/microbench.py DIM CELLS LEVELS [reps]
+ops: 0 fused global product, 3 apply only (y = A x + Dirichlet), 4 interface kernel only, 2 mul! (y += A x),
+1 V-cycle.  Prints ms, GDOF/s and the 16 B/DOF HBM fraction of the measured peak."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import hmgb200 as hmg
+
+
+def main():
+    dim, c, levels = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+    reps = int(sys.argv[4]) if len(sys.argv) > 4 else 20
+    peak = 6541.8
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    mesh, sigma = hmg.inputs.checkerboard_problem(dim, c)
+    g = hmg.ImplicitFineGrid(mesh, levels, sigma, lam=1.0)
+    nf = g.nf(levels)
+    dofs = nf * mesh.nelements
+    rng = np.random.default_rng(0)
+    st = g.state(levels)
+    x = np.asfortranarray(rng.random((nf, mesh.nelements)))
+    st.x.set(x); st.b.set(x); st.p.set(x)
+    hmg.broadcast_interfaces(st.p, g, levels)
+    out = {"dim": dim, "c": c, "levels": levels, "dofs": dofs, "regs": os.environ.get("HMG_APPLY_REGS", "64")}
+    for op, name in ((3, "apply"), (4, "interface"), (0, "fused_product"), (2, "mul")):
+        g.time_op(op, levels, 0, 3)
+        ms = g.time_op(op, levels, 0, reps) / reps
+        out[name] = {"ms": round(ms, 4), "gdofs": round(dofs / ms / 1e6, 2), "hbm16_frac": round(16 * dofs / ms / 1e6 / peak, 3)}
+    if len(sys.argv) > 5 and sys.argv[5] == "v":
+        bl = hmg.BaseLevel(g)
+        g.time_op(1, levels, 3, 2)
+        ms = g.time_op(1, levels, 3, 5) / 5
+        out["vcycle"] = {"ms": round(ms, 3), "gdofs": round(dofs / ms / 1e6, 3)}
+    print(json.dumps(out))
+    g.close()
+
+
+if __name__ == "__main__":
+    main()
