@@ -23,6 +23,7 @@ PROTOTYPES = {
     "hmg_nf": (_i64, [_p, _i32]),
     "hmg_ne_local": (_i64, [_p]),
     "hmg_ld": (_i64, [_p, _i32]),
+    "hmg_group_width": (_i32, [_p]),
     "hmg_local_elements": (_i32, [_p, _p]),
     "hmg_set_lambda": (_i32, [_p, _f64]),
     "hmg_set_sigma": (_i32, [_p, _p]),
@@ -70,6 +71,7 @@ HOST_PROTOTYPES = {
     "hmg_host_boundary": (_i32, [_i32, _i64, _i64, _p, _p, _p]),
     "hmg_host_class_of": (_i32, [_i32, _i32, _i32]),
     "hmg_host_element_coefficients": (_i32, [_i32, _i64, _i64, _p, _p, _p, _p, _i32]),
+    "hmg_host_apply_plan": (_i32, [_i32, _i32, _i32, _i32, _p, _p, _p, _p]),
 }
 
 _lib = None

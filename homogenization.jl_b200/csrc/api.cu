@@ -35,6 +35,9 @@ thread_local std::string g_err;
 
 struct LevelDev {
     LevelView view{};
+    ApplyPlanView plan{};
+    int plan_ctas = 1;
+    size_t plan_smem = 0;
     int32_t* hier2lat = nullptr;
     double* vec[HMG_NVEC] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -45,6 +48,8 @@ struct hmg_ctx {
     int dim = 0, nlevels = 0, device = 0;
     int rank = 0, nranks = 1;
     int64_t ne = 0, ne_global = 0, nn = 0;
+    int W = 16, wshift = 4;              // elements per unit of the interleaved device layout
+    int64_t nunits = 0;
     double lambda = 1.0;
     cudaStream_t stream = nullptr;
     RefElement ref;
@@ -54,9 +59,11 @@ struct hmg_ctx {
     std::vector<int64_t> local_to_global;
     std::vector<LevelDev> lv;
     TopoView tview{};
-    FuseView fview{};
-    double* elem_coef = nullptr;
-    uint16_t* cmask = nullptr;
+    double* elem_coef = nullptr;         // [nunits][CS][W]
+    std::vector<double> elem_coef_host;  // [ne][CS]
+    uint16_t* cmask = nullptr;           // [nunits * W]
+    int32_t* belems = nullptr;           // elements touching the domain boundary
+    int64_t nbelems = 0;
     int32_t* node_first = nullptr;
     int32_t* elems32 = nullptr;
     Reducer red{};
@@ -97,10 +104,11 @@ struct hmg_ctx {
     double* vecp(int l, int which) {
         HMG_CHECK(which >= 0 && which < HMG_NVEC, "unknown state vector id");
         LevelDev& L = level(l);
-        if (!L.vec[which]) L.vec[which] = dalloc<double>((size_t)L.view.ld * ne);   // scratch vectors are lazy
+        if (!L.vec[which]) L.vec[which] = dalloc<double>((size_t)nstored(l));   // scratch vectors are lazy
         return L.vec[which];
     }
-    int64_t nstored(int l) { return (int64_t)level(l).view.ld * ne; }
+    // stored entries of a level vector including the zero columns that pad the last unit
+    int64_t nstored(int l) { return (int64_t)level(l).view.nf * W * nunits; }
 };
 
 namespace {
@@ -112,10 +120,13 @@ void check_launch(hmg_ctx* c, int n) {
 
 void upload_operator(hmg_ctx* c, const double* sigma) {
     const int cs = c->dim == 3 ? 8 : 4;
-    std::vector<double> coef;
-    element_coefficients(c->dim, c->ne, c->nodes.data(), c->elems.data(), sigma, coef, cs);
-    if (!c->elem_coef) c->elem_coef = c->dalloc<double>(coef.size(), false);
-    CUDA_OK(cudaMemcpyAsync(c->elem_coef, coef.data(), coef.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    element_coefficients(c->dim, c->ne, c->nodes.data(), c->elems.data(), sigma, c->elem_coef_host, cs);
+    const int W = c->W;
+    std::vector<double> inter((size_t)c->nunits * cs * W, 0.0);     // [unit][component][lane]
+    for (int64_t e = 0; e < c->ne; ++e)
+        for (int q = 0; q < cs; ++q) inter[((size_t)(e / W) * cs + q) * W + e % W] = c->elem_coef_host[(size_t)e * cs + q];
+    if (!c->elem_coef) c->elem_coef = c->dalloc<double>(inter.size(), false);
+    CUDA_OK(cudaMemcpyAsync(c->elem_coef, inter.data(), inter.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
 }
 
@@ -149,6 +160,11 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne, int64_t nn, const double*
 
     c->ref = build_reference(dim, nlevels);
     c->topo = build_topology(dim, ne, nn, c->elems.data());
+    // interleave width: 16 elements per unit; the largest 3D level needs 8 to fit its planes in the ring
+    c->W = (dim == 3 && nlevels >= 6) ? 8 : 16;
+    if (const char* w = getenv("HMG_GROUP_WIDTH")) { const int v = atoi(w); if (v == 8 || v == 16) c->W = v; }
+    c->wshift = c->W == 16 ? 4 : 3;
+    c->nunits = (ne + c->W - 1) / c->W;
 
     // per-level tables and state vectors
     c->lv.resize(nlevels);
@@ -156,46 +172,63 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne, int64_t nn, const double*
         const RefLevel& R = c->ref.lv[l - 1];
         LevelDev& L = c->lv[l - 1];
         LevelView& V = L.view;
-        V.m = R.m; V.nf = R.nf; V.ld = R.ld;
-        V.n_interior = (int)R.interior.size();
+        V.m = R.m; V.nf = R.nf;
+        V.W = c->W; V.wshift = c->wshift;
         V.n_boundary = (int)R.boundary.size();
         V.npf = dim == 3 ? (int)R.face_bary.size() : 0;
         V.npe = R.m - 1;
         V.nodeinfo = c->dupload(R.nodeinfo);
-        V.interior = c->dupload(R.interior);
         V.boundary = c->dupload(R.boundary);
         V.G = c->dupload(R.G);
-        V.face_bary = c->dupload(R.face_bary);
         V.iface_idx = c->dupload(R.iface_idx);
         V.interp_tab = c->dupload(R.interp_tab);
         V.restrict_tab = c->dupload(R.restrict_tab);
-        V.tasks = c->dupload(R.tasks);
-        V.task_cls = c->dupload(R.task_cls);
-        V.ntasks = (int)R.task_cls.size();
-        V.n_uniform = R.n_uniform_tasks;
         for (int v = 0; v < 4; ++v) V.vpos[v] = v < nv ? R.hier2lat[v] : 0;
         L.hier2lat = c->dupload(R.hier2lat);
-        for (int w = 0; w <= HMG_AP; ++w) L.vec[w] = c->dalloc<double>((size_t)V.ld * ne);
+        const ApplyPlan plan = build_apply_plan(dim, R, c->W);
+        L.plan.nchunks = plan.nchunks; L.plan.nslots = plan.nslots;
+        L.plan.slot_doubles = plan.slot_nodes * c->W; L.plan.zero_doubles = plan.zero_nodes * c->W;
+        L.plan.ntasks = plan.ntasks; L.plan.nwarps = plan.nwarps;
+        L.plan.chunk_start = c->dupload(plan.chunk_start);
+        L.plan.tasks = c->dupload(plan.tasks);
+        L.plan.nodetab = c->dupload(plan.nodetab);
+        L.plan_ctas = plan.ctas_per_sm;
+        L.plan_smem = plan.smem_bytes;
+        for (int w = 0; w <= HMG_AP; ++w) L.vec[w] = c->dalloc<double>((size_t)V.nf * c->W * c->nunits);
     }
     // topology
     const Topology& T = c->topo;
-    c->tview.nfaces = T.faces.ncells();
-    c->tview.nedges = T.edges.ncells();
-    c->tview.nverts = T.verts.ncells();
-    c->tview.face_off = c->dupload(T.faces.offset);
-    c->tview.face_own = c->dupload(T.faces.owner);
-    c->tview.edge_off = c->dupload(T.edges.offset);
-    c->tview.edge_own = c->dupload(T.edges.owner);
-    c->tview.vert_off = c->dupload(T.verts.offset);
-    c->tview.vert_own = c->dupload(T.verts.owner);
-    c->fview.nfaces = T.faces.ncells();
-    c->fview.nedges = T.edges.ncells();
-    c->fview.nverts = T.verts.ncells();
-    c->fview.cell_off = c->dupload(T.cell_off);
-    c->fview.cell_own = c->dupload(T.cell_own);
-    c->fview.elem_cells = c->dupload(T.elem_cells);
-    c->fview.arrive = c->dalloc<unsigned int>(T.cell_off.size());
-    c->cmask = c->dupload(T.cmask);
+    {
+        const CellMap& pairs = dim == 3 ? T.faces : T.edges;     // codimension-1 cells: exactly two owners
+        std::vector<int32_t> partner((size_t)ne * 4, -1);
+        for (int64_t q = 0; q < pairs.ncells(); ++q) {
+            HMG_CHECK(pairs.offset[q + 1] - pairs.offset[q] == 2, "a face of the base mesh is shared by more than two elements");
+            const int32_t a = pairs.owner[pairs.offset[q]], b = pairs.owner[pairs.offset[q] + 1];
+            partner[(size_t)(a >> 3) * 4 + (a & 7)] = b;
+            partner[(size_t)(b >> 3) * 4 + (b & 7)] = a;
+        }
+        c->tview.ne = ne;
+        c->tview.partner = c->dupload(partner);
+        static const std::vector<int64_t> empty_off(1, 0);
+        static const std::vector<int32_t> empty_own;
+        c->tview.nedges = dim == 3 ? T.edges.ncells() : 0;
+        c->tview.edge_off = c->dupload(dim == 3 ? T.edges.offset : empty_off);
+        c->tview.edge_own = c->dupload(dim == 3 ? T.edges.owner : empty_own);
+        c->tview.nverts = T.verts.ncells();
+        c->tview.vert_off = c->dupload(T.verts.offset);
+        c->tview.vert_own = c->dupload(T.verts.owner);
+    }
+    {
+        std::vector<uint16_t> cm((size_t)c->nunits * c->W, 0);
+        std::vector<int32_t> be;
+        for (int64_t e = 0; e < ne; ++e) {
+            cm[e] = T.cmask[e];
+            if (T.cmask[e]) be.push_back((int32_t)e);
+        }
+        c->cmask = c->dupload(cm);
+        c->nbelems = (int64_t)be.size();
+        c->belems = c->dupload(be);
+    }
     c->node_first = c->dupload(T.node_first);
     std::vector<int32_t> e32(c->elems.begin(), c->elems.end());
     c->elems32 = c->dupload(e32);
@@ -211,19 +244,18 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne, int64_t nn, const double*
 }
 
 // ---- building blocks ---------------------------------------------------------------------
-void do_apply(hmg_ctx* c, int l, int mode, double alpha, const double* x, double* y, const double* b,
-              bool fused = false) {
+void do_apply(hmg_ctx* c, int l, int mode, double alpha, const double* x, double* y, const double* b) {
+    LevelDev& L = c->level(l);
     ApplyArgs a;
-    a.fused = fused ? 1 : 0;
-    a.F = c->fview;
-    a.L = c->level(l).view;
-    a.ne = c->ne;
-    a.elem_coef = c->elem_coef;
+    a.L = L.view;
+    a.P = L.plan;
+    a.nunits = c->nunits;
+    a.coef = c->elem_coef;
     a.cmask = c->cmask;
     a.x = x; a.y = y; a.b = b;
     a.alpha = alpha; a.lambda = c->lambda;
     a.mode = mode;
-    check_launch(c, launch_apply(c->dim, a, c->stream));
+    check_launch(c, launch_apply(c->dim, a, L.plan_ctas, L.plan_smem, c->stream));
 }
 void do_broadcast(hmg_ctx* c, int l, double* x) {
     check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->stream));
@@ -231,14 +263,19 @@ void do_broadcast(hmg_ctx* c, int l, double* x) {
 void do_local_residual(hmg_ctx* c, int l) {
     do_apply(c, l, APPLY_RESIDUAL, 1.0, c->vecp(l, HMG_X), c->vecp(l, HMG_R), c->vecp(l, HMG_B));
 }
+void do_global_product(hmg_ctx* c, int l, const double* x, double* y) {
+    do_apply(c, l, APPLY_AX, 1.0, x, y, nullptr);      // y = constraint(A x), column-local
+    do_broadcast(c, l, y);                             // interface sums
+}
 void do_smoothing(hmg_ctx* c, int l, int steps) {
     const int64_t n = c->nstored(l);
     double *x = c->vecp(l, HMG_X), *r = c->vecp(l, HMG_R), *p = c->vecp(l, HMG_P), *Ap = c->vecp(l, HMG_AP);
-    // r = broadcast(constraint(b - A x)) in one kernel; p = r and rho = r.r in one pass
-    do_apply(c, l, APPLY_RESIDUAL, 1.0, x, r, c->vecp(l, HMG_B), true);
+    // r = broadcast(constraint(b - A x)); p = r and rho = r.r in one pass
+    do_apply(c, l, APPLY_RESIDUAL, 1.0, x, r, c->vecp(l, HMG_B));
+    do_broadcast(c, l, r);
     check_launch(c, launch_copy_dot(c->red, r, p, n, c->stream));
     for (int i = 0; i < steps; ++i) {
-        do_apply(c, l, APPLY_AX, 1.0, p, Ap, nullptr, true);          // Ap = broadcast(constraint(A p))
+        do_global_product(c, l, p, Ap);                               // Ap = broadcast(constraint(A p))
         check_launch(c, launch_dot(c->red, p, Ap, n, POST_PAP, 0, c->stream));
         check_launch(c, launch_cg_update(c->red, x, p, r, Ap, n, c->stream));
         // the reference also updates p after the last step, but that value is never used
@@ -261,11 +298,11 @@ void do_vcycle(hmg_ctx* c, int k, int steps) {
     if (k == 1) { do_coarse_solve(c); return; }
     do_smoothing(c, k, steps);
     do_local_residual(c, k);
-    check_launch(c, launch_restrict(c->dim, c->level(k).view, c->level(k - 1).view, c->ne, c->vecp(k, HMG_R),
+    check_launch(c, launch_restrict(c->dim, c->level(k).view, c->level(k - 1).view, c->nunits, c->vecp(k, HMG_R),
                                     c->vecp(k - 1, HMG_B), c->stream));
     check_launch(c, launch_fill(c->vecp(k - 1, HMG_X), 0.0, c->nstored(k - 1), c->stream));
     do_vcycle(c, k - 1, 2);   // the reference does not forward `steps` (src/multigrid.jl:109)
-    check_launch(c, launch_interp_add(c->dim, c->level(k).view, c->level(k - 1).view, c->ne, c->vecp(k, HMG_X),
+    check_launch(c, launch_interp_add(c->dim, c->level(k).view, c->level(k - 1).view, c->nunits, c->vecp(k, HMG_X),
                                       c->vecp(k - 1, HMG_X), c->stream));
     do_smoothing(c, k, steps);
 }
@@ -396,8 +433,9 @@ int64_t hmg_nf(const hmg_ctx* c, int level) {
 int64_t hmg_ne_local(const hmg_ctx* c) { return c ? c->ne : -1; }
 int64_t hmg_ld(const hmg_ctx* c, int level) {
     if (!c || level < 1 || level > c->nlevels) return -1;
-    return c->lv[level - 1].view.ld;
+    return c->lv[level - 1].view.nf;
 }
+int hmg_group_width(const hmg_ctx* c) { return c ? c->W : -1; }
 int hmg_local_elements(const hmg_ctx* c, int64_t* out) {
     HMG_API_BEGIN
     NEED_CTX(c);
@@ -434,7 +472,7 @@ int hmg_upload(hmg_ctx* c, int level, int which, const double* host, int64_t ld_
         const int64_t nc = std::min(chunk, c->ne - c0);
         CUDA_OK(cudaMemcpy2DAsync(c->staging, (size_t)nf * 8, host + c0 * ld_host, (size_t)ld_host * 8, (size_t)nf * 8,
                                   (size_t)nc, cudaMemcpyHostToDevice, c->stream));
-        check_launch(c, launch_permute_in(L.view, L.hier2lat, c->staging, nf, dst + c0 * L.view.ld, nc, c->stream));
+        check_launch(c, launch_permute_in(L.view, L.hier2lat, c->staging, nf, dst, c0, nc, c->stream));
     }
     CUDA_OK(cudaStreamSynchronize(c->stream));
     HMG_API_END
@@ -452,7 +490,7 @@ int hmg_download(hmg_ctx* c, int level, int which, double* host, int64_t ld_host
     ensure_staging(c, (size_t)chunk * nf * 8);
     for (int64_t c0 = 0; c0 < c->ne; c0 += chunk) {
         const int64_t nc = std::min(chunk, c->ne - c0);
-        check_launch(c, launch_permute_out(L.view, L.hier2lat, src + c0 * L.view.ld, c->staging, nf, nc, c->stream));
+        check_launch(c, launch_permute_out(L.view, L.hier2lat, src, c->staging, nf, c0, nc, c->stream));
         CUDA_OK(cudaMemcpy2DAsync(host + c0 * ld_host, (size_t)ld_host * 8, c->staging, (size_t)nf * 8, (size_t)nf * 8,
                                   (size_t)nc, cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -467,10 +505,8 @@ int hmg_fill(hmg_ctx* c, int level, int which, double value) {
     if (value == 0.0) {
         check_launch(c, launch_fill(c->vecp(level, which), 0.0, c->nstored(level), c->stream));
     } else {
-        // pads must stay zero: fill column by column
-        LevelDev& L = c->level(level);
-        double* v = c->vecp(level, which);
-        for (int64_t e = 0; e < c->ne; ++e) check_launch(c, launch_fill(v + e * L.view.ld, value, L.view.nf, c->stream));
+        // the zero columns padding the last unit must stay zero
+        check_launch(c, launch_fill_columns(c->level(level).view, c->ne, c->vecp(level, which), value, c->stream));
     }
     HMG_API_END
 }
@@ -511,14 +547,15 @@ int hmg_apply_global(hmg_ctx* c, int level, int x, int y) {
     NEED_CTX(c);
     CUDA_OK(cudaSetDevice(c->device));
     HMG_CHECK(x != y, "apply: x and y must be different vectors");
-    do_apply(c, level, APPLY_AX, 1.0, c->vecp(level, x), c->vecp(level, y), nullptr, true);
+    do_global_product(c, level, c->vecp(level, x), c->vecp(level, y));
     HMG_API_END
 }
 int hmg_apply_constraint(hmg_ctx* c, int level, int which) {
     HMG_API_BEGIN
     NEED_CTX(c);
     CUDA_OK(cudaSetDevice(c->device));
-    check_launch(c, launch_apply_constraint(c->dim, c->level(level).view, c->ne, c->cmask, c->vecp(level, which), c->stream));
+    check_launch(c, launch_apply_constraint(c->dim, c->level(level).view, c->nbelems, c->belems, c->cmask,
+                                            c->vecp(level, which), c->stream));
     HMG_API_END
 }
 int hmg_broadcast_interfaces(hmg_ctx* c, int level, int which) {
@@ -547,7 +584,7 @@ int hmg_restrict(hmg_ctx* c, int k) {
     NEED_CTX(c);
     CUDA_OK(cudaSetDevice(c->device));
     HMG_CHECK(k >= 2 && k <= c->nlevels, "restrict: level must be in 2..nlevels");
-    check_launch(c, launch_restrict(c->dim, c->level(k).view, c->level(k - 1).view, c->ne, c->vecp(k, HMG_R),
+    check_launch(c, launch_restrict(c->dim, c->level(k).view, c->level(k - 1).view, c->nunits, c->vecp(k, HMG_R),
                                     c->vecp(k - 1, HMG_B), c->stream));
     HMG_API_END
 }
@@ -556,7 +593,7 @@ int hmg_interpolate_add(hmg_ctx* c, int k) {
     NEED_CTX(c);
     CUDA_OK(cudaSetDevice(c->device));
     HMG_CHECK(k >= 2 && k <= c->nlevels, "interpolate: level must be in 2..nlevels");
-    check_launch(c, launch_interp_add(c->dim, c->level(k).view, c->level(k - 1).view, c->ne, c->vecp(k, HMG_X),
+    check_launch(c, launch_interp_add(c->dim, c->level(k).view, c->level(k - 1).view, c->nunits, c->vecp(k, HMG_X),
                                       c->vecp(k - 1, HMG_X), c->stream));
     HMG_API_END
 }
@@ -592,8 +629,8 @@ int hmg_assemble_coarse(hmg_ctx* c) {
     CUDA_OK(cudaSetDevice(c->device));
     // P1 assembly of lambda*M + K(sigma) on the base mesh, restricted to the interior nodes
     const int dim = c->dim, nv = dim + 1, cs = dim == 3 ? 8 : 4, nc = dim == 3 ? 7 : 4;
-    std::vector<double> coef((size_t)c->ne * cs);
-    CUDA_OK(cudaMemcpy(coef.data(), c->elem_coef, coef.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    const std::vector<double>& coef = c->elem_coef_host;
+    HMG_CHECK(coef.size() == (size_t)c->ne * cs, "element coefficients missing");
     const std::vector<int64_t>& interior = c->topo.interior_nodes;
     const int64_t n = (int64_t)interior.size();
     HMG_CHECK(n > 0, "base mesh has no interior nodes");
@@ -736,7 +773,7 @@ int hmg_time_op(hmg_ctx* c, int op, int level, int steps, int reps, float* ms_ou
     CUDA_OK(cudaEventRecord(c->ev0, c->stream));
     for (int i = 0; i < reps; ++i) {
         if (op == 0) {
-            do_apply(c, level, APPLY_AX, 1.0, c->vecp(level, HMG_P), c->vecp(level, HMG_AP), nullptr, true);
+            do_global_product(c, level, c->vecp(level, HMG_P), c->vecp(level, HMG_AP));
         } else if (op == 1) {
             do_vcycle(c, level, steps);
         } else if (op == 2) {

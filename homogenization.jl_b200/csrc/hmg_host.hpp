@@ -45,17 +45,11 @@ constexpr int NCLS3 = 16, NCLS2 = 8;   // class = bitmask of reference faces the
 struct RefLevel {
     int m = 0;     // lattice size 2^(level-1)
     int nf = 0;    // nodes of the refined reference element
-    int ld = 0;    // padded leading dimension on the device
+    int ld = 0;    // = nf (kept for the introspection ABI; the device layout is element-interleaved)
     std::vector<int32_t> hier2lat;   // hierarchical row -> packed lattice index
     std::vector<uint32_t> nodeinfo;  // per packed index: i | j<<8 | k<<16 | class<<24
     std::vector<uint32_t> interior;  // interior nodes (class 0), packed p | i<<14 | j<<22
     std::vector<uint32_t> boundary;  // boundary nodes sorted by class, p | class<<14 ; (i,j,k) via nodeinfo
-    // warp tasks of the apply kernel: 32 entries (p | i<<14 | j<<22, or 0xFFFFFFFF) per task.
-    // Uniform tasks hold 32 nodes of ONE class (coefficients live in registers); the remainders of
-    // all classes are pooled into mixed tasks (class looked up per lane).  Uniform tasks come first.
-    std::vector<uint32_t> tasks;
-    std::vector<uint8_t> task_cls;   // class of a uniform task, 255 = mixed
-    int n_uniform_tasks = 0;
     // transfer tables between this level (fine) and the next coarser one (levels >= 2):
     std::vector<uint32_t> interp_tab;   // per fine node: coarse parents pa | pb<<16 (pa == pb: coincident)
     std::vector<uint16_t> restrict_tab; // per coarse node: [ndir] fine indices (centre first), 0xFFFF = outside
@@ -74,6 +68,43 @@ struct RefElement {
 };
 
 RefElement build_reference(int dim, int nlevels);
+
+// ---- streaming plan of the apply kernel (plan.cpp) ---------------------------------------
+// Device vectors are ELEMENT-INTERLEAVED: W consecutive coarse elements form a group ("unit"),
+// entry (element e, packed node p) lives at ((e / W) * nf + p) * W + e % W.  A warp lane is an
+// element, so every stencil access of a warp is one coalesced, bank-conflict-free line and the
+// control flow (node class, neighbour offsets) is warp-uniform.  A unit is streamed through shared
+// memory in CHUNKS (whole lattice planes i = const, merged when tiny) by TMA bulk copies into a
+// ring of slots; warps consume TASKS that only need chunks clo..chi (at most 3 consecutive).
+constexpr int PLAN_SLOT_INTS = 12;
+constexpr int PLAN_TASK_INTS = 4 + 4 * PLAN_SLOT_INTS;
+enum PlanTaskType { TASK_SWEEP_INTERIOR = 0, TASK_SWEEP_FACE_A = 1, TASK_SWEEP_FACE_B = 2, TASK_NODES = 3 };
+
+struct ApplyPlan {
+    int W = 16;            // elements per unit (lanes per row slot)
+    int spw = 2;           // row slots per warp = 32 / W
+    int nchunks = 0;       // chunks per unit
+    int nslots = 0;        // ring slots
+    int slot_nodes = 0;    // nodes per slot (largest chunk + slack)
+    int zero_nodes = 0;    // nodes of the zero line in front of the ring
+    int nwarps = 8;        // consumer warps per CTA (one more warp produces)
+    int ctas_per_sm = 1;
+    int ntasks = 0;
+    size_t smem_bytes = 0;
+    std::vector<int32_t> chunk_start;   // [nchunks + 1] packed node offsets
+    // task t: [type, clo, chi, 0] + 4 slots x 12 ints.
+    //  sweep slot: [0] centre ref, [1..3] "minus" line refs, [4..6] "plus" line refs, [7] count,
+    //              [8] packed index of the first node, [9] flags (1: first node is a face end, 2: last)
+    //  node slot:  [0] index into nodetab (-1: idle)
+    //  ref = (chunk - clo) << 28 | node offset inside the chunk; (3 << 28 | 1) = the zero line
+    std::vector<int32_t> tasks;
+    // special nodes (edge / vertex classes): [0] centre ref, [d] ref of neighbour d (0xFFFFFFFF outside),
+    // [15] packed index | class << 16; refs relative to the chunk of plane max(i - 1, 0)
+    std::vector<uint32_t> nodetab;
+};
+ApplyPlan build_apply_plan(int dim, const RefLevel& L, int W);
+// single-face classes derive their coefficients from the interior ones: weight of direction d
+double face_weight(int dim, int cls, int d);
 
 // ---- base-mesh topology ---------------------------------------------------------------
 struct CellMap {                     // CSR cell -> (element, local id), owners ascending

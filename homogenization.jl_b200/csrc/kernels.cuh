@@ -1,4 +1,11 @@
 // Device-side parameter blocks and launcher declarations of libhmg_b200 (sm_100a only).
+//
+// Device layout of every state vector ("element-interleaved"): W consecutive coarse elements form
+// a unit; entry (element e, packed lattice node p) of a level with nf nodes lives at
+//     ((e / W) * nf + p) * W + e % W .
+// The last unit is padded with zero columns.  A warp lane therefore IS a coarse element: node
+// class, neighbour offsets and transfer tables are warp-uniform and every access is one coalesced
+// 64/128-byte line.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -7,51 +14,46 @@ namespace hmg {
 
 // ---- per-level device view -------------------------------------------------------------
 struct LevelView {
-    int m, nf, ld;
-    int n_interior, n_boundary, npf, npe;
+    int m, nf;
+    int W, wshift;              // elements per unit, log2
+    int n_boundary, npf, npe;
     const uint32_t* nodeinfo;   // [nf]   i | j<<8 | k<<16 | class<<24   (lattice order)
-    const uint32_t* interior;   // [n_interior] p | i<<14 | j<<22
     const uint32_t* boundary;   // [n_boundary] p | class<<14   (sorted by class)
     const double* G;            // [ncls][ndir][nc]
-    const uint16_t* face_bary;  // [npf] a | b<<8
     const uint16_t* iface_idx;  // paired-node packed indices: faces [4][npf], edges [6|3][npe], vertices
     const uint32_t* interp_tab; // [nf] coarse parents pa | pb<<16 (levels >= 2)
     const uint16_t* restrict_tab; // [nf(level-1)][ndir] fine indices, 0xFFFF = outside
-    const uint32_t* tasks;      // [ntasks][32] p | i<<14 | j<<22, 0xFFFFFFFF = empty lane
-    const uint8_t* task_cls;    // [ntasks] class of a uniform task, 255 = mixed
-    int ntasks, n_uniform;
     int vpos[4];                // packed lattice index of the reference vertices
 };
 
-// unified interface-cell tables for the fused apply + interface sum ("last arriver" per cell)
-struct FuseView {
-    int64_t nfaces, nedges, nverts;   // cell id ranges: [0,nfaces) faces, then edges, then vertices
-    const int64_t* cell_off;          // CSR over all cells
-    const int32_t* cell_own;          // element*8 + local id, ascending element
-    const int32_t* elem_cells;        // [ne][16], -1 = not shared
-    unsigned int* arrive;             // [ncells] arrival counters, zero between launches
+struct ApplyPlanView {
+    int nchunks, nslots, slot_doubles, zero_doubles, ntasks, nwarps;
+    const int32_t* chunk_start;  // [nchunks + 1]
+    const int32_t* tasks;        // [ntasks][PLAN_TASK_INTS]
+    const uint32_t* nodetab;     // [nspecial][16]
 };
 
 struct TopoView {
-    int64_t nfaces, nedges, nverts;
-    const int64_t *face_off, *edge_off, *vert_off;
-    const int32_t *face_own, *edge_own, *vert_own;   // element*8 + local id
+    int64_t ne;
+    int64_t nedges, nverts;                 // multi-owner cells handled cell by cell (3D: edges + vertices, 2D: vertices)
+    const int64_t *edge_off, *vert_off;
+    const int32_t *edge_own, *vert_own;     // element*8 + local id, ascending element
+    const int32_t* partner;                 // [ne][4]: other owner (element*8 + local id) of local face (3D) / edge (2D), -1 none
 };
 
 enum ApplyMode { APPLY_AX = 0, APPLY_RESIDUAL = 1, APPLY_MULADD = 2 };
 
 struct ApplyArgs {
     LevelView L;
-    int64_t ne;
-    const double* elem_coef;   // [ne][CS]
-    const uint16_t* cmask;     // [ne]
-    const double* x;           // input  (ld x ne)
+    ApplyPlanView P;
+    int64_t nunits;
+    const double* coef;        // [nunits][CS][W]  |J| P (upper triangle) and |J|, element-interleaved
+    const uint16_t* cmask;     // [nunits * W]
+    const double* x;           // input
     double* y;                 // output
     const double* b;           // rhs for APPLY_RESIDUAL
     double alpha, lambda;
     int mode;
-    int fused;                 // 1: sum the interfaces inside the kernel (y becomes globally summed)
-    FuseView F;
 };
 
 // scalar slots on the device (no host round trip inside a V-cycle)
@@ -66,20 +68,25 @@ struct Reducer {
 };
 
 // launchers (all asynchronous on `st`); return the number of kernels launched
-int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st);
+int launch_apply(int dim, const ApplyArgs& a, int ctas_per_sm, size_t smem_bytes, cudaStream_t st);
 int launch_interface_sum(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
 int launch_zero_all_but_one(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
-int launch_apply_constraint(int dim, const LevelView& L, int64_t ne, const uint16_t* cmask, double* x, cudaStream_t st);
-int launch_restrict(int dim, const LevelView& Lf, const LevelView& Lc, int64_t ne, const double* rf, double* bc, cudaStream_t st);
-int launch_interp_add(int dim, const LevelView& Lf, const LevelView& Lc, int64_t ne, double* xf, const double* xc, cudaStream_t st);
+int launch_apply_constraint(int dim, const LevelView& L, int64_t nbelems, const int32_t* belems, const uint16_t* cmask,
+                            double* x, cudaStream_t st);
+int launch_restrict(int dim, const LevelView& Lf, const LevelView& Lc, int64_t nunits, const double* rf, double* bc, cudaStream_t st);
+int launch_interp_add(int dim, const LevelView& Lf, const LevelView& Lc, int64_t nunits, double* xf, const double* xc, cudaStream_t st);
 int launch_dot(const Reducer& R, const double* a, const double* b, int64_t n, int post, int slot, cudaStream_t st);
 int launch_copy_dot(const Reducer& R, const double* r, double* p, int64_t n, cudaStream_t st);
 int launch_cg_update(const Reducer& R, double* x, const double* p, double* r, const double* Ap, int64_t n, cudaStream_t st);
 int launch_p_update(const Reducer& R, double* p, const double* r, int64_t n, cudaStream_t st);
 int launch_axpy(double alpha, const double* x, double* y, int64_t n, cudaStream_t st);
 int launch_fill(double* x, double v, int64_t n, cudaStream_t st);
-int launch_permute_in(const LevelView& L, const int32_t* hier2lat, const double* staged, int64_t ld_staged, double* dst, int64_t ncols, cudaStream_t st);
-int launch_permute_out(const LevelView& L, const int32_t* hier2lat, const double* src, double* staged, int64_t ld_staged, int64_t ncols, cudaStream_t st);
+int launch_fill_columns(const LevelView& L, int64_t ne, double* x, double v, cudaStream_t st);
+// host layout (hierarchical rows, Nf x ncols column-major) <-> device layout, columns e0 .. e0+ncols
+int launch_permute_in(const LevelView& L, const int32_t* hier2lat, const double* staged, int64_t ld_staged, double* dst,
+                      int64_t e0, int64_t ncols, cudaStream_t st);
+int launch_permute_out(const LevelView& L, const int32_t* hier2lat, const double* src, double* staged, int64_t ld_staged,
+                       int64_t e0, int64_t ncols, cudaStream_t st);
 // level 1 <-> base vector
 int launch_copy_to_base(const LevelView& L1, int64_t nn, const int32_t* node_first, const double* v, double* u, cudaStream_t st);
 int launch_distribute(int dim, const LevelView& L1, int64_t ne, const int32_t* elems, const double* u, double* v, cudaStream_t st);

@@ -188,7 +188,7 @@ RefElement build_reference(int dim, int nlevels) {
         L.nf = (int)mesh.nodes.size();
         HMG_CHECK(L.nf == (dim == 3 ? tot3(m) : tri(m)), "unexpected node count of the refined element");
         HMG_CHECK(L.nf < (1 << 14), "reference element too large for the packed node lists");
-        L.ld = L.nf >= 64 ? (L.nf + 15) / 16 * 16 : (L.nf + 1) / 2 * 2;
+        L.ld = L.nf;
 
         auto lat = [&](int n) -> I3 {
             const I3& c = mesh.nodes[n];
@@ -217,30 +217,6 @@ RefElement build_reference(int dim, int nlevels) {
         for (int cls = 1; cls < ref.ncls; ++cls)
             for (int p = 0; p < L.nf; ++p)
                 if ((int)(L.nodeinfo[p] >> 24) == cls) L.boundary.push_back((uint32_t)p | ((uint32_t)cls << 14));
-
-        // warp tasks: full groups of 32 same-class nodes are uniform tasks, remainders are pooled
-        {
-            std::vector<std::vector<uint32_t>> by_cls(ref.ncls);
-            for (int p = 0; p < L.nf; ++p) {
-                uint32_t info = L.nodeinfo[p];
-                by_cls[info >> 24].push_back((uint32_t)p | ((info & 255u) << 14) | (((info >> 8) & 255u) << 22));
-            }
-            std::vector<uint32_t> pool;
-            for (int cls = 0; cls < ref.ncls; ++cls) {
-                const auto& v = by_cls[cls];
-                size_t full = v.size() / 32 * 32;
-                for (size_t q = 0; q < full; q += 32) {
-                    L.tasks.insert(L.tasks.end(), v.begin() + q, v.begin() + q + 32);
-                    L.task_cls.push_back((uint8_t)cls);
-                }
-                pool.insert(pool.end(), v.begin() + full, v.end());
-            }
-            L.n_uniform_tasks = (int)L.task_cls.size();
-            for (size_t q = 0; q < pool.size(); q += 32) {
-                for (size_t r = q; r < q + 32; ++r) L.tasks.push_back(r < pool.size() ? pool[r] : 0xFFFFFFFFu);
-                L.task_cls.push_back(255);
-            }
-        }
 
         // (2) integer stencil: acc[p][dir][c]
         const int ndir = ref.ndir, nc = ref.nc;
@@ -287,6 +263,21 @@ RefElement build_reference(int dim, int nlevels) {
             }
         }
         L.mass_total = mass_int * s_mass;
+        // facts the apply kernel relies on: the interior stencil is symmetric (one coefficient per
+        // +-direction pair) and the stencil of a node in the interior of ONE reference face is the
+        // interior stencil with weights 0 (outward) / 1/2 (inside the face, centre) / 1 (inward)
+        if (rep[0] >= 0)
+            for (int d = 1; d < ndir; ++d)
+                for (int c = 0; c < nc; ++c)
+                    HMG_CHECK(L.G[(size_t)d * nc + c] == L.G[(size_t)(d & 1 ? d + 1 : d - 1) * nc + c],
+                              "interior stencil is not symmetric");
+        for (int cls = 1; cls < ref.ncls; cls <<= 1) {
+            if (rep[cls] < 0 || rep[0] < 0) continue;
+            for (int d = 0; d < ndir; ++d)
+                for (int c = 0; c < nc; ++c)
+                    HMG_CHECK(L.G[((size_t)cls * ndir + d) * nc + c] == face_weight(dim, cls, d) * L.G[(size_t)d * nc + c],
+                              "face stencil is not the weighted interior stencil");
+        }
 
         // (3) pairing rule: on every reference face / edge the ascending hierarchical order is the
         // same sequence of barycentric coordinates (src/implicit_fine_grid.jl:232-234 pairs k-th with k-th)

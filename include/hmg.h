@@ -13,7 +13,7 @@
  *   - levels are 1-based as in the reference: level 1 = base mesh, level `nlevels` = finest.
  *   - host matrices are the reference's layout: column-major Nf(level) x Ne Float64 with the
  *     rows in the reference's HIERARCHICAL node order (src/multilevel_reference.jl:41-61);
- *     the library permutes to its lattice order and pads the leading dimension internally.
+ *     the library permutes to its lattice order and interleaves groups of columns internally.
  *   - a context is owned by the caller (hmg_destroy), is not thread-safe, and all calls are
  *     stream-ordered on the context's CUDA stream; calls that return host data synchronise.
  *   - there is no CPU fallback: without a CUDA device hmg_create fails.
@@ -57,10 +57,13 @@ int hmg_create_partitioned(int dim, int nlevels, int64_t ne, int64_t nn, const d
                            const void* nccl_id, hmg_ctx** out);
 int hmg_nccl_unique_id(void* out128);
 
-/* sizes: nnodes(refined_mesh(implicit, level)), local column count, padded leading dimension */
+/* sizes: nnodes(refined_mesh(implicit, level)), local column count, rows of a device column
+ * (= nf), and the interleave width W of the device layout: entry (column e, lattice node p) of
+ * a level vector lives at ((e / W) * nf + p) * W + e % W */
 int64_t hmg_nf(const hmg_ctx* ctx, int level);
 int64_t hmg_ne_local(const hmg_ctx* ctx);
 int64_t hmg_ld(const hmg_ctx* ctx, int level);
+int hmg_group_width(const hmg_ctx* ctx);
 /* global element index (1-based) of local column j (1-based) */
 int hmg_local_elements(const hmg_ctx* ctx, int64_t* out);
 
@@ -139,7 +142,7 @@ int hmg_synchronize(hmg_ctx* ctx);
 int hmg_time_op(hmg_ctx* ctx, int op, int level, int steps, int reps, float* ms_out);
 /* number of kernel launches issued on the context's stream since creation */
 int64_t hmg_launch_count(const hmg_ctx* ctx);
-/* raw device pointer of a state vector (column-major ld(level) x ne_local, lattice row order) */
+/* raw device pointer of a state vector (element-interleaved, lattice row order; see hmg_group_width) */
 void* hmg_device_ptr(hmg_ctx* ctx, int level, int which);
 /* permutation: lattice position (0-based) of hierarchical row i (0-based) at `level` */
 int hmg_hier_to_lattice(const hmg_ctx* ctx, int level, int32_t* out);
