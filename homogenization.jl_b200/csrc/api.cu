@@ -35,9 +35,8 @@ thread_local std::string g_err;
 
 struct LevelDev {
     LevelView view{};
-    ApplyPlanView plan{};
-    int plan_ctas = 1;
-    size_t plan_smem = 0;
+    ApplyConfig cfg{};
+    std::vector<double> tab;      // StencilTab of the level (travels in the kernel parameter block)
     int32_t* hier2lat = nullptr;
     double* vec[HMG_NVEC] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -48,7 +47,7 @@ struct hmg_ctx {
     int dim = 0, nlevels = 0, device = 0;
     int rank = 0, nranks = 1;
     int64_t ne = 0, ne_global = 0, nn = 0;
-    int W = 16, wshift = 4;              // elements per unit of the interleaved device layout
+    int W = 32, wshift = 5;              // elements per unit of the interleaved device layout (= warp size)
     int64_t nunits = 0;
     double lambda = 1.0;
     cudaStream_t stream = nullptr;
@@ -62,6 +61,7 @@ struct hmg_ctx {
     double* elem_coef = nullptr;         // [nunits][CS][W]
     std::vector<double> elem_coef_host;  // [ne][CS]
     uint16_t* cmask = nullptr;           // [nunits * W]
+    uint8_t* mult = nullptr;             // [nunits][16][W] owners of the cell of every node class
     int32_t* belems = nullptr;           // elements touching the domain boundary
     int64_t nbelems = 0;
     int32_t* node_first = nullptr;
@@ -160,10 +160,9 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne, int64_t nn, const double*
 
     c->ref = build_reference(dim, nlevels);
     c->topo = build_topology(dim, ne, nn, c->elems.data());
-    // interleave width: 16 elements per unit; the largest 3D level needs 8 to fit its planes in the ring
-    c->W = (dim == 3 && nlevels >= 6) ? 8 : 16;
-    if (const char* w = getenv("HMG_GROUP_WIDTH")) { const int v = atoi(w); if (v == 8 || v == 16) c->W = v; }
-    c->wshift = c->W == 16 ? 4 : 3;
+    // interleave width: one warp lane per element of a unit
+    c->W = 32;
+    c->wshift = 5;
     c->nunits = (ne + c->W - 1) / c->W;
 
     // per-level tables and state vectors
@@ -185,15 +184,11 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne, int64_t nn, const double*
         V.restrict_tab = c->dupload(R.restrict_tab);
         for (int v = 0; v < 4; ++v) V.vpos[v] = v < nv ? R.hier2lat[v] : 0;
         L.hier2lat = c->dupload(R.hier2lat);
-        const ApplyPlan plan = build_apply_plan(dim, R, c->W);
-        L.plan.nchunks = plan.nchunks; L.plan.nslots = plan.nslots;
-        L.plan.slot_doubles = plan.slot_nodes * c->W; L.plan.zero_doubles = plan.zero_nodes * c->W;
-        L.plan.ntasks = plan.ntasks; L.plan.nwarps = plan.nwarps;
-        L.plan.chunk_start = c->dupload(plan.chunk_start);
-        L.plan.tasks = c->dupload(plan.tasks);
-        L.plan.nodetab = c->dupload(plan.nodetab);
-        L.plan_ctas = plan.ctas_per_sm;
-        L.plan_smem = plan.smem_bytes;
+        L.cfg = make_apply_config(dim, R.m, R.nf, c->W);
+        HMG_CHECK(L.cfg.ring_rows > 0, "a level of this hierarchy does not fit the shared-memory ring of the apply kernel");
+        L.tab = R.gi;
+        L.tab.insert(L.tab.end(), R.gc.begin(), R.gc.end());
+        L.tab.insert(L.tab.end(), R.ge.begin(), R.ge.end());
         for (int w = 0; w <= HMG_AP; ++w) L.vec[w] = c->dalloc<double>((size_t)V.nf * c->W * c->nunits);
     }
     // topology
@@ -228,6 +223,23 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne, int64_t nn, const double*
         c->cmask = c->dupload(cm);
         c->nbelems = (int64_t)be.size();
         c->belems = c->dupload(be);
+        // owners of the base-mesh cell behind every node class (weights of the fused dot products)
+        std::vector<uint8_t> mult((size_t)c->nunits * 16 * c->W, 1);
+        auto owners = [&](int64_t e, int slot) -> int {
+            const int32_t id = T.elem_cells[(size_t)e * 16 + slot];
+            if (id < 0) return 1;
+            const int64_t n = T.cell_off[id + 1] - T.cell_off[id];
+            HMG_CHECK(n <= 255, "a base-mesh cell has more than 255 owners");
+            return (int)n;
+        };
+        const int nfl = dim == 3 ? 4 : 0, nel = dim == 3 ? 6 : 3;
+        for (int64_t e = 0; e < ne; ++e) {
+            uint8_t* dst = &mult[(size_t)(e / c->W) * 16 * c->W + e % c->W];
+            for (int q = 0; q < nfl; ++q) dst[(size_t)class_of_face(q) * c->W] = (uint8_t)owners(e, q);
+            for (int q = 0; q < nel; ++q) dst[(size_t)class_of_edge(dim, q) * c->W] = (uint8_t)owners(e, nfl + q);
+            for (int q = 0; q < nv; ++q) dst[(size_t)class_of_vertex(dim, q) * c->W] = (uint8_t)owners(e, nfl + nel + q);
+        }
+        c->mult = c->dupload(mult);
     }
     c->node_first = c->dupload(T.node_first);
     std::vector<int32_t> e32(c->elems.begin(), c->elems.end());
@@ -244,18 +256,24 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne, int64_t nn, const double*
 }
 
 // ---- building blocks ---------------------------------------------------------------------
-void do_apply(hmg_ctx* c, int l, int mode, double alpha, const double* x, double* y, const double* b) {
+void do_apply(hmg_ctx* c, int l, int mode, double alpha, const double* x, double* y, const double* b, int dot_post = -1) {
     LevelDev& L = c->level(l);
     ApplyArgs a;
     a.L = L.view;
-    a.P = L.plan;
+    a.cfg = L.cfg;
     a.nunits = c->nunits;
+    a.tab = L.tab.data();
     a.coef = c->elem_coef;
     a.cmask = c->cmask;
+    a.mult = c->mult;
     a.x = x; a.y = y; a.b = b;
     a.alpha = alpha; a.lambda = c->lambda;
     a.mode = mode;
-    check_launch(c, launch_apply(c->dim, a, L.plan_ctas, L.plan_smem, c->stream));
+    a.dot_post = dot_post;
+    a.red = c->red;
+    const int n = launch_apply(c->dim, a, c->stream);
+    HMG_CHECK(n >= 0, "apply kernel refused the launch configuration");
+    check_launch(c, n);
 }
 void do_broadcast(hmg_ctx* c, int l, double* x) {
     check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->stream));
@@ -263,9 +281,11 @@ void do_broadcast(hmg_ctx* c, int l, double* x) {
 void do_local_residual(hmg_ctx* c, int l) {
     do_apply(c, l, APPLY_RESIDUAL, 1.0, c->vecp(l, HMG_X), c->vecp(l, HMG_R), c->vecp(l, HMG_B));
 }
-void do_global_product(hmg_ctx* c, int l, const double* x, double* y) {
-    do_apply(c, l, APPLY_AX, 1.0, x, y, nullptr);      // y = constraint(A x), column-local
-    do_broadcast(c, l, y);                             // interface sums
+// y = broadcast(constraint(A x)); with dot_post >= 0 the apply kernel also reduces
+// sum_entries owners(entry) * x * y_local = dot(x, y) over all stored entries (x consistent across owners)
+void do_global_product(hmg_ctx* c, int l, const double* x, double* y, int dot_post = -1) {
+    do_apply(c, l, APPLY_AX, 1.0, x, y, nullptr, dot_post);      // y = constraint(A x), column-local
+    do_broadcast(c, l, y);                                       // interface sums
 }
 void do_smoothing(hmg_ctx* c, int l, int steps) {
     const int64_t n = c->nstored(l);
@@ -275,8 +295,7 @@ void do_smoothing(hmg_ctx* c, int l, int steps) {
     do_broadcast(c, l, r);
     check_launch(c, launch_copy_dot(c->red, r, p, n, c->stream));
     for (int i = 0; i < steps; ++i) {
-        do_global_product(c, l, p, Ap);                               // Ap = broadcast(constraint(A p))
-        check_launch(c, launch_dot(c->red, p, Ap, n, POST_PAP, 0, c->stream));
+        do_global_product(c, l, p, Ap, POST_PAP);                     // Ap = broadcast(constraint(A p)), alpha = rho / p.Ap
         check_launch(c, launch_cg_update(c->red, x, p, r, Ap, n, c->stream));
         // the reference also updates p after the last step, but that value is never used
         // (src/multigrid.jl:68; the next smoothing call starts from a fresh residual)

@@ -29,9 +29,10 @@ inline int tri(int q) { return (q + 1) * (q + 2) / 2; }            // #points of
 inline int tot3(int q) { return (q + 1) * (q + 2) * (q + 3) / 6; } // #points of a 3-simplex lattice
 // packed (lexicographic, last coordinate fastest) index of a lattice point
 inline int pack2(int m, int i, int j) { return tri(m) - tri(m - i) + j; }
+// 3D: diagonal-plane order (t = i + j, then i, then k), see lattice.hpp
 inline int pack3(int m, int i, int j, int k) {
-    int n1 = m - i;
-    return tot3(m) - tot3(n1) + tri(n1) - tri(n1 - j) + k;
+    const int t = i + j;
+    return (m + 1) * t * (t + 1) / 2 - (t - 1) * t * (t + 1) / 3 + i * (m - t + 1) + k;
 }
 
 // stencil directions (index 0 = centre); the set is verified against the assembled stencil
@@ -54,6 +55,9 @@ struct RefLevel {
     std::vector<uint32_t> interp_tab;   // per fine node: coarse parents pa | pb<<16 (pa == pb: coincident)
     std::vector<uint16_t> restrict_tab; // per coarse node: [ndir] fine indices (centre first), 0xFFFF = outside
     std::vector<double> G;           // [ncls][ndir][nc] stencil table, scale factors folded in
+    // the tables the apply kernel is launched with (StencilTab of apply_core.cuh): interior rows
+    // [npair][nc], diagonal of every class [ncls][nc], reference-edge segment of 2-face classes [ncls][nc]
+    std::vector<double> gi, gc, ge;
     std::vector<uint16_t> face_bary; // 3D: interior nodes of a face, barycentric a | b<<8
     // packed index of the t-th paired node of every local cell: faces [4][npf] (3D), then edges
     // [6|3][npe], then vertices [4|3]
@@ -68,43 +72,6 @@ struct RefElement {
 };
 
 RefElement build_reference(int dim, int nlevels);
-
-// ---- streaming plan of the apply kernel (plan.cpp) ---------------------------------------
-// Device vectors are ELEMENT-INTERLEAVED: W consecutive coarse elements form a group ("unit"),
-// entry (element e, packed node p) lives at ((e / W) * nf + p) * W + e % W.  A warp lane is an
-// element, so every stencil access of a warp is one coalesced, bank-conflict-free line and the
-// control flow (node class, neighbour offsets) is warp-uniform.  A unit is streamed through shared
-// memory in CHUNKS (whole lattice planes i = const, merged when tiny) by TMA bulk copies into a
-// ring of slots; warps consume TASKS that only need chunks clo..chi (at most 3 consecutive).
-constexpr int PLAN_SLOT_INTS = 12;
-constexpr int PLAN_TASK_INTS = 4 + 4 * PLAN_SLOT_INTS;
-enum PlanTaskType { TASK_SWEEP_INTERIOR = 0, TASK_SWEEP_FACE_A = 1, TASK_SWEEP_FACE_B = 2, TASK_NODES = 3 };
-
-struct ApplyPlan {
-    int W = 16;            // elements per unit (lanes per row slot)
-    int spw = 2;           // row slots per warp = 32 / W
-    int nchunks = 0;       // chunks per unit
-    int nslots = 0;        // ring slots
-    int slot_nodes = 0;    // nodes per slot (largest chunk + slack)
-    int zero_nodes = 0;    // nodes of the zero line in front of the ring
-    int nwarps = 8;        // consumer warps per CTA (one more warp produces)
-    int ctas_per_sm = 1;
-    int ntasks = 0;
-    size_t smem_bytes = 0;
-    std::vector<int32_t> chunk_start;   // [nchunks + 1] packed node offsets
-    // task t: [type, clo, chi, 0] + 4 slots x 12 ints.
-    //  sweep slot: [0] centre ref, [1..3] "minus" line refs, [4..6] "plus" line refs, [7] count,
-    //              [8] packed index of the first node, [9] flags (1: first node is a face end, 2: last)
-    //  node slot:  [0] index into nodetab (-1: idle)
-    //  ref = (chunk - clo) << 28 | node offset inside the chunk; (3 << 28 | 1) = the zero line
-    std::vector<int32_t> tasks;
-    // special nodes (edge / vertex classes): [0] centre ref, [d] ref of neighbour d (0xFFFFFFFF outside),
-    // [15] packed index | class << 16; refs relative to the chunk of plane max(i - 1, 0)
-    std::vector<uint32_t> nodetab;
-};
-ApplyPlan build_apply_plan(int dim, const RefLevel& L, int W);
-// single-face classes derive their coefficients from the interior ones: weight of direction d
-double face_weight(int dim, int cls, int d);
 
 // ---- base-mesh topology ---------------------------------------------------------------
 struct CellMap {                     // CSR cell -> (element, local id), owners ascending

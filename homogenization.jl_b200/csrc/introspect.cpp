@@ -3,6 +3,7 @@
 // functions the kernels use (lattice.hpp), so that the CPU test-suite can compare them with the
 // oracle's explicit sparse operators and interface maps.
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -10,6 +11,8 @@
 #include "../../include/hmg.h"
 #include "hmg_host.hpp"
 #include "lattice.hpp"
+#include "apply_core.cuh"
+#include "kernels.cuh"
 
 using namespace hmg;
 
@@ -61,96 +64,79 @@ void transfer_matrix_t(const RefLevel& Lf, const RefLevel& Lc, double* dense) {
     }
 }
 
-// Executes the apply plan of one level for ONE element on the host, task by task and slot by slot,
-// with the same reference decoding, tap directions and face weights as apply_kernel (kernels.cu),
-// all chunks resident.  y (lattice order) = A x.  Verifies the plan tables without a GPU; the
-// device code itself is checked by the -m gpu parity tests.
-template <int DIM>
-void emulate_plan_t(const RefLevel& L, const ApplyPlan& P, const double* coef, const double* x, double* y, int64_t* info) {
-    using D = Dims<DIM>;
-    constexpr int NP = DIM == 3 ? 3 : 1;
-    const int KP = DIM == 3 ? 5 : 3, KM = DIM == 3 ? 6 : 4;
-    const int M0[3] = {1, DIM == 3 ? 3 : 0, 7}, M1[3] = {DIM == 3 ? 10 : 6, 12, 14};
-    const int P0[3] = {2, 4, 8}, P1[3] = {DIM == 3 ? 9 : 5, 11, 13};
-    const int FIRST = 1, LAST = DIM == 3 ? 8 : 4, FACE_A = 2, FACE_B = 4;
-    // image: zero line, then the chunks back to back with two nodes of slack each, poisoned slack
-    const double poison = std::nan("");
-    const int Z = P.zero_nodes;
-    std::vector<int> cbase(P.nchunks);
-    int total = Z;
-    for (int c = 0; c < P.nchunks; ++c) { cbase[c] = total; total += P.chunk_start[c + 1] - P.chunk_start[c] + 2; }
-    std::vector<double> sm(total, poison);
-    for (int q = 0; q < Z; ++q) sm[q] = 0.0;
-    for (int c = 0; c < P.nchunks; ++c)
-        for (int p = P.chunk_start[c]; p < P.chunk_start[c + 1]; ++p) sm[cbase[c] + p - P.chunk_start[c]] = x[p];
-    auto coefI = [&](int cls, int d) {
-        double s = 0.0;
-        for (int q = 0; q < D::NC; ++q) s = std::fma(coef[q], L.G[((size_t)cls * D::NDIR + d) * D::NC + q], s);
-        return s;
-    };
-    std::vector<int> written(L.nf, 0);
-    int64_t nsweep_nodes = 0, nspecial = 0;
-    for (int t = 0; t < P.ntasks; ++t) {
-        const int32_t* T = &P.tasks[(size_t)t * PLAN_TASK_INTS];
-        const int type = T[0], clo = T[1], chi = T[2];
-        HMG_CHECK(clo >= 0 && chi < P.nchunks && chi - clo <= 2, "bad chunk window");
-        auto off = [&](uint32_t ref) -> int {
-            const unsigned sel = ref >> 28;
-            if (sel == 3) return (int)(ref & 0x0fffffff);
-            HMG_CHECK((int)(clo + sel) <= chi, "reference beyond the task's chunk window");
-            return cbase[clo + sel] + (int)(ref & 0x0fffffff);
-        };
-        for (int s = 0; s < P.spw; ++s) {
-            const int32_t* d = T + 4 + s * PLAN_SLOT_INTS;
-            if (type == TASK_NODES) {
-                if (d[0] < 0) continue;
-                const uint32_t* e = &P.nodetab[(size_t)d[0] * 16];
-                const int p = e[15] & 0xffff, cls = e[15] >> 16;
-                double acc = 0.0;
-                for (int dd = 0; dd < D::NDIR; ++dd)
-                    if (e[dd] != 0xFFFFFFFFu) acc = std::fma(coefI(cls, dd), sm[off(e[dd])], acc);
-                y[p] = acc;
-                written[p]++;
-                ++nspecial;
-                continue;
-            }
-            const int rcls = type == TASK_SWEEP_INTERIOR ? 0 : (type == TASK_SWEEP_FACE_A ? FACE_A : FACE_B);
-            const int cnt = d[7];
-            if (cnt == 0) continue;
-            const int oc = off((uint32_t)d[0]);
-            int om[3], op[3];
-            for (int q = 0; q < NP; ++q) { om[q] = off((uint32_t)d[1 + q]); op[q] = off((uint32_t)d[4 + q]); }
-            for (int k = 0; k < cnt; ++k) {
-                int cls = rcls;
-                if (rcls == 0 && (d[9] & 1) && k == 0) cls = FIRST;
-                else if (rcls == 0 && (d[9] & 2) && k == cnt - 1) cls = LAST;
-                const int p = d[8] + k;
-                HMG_CHECK((int)(L.nodeinfo[p] >> 24) == cls, "sweep visits a node of another class");
-                double a1 = 0.0, ah = 0.0;
-                auto term = [&](int dir, double c, int o) {
-                    const double w = face_weight(DIM, cls, dir);
-                    if (w == 1.0) a1 = std::fma(c, sm[o], a1);
-                    else if (w == 0.5) ah = std::fma(c, sm[o], ah);
-                };
-                term(0, coefI(0, 0), oc + k);
-                term(KP, coefI(0, KP), oc + k + 1);
-                term(KM, coefI(0, KP), oc + k - 1);
-                for (int q = 0; q < NP; ++q) {
-                    term(M0[q], coefI(0, M0[q]), om[q] + k);
-                    term(M1[q], coefI(0, M1[q]), om[q] + k - 1);
-                    term(P0[q], coefI(0, M0[q]), op[q] + k);
-                    term(P1[q], coefI(0, M1[q]), op[q] + k + 1);
-                }
-                y[p] = a1 + 0.5 * ah;
-                written[p]++;
-                ++nsweep_nodes;
-            }
-        }
+// Runs the apply kernel's task enumeration and line sweeps (apply_core.cuh: the SAME templates the
+// device kernel instantiates -- class dispatch, compile-time weights, sliding windows, row geometry)
+// for ONE element on the host, values addressed by packed row.  y (lattice order) = A x.  Verifies
+// everything of K1 except the shared-memory ring / TMA plumbing, which the -m gpu parity tests cover.
+struct HostMem {
+    const double* x;
+    int nf;
+    double operator()(int addr) const {
+        HMG_CHECK(addr >= 0 && addr < nf, "sweep reads a row outside the element");
+        return x[addr];
     }
-    for (int p = 0; p < L.nf; ++p) HMG_CHECK(written[p] == 1, "plan does not write every node exactly once");
+};
+struct HostOut {
+    double* y;
+    int* written;
+    const uint32_t* nodeinfo;
+    int row0, nf;
+    template <int CLS> void put(int k, double acc, double) {
+        const int p = row0 + k;
+        HMG_CHECK(p >= 0 && p < nf, "sweep writes a row outside the element");
+        HMG_CHECK((int)(nodeinfo[p] >> 24) == CLS, "sweep visits a node with the wrong class");
+        y[p] = acc;
+        written[p]++;
+    }
+};
+template <int DIM>
+void emulate_sweep_t(const RefLevel& L, int seg_shift, const double* coef, const double* x, double* y, int64_t* info) {
+    using D = Dims<DIM>;
+    StencilTab<DIM> T;
+    static_assert(sizeof(T) == sizeof(double) * (Pairs<DIM>::N + 2 * D::NCLS) * D::NC, "table layout");
+    HMG_CHECK(L.gi.size() + L.gc.size() + L.ge.size() == sizeof(T) / sizeof(double), "stencil table size");
+    std::vector<double> flat = L.gi;
+    flat.insert(flat.end(), L.gc.begin(), L.gc.end());
+    flat.insert(flat.end(), L.ge.begin(), L.ge.end());
+    std::memcpy(&T, flat.data(), sizeof(T));
+    LaneOp<DIM> op;
+    for (int q = 0; q < D::NC; ++q) op.ec[q] = coef[q];
+    interior_coefficients(op, T);
+    std::vector<int> written(L.nf, 0);
+    HostMem mem{x, L.nf};
+    HostOut out{y, written.data(), L.nodeinfo.data(), 0, L.nf};
+    const int m = L.m;
+    int64_t ntasks = 0, window = 0;
+    if constexpr (DIM == 3) {
+        for (int t = 0; t <= m; ++t)
+            for (int i = 0; i <= t; ++i) {
+                const LineRows3 r = line_rows3(m, t, i, lat_off3(m, t));
+                LineGeo<3> g;
+                g.L = r.L; g.k0 = 0; g.k1 = r.L; g.bc = r.c;
+                for (int q = 0; q < 3; ++q) { g.bm[q] = r.rm[q]; g.bp[q] = r.rp[q]; }
+                out.row0 = r.c;
+                run_line3(op, T, mem, 1, g, t, i, out);
+                window = std::max<int64_t>(window, r.need - r.behind + 1);
+                ++ntasks;
+            }
+    } else {
+        const int SEG = 1 << seg_shift;
+        for (int i = 0; i <= m; ++i)
+            for (int k0 = 0; k0 < m - i + 1; k0 += SEG) {
+                const int k1 = std::min(m - i + 1, k0 + SEG);
+                const LineRows2 r = line_rows2(m, i, k0, k1);
+                LineGeo<2> g;
+                g.L = r.L; g.k0 = k0; g.k1 = k1; g.bc = r.c; g.bm[0] = r.rm[0]; g.bp[0] = r.rp[0];
+                out.row0 = r.c;
+                run_line2(op, T, mem, 1, g, i, out);
+                window = std::max<int64_t>(window, r.need - r.behind + 1);
+                ++ntasks;
+            }
+    }
+    for (int p = 0; p < L.nf; ++p) HMG_CHECK(written[p] == 1, "sweeps do not write every node exactly once");
     if (info) {
-        info[0] = P.nchunks; info[1] = P.nslots; info[2] = P.slot_nodes; info[3] = P.ntasks; info[4] = P.nwarps;
-        info[5] = P.ctas_per_sm; info[6] = (int64_t)P.smem_bytes; info[7] = nsweep_nodes; info[8] = nspecial;
+        const ApplyConfig cfg = make_apply_config(DIM, m, L.nf, 32);
+        info[0] = ntasks; info[1] = window; info[2] = cfg.ring_rows; info[3] = (int64_t)cfg.smem_bytes;
     }
 }
 }  // namespace
@@ -278,16 +264,16 @@ int hmg_host_element_coefficients(int dim, int64_t ne, int64_t nn, const double*
     HOST_END
 }
 
-// y = A x for one element through the apply plan (lattice order), info[9] = nchunks, nslots, slot_nodes,
-// ntasks, nwarps, ctas_per_sm, smem_bytes, nodes computed by sweeps, nodes computed by the generic path
-int hmg_host_apply_plan(int dim, int nlevels, int level, int W, const double* coef, const double* x, double* y,
-                        int64_t* info) {
+// y = A x for one element through the apply kernel's sweeps (lattice order); 2D lines are split into
+// segments of 2^seg_shift nodes; info[4] = tasks, largest row window of a task, ring rows, smem bytes
+int hmg_host_apply_sweep(int dim, int nlevels, int level, int seg_shift, const double* coef, const double* x, double* y,
+                         int64_t* info) {
     HOST_BEGIN
     RefElement ref = build_reference(dim, nlevels);
     const RefLevel& L = get_level(ref, level);
-    const ApplyPlan P = build_apply_plan(dim, L, W);
-    if (dim == 3) emulate_plan_t<3>(L, P, coef, x, y, info);
-    else emulate_plan_t<2>(L, P, coef, x, y, info);
+    HMG_CHECK(seg_shift >= 1 && seg_shift <= 8, "bad segment size");
+    if (dim == 3) emulate_sweep_t<3>(L, seg_shift, coef, x, y, info);
+    else emulate_sweep_t<2>(L, seg_shift, coef, x, y, info);
     HOST_END
 }
 

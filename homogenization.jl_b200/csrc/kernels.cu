@@ -14,15 +14,14 @@
 //                          level-1 gather/scatter (src/implicit_fine_grid.jl:148-202).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <algorithm>
 
 #include "kernels.cuh"
 #include "lattice.hpp"
+#include "apply_core.cuh"
 
 namespace hmg {
-
-constexpr int TASK_INTS = 52, SLOT_INTS = 12;   // = PLAN_TASK_INTS / PLAN_SLOT_INTS of hmg_host.hpp
-constexpr int MAX_SLOTS = 8;
 
 // ------------------------------------------------------------------------------------------
 // small device helpers
@@ -62,324 +61,392 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// deterministic: fixed grid, fixed per-block tree, partials summed in block order by the last block
+__device__ __forceinline__ void block_reduce_finish(double v, const Reducer& R, int post, int slot) {
+    __shared__ double wsum[32];
+    __shared__ bool last;
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) wsum[wid] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += wsum[w];
+        R.partials[blockIdx.x] = s;
+        __threadfence();
+        const unsigned t = atomicAdd(R.ticket, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double s = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += __ldcg(R.partials + b);
+    s = warp_sum(s);
+    __syncthreads();
+    if (lane == 0) wsum[wid] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += wsum[w];
+        double* S = R.scalars;
+        if (post == POST_STORE) S[slot] = tot;
+        else if (post == POST_RHO) S[S_RHO] = tot;
+        else if (post == POST_PAP) { S[S_PAP] = tot; S[S_ALPHA] = S[S_RHO] / tot; }
+        else if (post == POST_RSQR) { S[S_RSQR] = tot; S[S_BETA] = tot / S[S_RHO]; S[S_RHO] = tot; }
+        *R.ticket = 0u;
+    }
+}
+
+
 // ------------------------------------------------------------------------------------------
 // K1: local operator apply
 // ------------------------------------------------------------------------------------------
-// Face set a stencil direction points out of: a neighbour n+d of a node of class `cls` lies outside
-// the simplex iff (cls & out_mask(d)) != 0 (the lattice simplex is convex and d has entries in {-1,0,1}).
-template <int DIM> __host__ __device__ constexpr int out_mask(int d) {
-    if (DIM == 3) {
-        constexpr int I[15] = {0, 1, -1, 0, 0, 0, 0, -1, 1, -1, 1, 0, 0, 1, -1};
-        constexpr int J[15] = {0, 0, 0, 1, -1, 0, 0, 1, -1, 0, 0, -1, 1, -1, 1};
-        constexpr int K[15] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 1, -1};
-        return (K[d] < 0 ? 1 : 0) | (J[d] < 0 ? 2 : 0) | (I[d] < 0 ? 4 : 0) | (I[d] + J[d] + K[d] > 0 ? 8 : 0);
-    }
-    constexpr int I2[7] = {0, 1, -1, 0, 0, -1, 1};
-    constexpr int J2[7] = {0, 0, 0, 1, -1, 1, -1};
-    return (J2[d] < 0 ? 1 : 0) | (I2[d] < 0 ? 2 : 0) | (I2[d] + J2[d] > 0 ? 4 : 0);
-}
-__host__ __device__ constexpr int opp_dir(int d) { return d == 0 ? 0 : ((d & 1) ? d + 1 : d - 1); }
-// weight of direction d in the stencil of a node of a single-face class, relative to the interior
-// stencil: 0 dropped (points outside), 1 = one half (direction inside the face: half of the fine
-// elements around that edge exist), 2 = full (points inwards).  Verified against the assembled
-// tables at setup (reference.cpp).
-template <int DIM> __host__ __device__ constexpr int wcode(int cls, int d) {
-    return cls == 0 ? 2
-                    : ((cls & out_mask<DIM>(d)) ? 0 : (d == 0 ? 1 : ((cls & out_mask<DIM>(opp_dir(d))) ? 2 : 1)));
-}
+// Lanes are coarse elements (W = 32 interleaved columns), so node class, neighbour offsets and control
+// flow are warp-uniform and every shared/global access of a warp is one conflict-free 256-byte row.
+// A CTA owns a contiguous range of (element group, lattice plane) pairs, balanced by rows.  Its input
+// rows stream ONCE from HBM through a shared-memory ring: one elected thread issues TMA bulk copies
+// (cp.async.bulk, completion on mbarriers) of fixed-size chunks, consumer warps take the lines of the
+// planes round-robin, wait for the chunk that holds the last row their line reads, and hand chunks
+// back once their window has passed them.  The ring is addressed by (stream row mod R); the first
+// SP rows are mirrored behind the ring so that a line never wraps.  Each lane walks its line with a
+// register sliding window: 7 (3D) / 3 (2D) shared loads per node instead of 15 / 7.
+constexpr int APPLY_W = 32;             // element-interleave width = warp size
+constexpr int APPLY_Q = 64, APPLY_QS = 6;   // mbarrier slots (chunks in flight), log2
+constexpr int APPLY_MAXT = 16 * 32;    // 15 consumer warps + the producer warp: 128 registers per thread
 
-// directions of the taps of a line sweep along the fastest lattice coordinate.  Centre line: -k, 0,
-// +k; NP "minus" lines with taps at k and k-1; NP "plus" lines with taps at k and k+1; tap t of
-// minus line q is the opposite direction of tap t of plus line q.
-template <int DIM> struct Sweep;
-template <> struct Sweep<3> {
-    static constexpr int NP = 3, KP = 5, KM = 6, FIRST = 1, LAST = 8, FACE_A = 2, FACE_B = 4;
-    __host__ __device__ static constexpr int m0(int q) { return q == 0 ? 1 : (q == 1 ? 3 : 7); }     // (1,0,0) (0,1,0) (-1,1,0)
-    __host__ __device__ static constexpr int m1(int q) { return q == 0 ? 10 : (q == 1 ? 12 : 14); }  // ... + (0,0,-1)
-    __host__ __device__ static constexpr int p0(int q) { return q == 0 ? 2 : (q == 1 ? 4 : 8); }     // (-1,0,0) (0,-1,0) (1,-1,0)
-    __host__ __device__ static constexpr int p1(int q) { return q == 0 ? 9 : (q == 1 ? 11 : 13); }   // ... + (0,0,1)
-};
-template <> struct Sweep<2> {
-    static constexpr int NP = 1, KP = 3, KM = 4, FIRST = 1, LAST = 4, FACE_A = 2, FACE_B = 2;
-    __host__ __device__ static constexpr int m0(int) { return 1; }   // (1,0)
-    __host__ __device__ static constexpr int m1(int) { return 6; }   // (1,-1)
-    __host__ __device__ static constexpr int p0(int) { return 2; }   // (-1,0)
-    __host__ __device__ static constexpr int p1(int) { return 5; }   // (-1,1)
+template <int DIM> struct ApplyParams {
+    StencilTab<DIM> T;
+    const double* x;
+    double* y;
+    const double* t;           // b (RESIDUAL) or y (MULADD)
+    const double* coef;
+    const uint16_t* cmask;
+    const uint8_t* mult;
+    int64_t nunits;
+    double sa, lambda;
+    int m, nf, nwarps, R, SP, cs, seg_shift;
+    int dot_post;
+    Reducer red;
 };
 
-// per-lane (= per coarse element) operator data
-template <int DIM> struct LaneOp {
-    double ec[Dims<DIM>::NC];                      // |J| P (upper triangle), lambda |J|
-    double c0, cz, ca[Sweep<DIM>::NP], cb[Sweep<DIM>::NP];   // interior stencil, one value per +-pair
-    unsigned cm;                                   // Dirichlet class mask
+template <int DIM> __device__ __forceinline__ int plane_off(int m, int t) { return DIM == 3 ? lat_off3(m, t) : lat_off2(m, t); }
+
+// first (group, plane) boundary at or after global row r; returns group * (m + 1) + plane
+template <int DIM> __device__ __forceinline__ int64_t plane_at_or_after(int64_t r, int m, int nf) {
+    const int64_t u = r / nf;
+    const int rem = (int)(r - u * nf);
+    if (rem == 0) return u * (m + 1);
+    for (int t = 1; t <= m; ++t)
+        if (plane_off<DIM>(m, t) >= rem) return u * (m + 1) + t;
+    return (u + 1) * (m + 1);
+}
+
+template <int DIM, int MODE, bool DOT> struct OutDev {
+    double* yl;            // output row of node 0 of the current line (lane included)
+    const double* tl;
+    double sa;
+    unsigned cm;
+    double dsum;
+    double mw[4];          // owners of the cells of the single-face classes
+    unsigned long long ml, mh;   // owners of every class, one byte each
+    template <int CLS> __device__ __forceinline__ double weight() const {
+        if (CLS == 0) return 1.0;
+        if (CLS == 1) return mw[0];
+        if (CLS == 2) return mw[1];
+        if (CLS == 4) return mw[2];
+        if (CLS == 8) return mw[3];
+        return (double)(unsigned)((CLS < 8 ? (ml >> (8 * (CLS & 7))) : (mh >> (8 * (CLS & 7)))) & 255ull);
+    }
+    template <int CLS> __device__ __forceinline__ void put(int k, double acc, double x0) {
+        const bool fixed = MODE != APPLY_MULADD && ((cm >> CLS) & 1u);
+        double v;
+        if (MODE == APPLY_AX) v = fixed ? 0.0 : acc;
+        else if (MODE == APPLY_RESIDUAL) v = fixed ? 0.0 : __ldcs(tl + k * APPLY_W) - acc;
+        else v = fma(sa, acc, __ldcs(tl + k * APPLY_W));
+        yl[k * APPLY_W] = v;
+        if (DOT) dsum = fma(weight<CLS>() * x0, v, dsum);
+    }
 };
 
-template <int DIM, int CLS>
-__device__ __forceinline__ double eval_node(const LaneOp<DIM>& op, double xm, double x0, double xp,
-                                            const double* Mm, const double* Mk, const double* Pk, const double* Pp) {
-    using S = Sweep<DIM>;
-    if (CLS == 0) {
-        double a = op.c0 * x0;
-        a = fma(op.cz, xm + xp, a);
-#pragma unroll
-        for (int q = 0; q < S::NP; ++q) {
-            a = fma(op.ca[q], Mk[q] + Pk[q], a);
-            a = fma(op.cb[q], Mm[q] + Pp[q], a);
-        }
-        return a;
-    }
-    double a1 = 0.0, ah = op.c0 * x0;    // the diagonal of a face node is one half of the interior one
-    {
-        constexpr int wp = wcode<DIM>(CLS, S::KP), wm = wcode<DIM>(CLS, S::KM);
-        if (wp == 2) a1 = fma(op.cz, xp, a1); else if (wp == 1) ah = fma(op.cz, xp, ah);
-        if (wm == 2) a1 = fma(op.cz, xm, a1); else if (wm == 1) ah = fma(op.cz, xm, ah);
-    }
-#pragma unroll
-    for (int q = 0; q < S::NP; ++q) {
-        const int w0 = wcode<DIM>(CLS, S::m0(q)), w1 = wcode<DIM>(CLS, S::m1(q));
-        const int w2 = wcode<DIM>(CLS, S::p0(q)), w3 = wcode<DIM>(CLS, S::p1(q));
-        if (w0 == 2) a1 = fma(op.ca[q], Mk[q], a1); else if (w0 == 1) ah = fma(op.ca[q], Mk[q], ah);
-        if (w2 == 2) a1 = fma(op.ca[q], Pk[q], a1); else if (w2 == 1) ah = fma(op.ca[q], Pk[q], ah);
-        if (w1 == 2) a1 = fma(op.cb[q], Mm[q], a1); else if (w1 == 1) ah = fma(op.cb[q], Mm[q], ah);
-        if (w3 == 2) a1 = fma(op.cb[q], Pp[q], a1); else if (w3 == 1) ah = fma(op.cb[q], Pp[q], ah);
-    }
-    return fma(0.5, ah, a1);
-}
-
-// output of one node: AX  y = fixed ? 0 : acc ; RESIDUAL  r = fixed ? 0 : b - acc ; MULADD  y += alpha acc
-struct OutCtx {
-    double* y;             // lane pointer at packed node 0 of the unit
-    const double* t;       // b (RESIDUAL) or y (MULADD) or nullptr (AX)
-    double sa;             // 1, -1 or alpha
+struct SmemLoad {
+    const double* sm;
+    __device__ __forceinline__ double operator()(int addr) const { return sm[addr]; }
 };
-__device__ __forceinline__ void store_node(const OutCtx& o, int64_t off, double acc, bool fixed, double t) {
-    o.y[off] = fixed ? 0.0 : fma(o.sa, acc, t);
-}
 
-template <int W> __device__ __forceinline__ int ref_offset(int ref, int b0, int b1, int b2, int bz, int l) {
-    const unsigned sel = (unsigned)ref >> 28;
-    const int base = sel == 0 ? b0 : (sel == 1 ? b1 : (sel == 2 ? b2 : bz));
-    return base + (ref & 0x0fffffff) * W + l;
-}
-
-// one line sweep per row slot: nodes kstart .. kstart+cnt-1 of a lattice line, classes RCLS (|FIRST/LAST)
-template <int DIM, int W, int RCLS>
-__device__ __forceinline__ void sweep_task(const double* __restrict__ sm, const int* __restrict__ d, int b0, int b1, int b2,
-                                           int bz, int l, const LaneOp<DIM>& op, const OutCtx& out) {
-    using S = Sweep<DIM>;
-    constexpr int NP = S::NP;
-    const int cnt = d[7];
-    const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
-    const int oc = ref_offset<W>(d[0], b0, b1, b2, bz, l);
-    int om[NP], opl[NP];
-#pragma unroll
-    for (int q = 0; q < NP; ++q) {
-        om[q] = ref_offset<W>(d[1 + q], b0, b1, b2, bz, l);
-        opl[q] = ref_offset<W>(d[4 + q], b0, b1, b2, bz, l);
-    }
-    const int64_t pout = (int64_t)d[8] * W;
-    const bool ff = d[9] & 1, lf = d[9] & 2;
-    double xm = sm[oc - W], x0 = sm[oc];
-    double Mm[NP], Pk[NP];
-#pragma unroll
-    for (int q = 0; q < NP; ++q) { Mm[q] = sm[om[q] - W]; Pk[q] = sm[opl[q]]; }
-#pragma unroll 2
-    for (int s = 0; s < maxcnt; ++s) {
-        if (s < cnt) {
-            const double t = out.t ? out.t[pout + (int64_t)s * W] : 0.0;
-            const double xp = sm[oc + (s + 1) * W];
-            double Mk[NP], Pp[NP];
-#pragma unroll
-            for (int q = 0; q < NP; ++q) { Mk[q] = sm[om[q] + s * W]; Pp[q] = sm[opl[q] + (s + 1) * W]; }
-            double acc;
-            int cls = RCLS;
-            if (RCLS == 0 && ff && s == 0) {
-                acc = eval_node<DIM, S::FIRST>(op, xm, x0, xp, Mm, Mk, Pk, Pp);
-                cls = S::FIRST;
-            } else if (RCLS == 0 && lf && s == cnt - 1) {
-                acc = eval_node<DIM, S::LAST>(op, xm, x0, xp, Mm, Mk, Pk, Pp);
-                cls = S::LAST;
-            } else {
-                acc = eval_node<DIM, RCLS>(op, xm, x0, xp, Mm, Mk, Pk, Pp);
-            }
-            store_node(out, pout + (int64_t)s * W, acc, (op.cm >> cls) & 1u, t);
-            xm = x0; x0 = xp;
-#pragma unroll
-            for (int q = 0; q < NP; ++q) { Mm[q] = Mk[q]; Pk[q] = Pp[q]; }
-        }
-    }
-}
-
-// generic path for the nodes on reference edges / vertices: coefficients from the class table
-template <int DIM, int W>
-__device__ __forceinline__ void node_task(const double* __restrict__ sm, int idx, const uint32_t* __restrict__ nodetab,
-                                          const double* __restrict__ G, int b0, int b1, int b2, int bz, int l,
-                                          const LaneOp<DIM>& op, const OutCtx& out) {
+template <int DIM, int MODE, bool DOT>
+__global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_constant__ ApplyParams<DIM> a) {
     using D = Dims<DIM>;
-    if (idx < 0) return;
-    const uint32_t* e = nodetab + (size_t)idx * 16;
-    const uint32_t info = __ldg(e + 15);
-    const int p = info & 0xffff, cls = info >> 16;
-    const double t = out.t ? out.t[(int64_t)p * W] : 0.0;
-    const double* g = G + (size_t)cls * D::NDIR * D::NC;
-    double acc = 0.0;
-#pragma unroll 1
-    for (int dd = 0; dd < D::NDIR; ++dd) {
-        const uint32_t ref = __ldg(e + dd);
-        if (ref == 0xFFFFFFFFu) continue;
-        double c = 0.0;
-#pragma unroll
-        for (int q = 0; q < D::NC; ++q) c = fma(op.ec[q], __ldg(g + dd * D::NC + q), c);
-        acc = fma(c, sm[ref_offset<W>((int)ref, b0, b1, b2, bz, l)], acc);
-    }
-    store_node(out, (int64_t)p * W, acc, (op.cm >> cls) & 1u, t);
-}
-
-// Persistent kernel.  Warp `nwarps` is the TMA producer, warps 0..nwarps-1 consume.  CTA b handles the
-// units b, b + gridDim.x, ...; the chunks of consecutive units form one stream through the ring.
-template <int DIM, int W, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) apply_kernel(const ApplyArgs a) {
-    using D = Dims<DIM>;
-    using S = Sweep<DIM>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[MAX_SLOTS], empty_bar[MAX_SLOTS];
+    __shared__ __align__(8) uint64_t full_bar[APPLY_Q], empty_bar[APPLY_Q];
     double* sm = reinterpret_cast<double*>(smem_raw);
-    const ApplyPlanView& P = a.P;
-    const int K = P.nslots, nch = P.nchunks, NW = P.nwarps;
-    const int SD = P.slot_doubles, ZD = P.zero_doubles;
+    const int m = a.m, nf = a.nf, NW = a.nwarps, R = a.R, SP = a.SP, CS = a.cs, CH = 1 << a.cs;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nf = a.L.nf;
+    const int NPL = m + 1;
 
-    for (int q = threadIdx.x; q < ZD + K * SD; q += blockDim.x) sm[q] = 0.0;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < K; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NW); }
+        for (int s = 0; s < APPLY_Q; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NW); }
         fence_mbar_init();
     }
     fence_proxy_async();
     __syncthreads();
 
+    // this CTA's range of (group, plane) pairs and the rows it streams (one halo plane on each side)
+    const int64_t total_rows = a.nunits * nf;
+    const int64_t P0 = plane_at_or_after<DIM>(total_rows * blockIdx.x / gridDim.x, m, nf);
+    const int64_t P1 = blockIdx.x + 1 == gridDim.x ? a.nunits * NPL
+                                                   : plane_at_or_after<DIM>(total_rows * (blockIdx.x + 1) / gridDim.x, m, nf);
+    const int64_t u0 = P0 / NPL, u1 = P1 / NPL;
+    const int t0 = (int)(P0 - u0 * NPL), t1 = (int)(P1 - u1 * NPL);
+    const int64_t g0 = u0 * nf + plane_off<DIM>(m, t0 > 0 ? t0 - 1 : 0);
+    const int64_t gend = t1 == 0 ? u1 * nf : u1 * nf + plane_off<DIM>(m, t1 + 1);
+    const int stotal = P1 > P0 ? (int)(gend - g0) : 0;
+    const int nchunks = (stotal + CH - 1) >> CS;
+    double dsum = 0.0;
+
     if (warp == NW) {
         // ---------------- producer ----------------
-        if (lane == 0) {
-            unsigned n = 0;
-            for (int64_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
-                const double* src = a.x + u * (int64_t)nf * W;
-                for (int c = 0; c < nch; ++c, ++n) {
-                    const unsigned s = n % K, use = n / K;
-                    if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1u);
-                    const int c0 = __ldg(P.chunk_start + c), c1 = __ldg(P.chunk_start + c + 1);
-                    const uint32_t bytes = (uint32_t)(c1 - c0) * W * 8u;
-                    mbar_expect_tx(&full_bar[s], bytes);
-                    bulk_g2s(sm + ZD + (size_t)s * SD, src + (int64_t)c0 * W, bytes, &full_bar[s]);
+        if (lane == 0 && nchunks > 0) {
+            const uint32_t RB = APPLY_W * 8;
+            int phys = 0, confirmed = 0;
+            const double* src = a.x + g0 * APPLY_W;
+            const char* pre = MODE == APPLY_AX ? nullptr : reinterpret_cast<const char*>(a.t + g0 * APPLY_W);
+            for (int q = 0; q < nchunks; ++q) {
+                const int s0 = q << CS;
+                const int n = min(CH, stotal - s0);
+                const int old = s0 + n - 1 - R;
+                if (old >= 0) {
+                    const int c_old = old >> CS;
+                    while (confirmed <= c_old) {
+                        mbar_wait(&empty_bar[confirmed & (APPLY_Q - 1)], (confirmed >> APPLY_QS) & 1u);
+                        ++confirmed;
+                    }
                 }
+                uint64_t* bar = &full_bar[q & (APPLY_Q - 1)];
+                const int n1 = min(n, R + SP - phys);
+                const int wrapped = phys + n - R;
+                const int dup = phys < SP ? min(n, SP - phys) : 0;
+                mbar_expect_tx(bar, (uint32_t)(n1 + (wrapped > 0 ? wrapped : 0) + dup) * RB);
+                const double* s = src + (int64_t)s0 * APPLY_W;
+                bulk_g2s(sm + (size_t)phys * APPLY_W, s, (uint32_t)n1 * RB, bar);
+                if (wrapped > 0) bulk_g2s(sm, s + (size_t)(R - phys) * APPLY_W, (uint32_t)wrapped * RB, bar);
+                if (dup > 0) bulk_g2s(sm + (size_t)(R + phys) * APPLY_W, s, (uint32_t)dup * RB, bar);
+                if (MODE != APPLY_AX)      // the rows of b / y the consumers will read directly: pull them into L2
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pre + (size_t)s0 * RB), "r"((uint32_t)n * RB) : "memory");
+                phys += n;
+                if (phys >= R) phys -= R;
             }
         }
-        return;
-    }
-
-    // ---------------- consumers ----------------
-    const int l = lane % W, slot = lane / W;
-    unsigned n0 = 0, waited = 0, released = 0;
-    OutCtx out;
-    out.sa = a.mode == APPLY_AX ? 1.0 : (a.mode == APPLY_RESIDUAL ? -1.0 : a.alpha);
-    for (int64_t u = blockIdx.x; u < a.nunits; u += gridDim.x, n0 += nch) {
+    } else if (nchunks > 0) {
+        // ---------------- consumers ----------------
+        SmemLoad mem{sm};
+        OutDev<DIM, MODE, DOT> out;
+        out.sa = a.sa;
+        out.dsum = 0.0;
+        out.cm = 0; out.ml = out.mh = 0ull;
         LaneOp<DIM> op;
+        int64_t u = u0, ucur = -1;
+        int t = t0, i = 0;                 // 3D: line i of plane t; 2D: segment i of line t
+        int su = 0;                        // stream row of node 0 of the current group
+        int waited = 0, released = 0;
+        int sb = 0, pb = 0;                // stream row / ring row of the oldest row of the current window
+        double* ybase = nullptr;
+        const double* tbase = nullptr;
+        int step = warp;                   // tasks to skip before the next one of this warp
+        for (;;) {
+            // advance the cursor by `step` tasks
+            i += step;
+            for (;;) {
+                const int cnt = DIM == 3 ? t + 1 : ((m - t + 1 + (1 << a.seg_shift) - 1) >> a.seg_shift);
+                if (i < cnt) break;
+                i -= cnt;
+                if (++t > m) { t = 0; ++u; }
+                if (u * NPL + t >= P1) break;
+            }
+            if (u * NPL + t >= P1) break;
+            step = NW;
+            if (u != ucur) {
+                ucur = u;
+                const int64_t e = u * APPLY_W + lane;
 #pragma unroll
-        for (int q = 0; q < D::NC; ++q) op.ec[q] = __ldg(a.coef + (u * D::CS + q) * W + l);
-        op.ec[D::NC - 1] *= a.lambda;
-        op.cm = a.mode == APPLY_MULADD ? 0u : (unsigned)__ldg(a.cmask + u * W + l);
-        {
-            auto coefI = [&](int dir) {
-                double c = 0.0;
+                for (int q = 0; q < D::NC; ++q) op.ec[q] = __ldg(a.coef + (u * D::CS + q) * APPLY_W + lane);
+                op.ec[D::NC - 1] *= a.lambda;
+                interior_coefficients(op, a.T);
+                if (MODE != APPLY_MULADD) out.cm = (unsigned)__ldg(a.cmask + e);
+                if (DOT) {
+                    const uint8_t* mp = a.mult + u * 16 * APPLY_W + lane;
+                    unsigned long long lo = 0, hi = 0;
 #pragma unroll
-                for (int q = 0; q < D::NC; ++q) c = fma(op.ec[q], __ldg(a.L.G + dir * D::NC + q), c);
-                return c;
-            };
-            op.c0 = coefI(0);
-            op.cz = coefI(S::KP);
+                    for (int c = 0; c < 8; ++c) {
+                        lo |= (unsigned long long)__ldg(mp + c * APPLY_W) << (8 * c);
+                        hi |= (unsigned long long)__ldg(mp + (c + 8) * APPLY_W) << (8 * c);
+                    }
+                    out.ml = lo; out.mh = hi;
+                    out.mw[0] = (double)(unsigned)((lo >> 8) & 255ull);
+                    out.mw[1] = (double)(unsigned)((lo >> 16) & 255ull);
+                    out.mw[2] = (double)(unsigned)((lo >> 32) & 255ull);
+                    out.mw[3] = (double)(unsigned)(hi & 255ull);
+                }
+                su = (int)(u * nf - g0);
+                ybase = a.y + u * (int64_t)nf * APPLY_W + lane;
+                tbase = MODE == APPLY_AX ? nullptr : a.t + u * (int64_t)nf * APPLY_W + lane;
+            }
+            // rows of the task
+            LineGeo<DIM> g;
+            int rc, rm[Sweep<DIM>::NP], rp[Sweep<DIM>::NP], need, behind;
+            if constexpr (DIM == 3) {
+                const LineRows3 r = line_rows3(m, t, i, lat_off3(m, t));
+                g.L = r.L; g.k0 = 0; g.k1 = r.L;
+                rc = r.c; need = r.need; behind = r.behind;
 #pragma unroll
-            for (int q = 0; q < S::NP; ++q) { op.ca[q] = coefI(S::m0(q)); op.cb[q] = coefI(S::m1(q)); }
-        }
-        const int64_t ubase = u * (int64_t)nf * W + l;
-        out.y = a.y + ubase;
-        out.t = a.mode == APPLY_AX ? nullptr : (a.mode == APPLY_RESIDUAL ? a.b + ubase : a.y + ubase);
-
-        for (int t = warp; t < P.ntasks; t += NW) {
-            const int32_t* T = P.tasks + (size_t)t * TASK_INTS;
-            const int type = __ldg(T), clo = __ldg(T + 1), chi = __ldg(T + 2);
-            // Advance this warp's view of the chunk stream: observe every chunk up to n0+chi, hand back
-            // every chunk below n0+clo.  A slot is only released after its chunk was seen (an early
-            // arrival would be counted in the previous phase of the empty barrier), and releases are
-            // not postponed behind a wait (the producer may need them to load what we wait for).
+                for (int q = 0; q < Sweep<DIM>::NP; ++q) { rm[q] = r.rm[q]; rp[q] = r.rp[q]; }
+            } else {
+                const int k0 = i << a.seg_shift;
+                const LineRows2 r = line_rows2(m, t, k0, min(m - t + 1, k0 + (1 << a.seg_shift)));
+                g.L = r.L; g.k0 = k0; g.k1 = min(r.L, k0 + (1 << a.seg_shift));
+                rc = r.c; need = r.need; behind = r.behind;
+                rm[0] = r.rm[0]; rp[0] = r.rp[0];
+            }
+            // observe every chunk up to the one holding the last row this task reads, hand back the chunks
+            // below its window (an arrival on an empty barrier must not overtake the phase of the previous
+            // user of the slot, which is guaranteed once the chunk itself has been seen).
+            // A slot is handed back only after its chunk was seen, and hand-backs are not postponed behind a
+            // wait (the producer may need them to load what this warp waits for).
             {
-                const unsigned need = n0 + chi, lo = n0 + clo;
-                while (waited <= need || released < lo) {
-                    if (released < lo && released < waited) {
+                const int qn = (su + need) >> CS, qb = (su + behind) >> CS;
+                while (waited <= qn || released < qb) {
+                    if (released < qb && released < waited) {
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&empty_bar[released % K]);
+                        if (lane == 0) mbar_arrive(&empty_bar[released & (APPLY_Q - 1)]);
                         ++released;
                     } else {
-                        mbar_wait(&full_bar[waited % K], (waited / K) & 1u);
+                        mbar_wait(&full_bar[waited & (APPLY_Q - 1)], (waited >> APPLY_QS) & 1u);
                         ++waited;
                     }
                 }
             }
-            const int b0 = ZD + (int)((n0 + clo) % K) * SD;
-            const int b1 = ZD + (int)((n0 + clo + 1) % K) * SD;
-            const int b2 = ZD + (int)((n0 + clo + 2) % K) * SD;
-            int d[SLOT_INTS];
-            {
-                const int4* src = reinterpret_cast<const int4*>(T + 4 + slot * SLOT_INTS);
-                const int4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2);
-                d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w;
-                d[4] = v1.x; d[5] = v1.y; d[6] = v1.z; d[7] = v1.w;
-                d[8] = v2.x; d[9] = v2.y; d[10] = v2.z; d[11] = v2.w;
+            // ring rows: the window start moves monotonically, every line starts less than R rows after it
+            pb += su + behind - sb;
+            sb = su + behind;
+            while (pb >= R) pb -= R;
+            auto ring = [&](int row) {
+                int p = pb + (row - behind);
+                if (p >= R) p -= R;
+                return p * APPLY_W + lane;
+            };
+            g.bc = ring(rc);
+#pragma unroll
+            for (int q = 0; q < Sweep<DIM>::NP; ++q) { g.bm[q] = ring(rm[q]); g.bp[q] = ring(rp[q]); }
+            out.yl = ybase + (int64_t)rc * APPLY_W;
+            out.tl = MODE == APPLY_AX ? nullptr : tbase + (int64_t)rc * APPLY_W;
+            if constexpr (DIM == 3) run_line3(op, a.T, mem, APPLY_W, g, t, i, out);
+            else run_line2(op, a.T, mem, APPLY_W, g, t, out);
+        }
+        // hand every remaining chunk back (other warps may still need the slots they occupy)
+        while (released < nchunks) {
+            if (waited <= released) {
+                mbar_wait(&full_bar[waited & (APPLY_Q - 1)], (waited >> APPLY_QS) & 1u);
+                ++waited;
             }
-            if (type == 0) sweep_task<DIM, W, 0>(sm, d, b0, b1, b2, 0, l, op, out);
-            else if (type == 1) sweep_task<DIM, W, S::FACE_A>(sm, d, b0, b1, b2, 0, l, op, out);
-            else if (type == 2) sweep_task<DIM, W, S::FACE_B>(sm, d, b0, b1, b2, 0, l, op, out);
-            else node_task<DIM, W>(sm, d[0], P.nodetab, a.L.G, b0, b1, b2, 0, l, op, out);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[released & (APPLY_Q - 1)]);
+            ++released;
         }
+        dsum = out.dsum;
     }
-    // hand every remaining slot back: other warps may still need chunks that reuse them
-    while (released < n0) {
-        if (waited <= released) {
-            mbar_wait(&full_bar[waited % K], (waited / K) & 1u);
-            ++waited;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[released % K]);
-        ++released;
-    }
+    if (DOT) block_reduce_finish(dsum, a.red, a.dot_post, 0);
 }
 
-template <int DIM, int W>
-static int launch_apply_w(const ApplyArgs& a, int ctas_per_sm, size_t smem, cudaStream_t st) {
-    auto kern = ctas_per_sm >= 2 ? apply_kernel<DIM, W, 288, 2> : apply_kernel<DIM, W, 288, 1>;
-    static size_t configured[2] = {0, 0};
-    const int ki = ctas_per_sm >= 2 ? 1 : 0;
-    if (smem > configured[ki]) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-        configured[ki] = smem;
+// ring size and launch shape of one level
+ApplyConfig make_apply_config(int dim, int m, int nf, int W) {
+    ApplyConfig c{};
+    auto envi = [](const char* name, int dflt) {
+        const char* v = getenv(name);
+        return v ? atoi(v) : dflt;
+    };
+    c.nwarps = std::max(1, std::min(15, envi("HMG_APPLY_WARPS", 15)));
+    c.chunk_shift = std::max(2, std::min(7, envi("HMG_APPLY_CHUNK_SHIFT", 5)));
+    c.ctas_per_sm = 1;
+    int seg_shift = std::max(2, std::min(8, envi("HMG_APPLY_SEG_SHIFT", 4)));
+    c.seg = dim == 2 ? seg_shift : 30;
+    c.spill_rows = m + 3;
+    // the largest window of a task: rows from the oldest to the newest row it reads
+    int window = 1;
+    if (dim == 3) {
+        for (int t = 0; t <= m; ++t)
+            for (int i = 0; i <= t; ++i) {
+                const LineRows3 r = line_rows3(m, t, i, lat_off3(m, t));
+                window = std::max(window, r.need - r.behind + 1);
+            }
+    } else {
+        for (int i = 0; i <= m; ++i) {
+            const LineRows2 r = line_rows2(m, i, 0, m - i + 1);
+            window = std::max(window, r.need - r.behind + 1);
+        }
     }
+    const int CH = 1 << c.chunk_shift;
+    const int rowb = W * 8;
+    const int max_rows = (227 * 1024 - 2048) / rowb - c.spill_rows;
+    const int min_rows = window + 2 * CH;
+    int R = envi("HMG_APPLY_RING_ROWS", max_rows);
+    R = std::min(R, std::min(max_rows, (APPLY_Q - 2) * CH));
+    if (R < min_rows) R = min_rows;
+    c.ring_rows = R <= max_rows ? R : -1;        // -1: the level does not fit (refused by the launcher)
+    c.smem_bytes = (size_t)(R + c.spill_rows) * rowb;
+    (void)nf;
+    return c;
+}
+
+template <int DIM, int MODE, bool DOT>
+static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
+    static size_t configured = 0;
     static int sms = 0;
+    auto kern = apply_kernel<DIM, MODE, DOT>;
+    if (a.cfg.smem_bytes > configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.cfg.smem_bytes) != cudaSuccess) return 0;
+        configured = a.cfg.smem_bytes;
+    }
     if (sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int threads = (a.P.nwarps + 1) * 32;
-    const int64_t maxgrid = (int64_t)sms * (ctas_per_sm >= 2 ? 2 : 1);
-    dim3 grid((unsigned)std::min<int64_t>(a.nunits, maxgrid));
-    kern<<<grid, threads, smem, st>>>(a);
+    ApplyParams<DIM> p;
+    memcpy(&p.T, a.tab, sizeof(p.T));
+    p.x = a.x; p.y = a.y;
+    p.t = MODE == APPLY_RESIDUAL ? a.b : (MODE == APPLY_MULADD ? a.y : nullptr);
+    p.coef = a.coef; p.cmask = a.cmask; p.mult = a.mult;
+    p.nunits = a.nunits;
+    p.sa = MODE == APPLY_MULADD ? a.alpha : 1.0;
+    p.lambda = a.lambda;
+    p.m = a.L.m; p.nf = a.L.nf;
+    p.nwarps = a.cfg.nwarps; p.R = a.cfg.ring_rows; p.SP = a.cfg.spill_rows; p.cs = a.cfg.chunk_shift;
+    p.seg_shift = a.cfg.seg;
+    p.dot_post = a.dot_post;
+    p.red = a.red;
+    const int64_t planes = a.nunits * (a.L.m + 1);
+    int64_t grid = std::min<int64_t>((int64_t)sms * a.cfg.ctas_per_sm, planes);
+    if (DOT) grid = std::min<int64_t>(grid, a.red.max_blocks);
+    kern<<<(unsigned)grid, (a.cfg.nwarps + 1) * 32, a.cfg.smem_bytes, st>>>(p);
     return 1;
 }
 
-int launch_apply(int dim, const ApplyArgs& a, int ctas_per_sm, size_t smem_bytes, cudaStream_t st) {
+template <int DIM> static int launch_apply_d(const ApplyArgs& a, cudaStream_t st) {
+    if (a.mode == APPLY_AX) return a.dot_post >= 0 ? launch_apply_t<DIM, APPLY_AX, true>(a, st) : launch_apply_t<DIM, APPLY_AX, false>(a, st);
+    if (a.mode == APPLY_RESIDUAL) return launch_apply_t<DIM, APPLY_RESIDUAL, false>(a, st);
+    return launch_apply_t<DIM, APPLY_MULADD, false>(a, st);
+}
+
+int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st) {
     if (a.nunits == 0) return 0;
-    const int W = a.L.W;
-    if (dim == 3) return W == 16 ? launch_apply_w<3, 16>(a, ctas_per_sm, smem_bytes, st) : launch_apply_w<3, 8>(a, ctas_per_sm, smem_bytes, st);
-    return W == 16 ? launch_apply_w<2, 16>(a, ctas_per_sm, smem_bytes, st) : launch_apply_w<2, 8>(a, ctas_per_sm, smem_bytes, st);
+    if (a.L.W != APPLY_W || a.cfg.ring_rows <= 0) return -1;
+    return dim == 3 ? launch_apply_d<3>(a, st) : launch_apply_d<2>(a, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -567,49 +634,6 @@ int launch_interp_add(int, const LevelView& Lf, const LevelView& Lc, int64_t nun
 // ------------------------------------------------------------------------------------------
 // K3: reductions and fused CG vector updates (scalars stay on the device)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// deterministic: fixed grid, fixed per-block tree, partials summed in block order by the last block
-__device__ __forceinline__ void block_reduce_finish(double v, const Reducer& R, int post, int slot) {
-    __shared__ double wsum[8];
-    __shared__ bool last;
-    v = warp_sum(v);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) wsum[wid] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += wsum[w];
-        R.partials[blockIdx.x] = s;
-        __threadfence();
-        const unsigned t = atomicAdd(R.ticket, 1u);
-        last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    double s = 0.0;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += __ldcg(R.partials + b);
-    s = warp_sum(s);
-    __syncthreads();
-    if (lane == 0) wsum[wid] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double tot = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += wsum[w];
-        double* S = R.scalars;
-        if (post == POST_STORE) S[slot] = tot;
-        else if (post == POST_RHO) S[S_RHO] = tot;
-        else if (post == POST_PAP) { S[S_PAP] = tot; S[S_ALPHA] = S[S_RHO] / tot; }
-        else if (post == POST_RSQR) { S[S_RSQR] = tot; S[S_BETA] = tot / S[S_RHO]; S[S_RHO] = tot; }
-        *R.ticket = 0u;
-    }
-}
-
 __global__ void __launch_bounds__(256) dot_kernel(const Reducer R, const double* __restrict__ a, const double* __restrict__ b,
                                                   int64_t n, int post, int slot) {
     double s = 0.0;

@@ -26,34 +26,12 @@ struct LevelView {
     int vpos[4];                // packed lattice index of the reference vertices
 };
 
-struct ApplyPlanView {
-    int nchunks, nslots, slot_doubles, zero_doubles, ntasks, nwarps;
-    const int32_t* chunk_start;  // [nchunks + 1]
-    const int32_t* tasks;        // [ntasks][PLAN_TASK_INTS]
-    const uint32_t* nodetab;     // [nspecial][16]
-};
-
 struct TopoView {
     int64_t ne;
     int64_t nedges, nverts;                 // multi-owner cells handled cell by cell (3D: edges + vertices, 2D: vertices)
     const int64_t *edge_off, *vert_off;
     const int32_t *edge_own, *vert_own;     // element*8 + local id, ascending element
     const int32_t* partner;                 // [ne][4]: other owner (element*8 + local id) of local face (3D) / edge (2D), -1 none
-};
-
-enum ApplyMode { APPLY_AX = 0, APPLY_RESIDUAL = 1, APPLY_MULADD = 2 };
-
-struct ApplyArgs {
-    LevelView L;
-    ApplyPlanView P;
-    int64_t nunits;
-    const double* coef;        // [nunits][CS][W]  |J| P (upper triangle) and |J|, element-interleaved
-    const uint16_t* cmask;     // [nunits * W]
-    const double* x;           // input
-    double* y;                 // output
-    const double* b;           // rhs for APPLY_RESIDUAL
-    double alpha, lambda;
-    int mode;
 };
 
 // scalar slots on the device (no host round trip inside a V-cycle)
@@ -67,8 +45,41 @@ struct Reducer {
     int max_blocks;
 };
 
+enum ApplyMode { APPLY_AX = 0, APPLY_RESIDUAL = 1, APPLY_MULADD = 2 };
+
+// launch configuration of the streaming apply kernel for one level (chosen on the host, api.cu)
+struct ApplyConfig {
+    int nwarps;        // consumer warps per CTA (one more warp issues the TMA copies)
+    int ring_rows;     // rows (W doubles each) of the shared-memory ring
+    int spill_rows;    // rows mirrored behind the ring so that a line never wraps
+    int chunk_shift;   // log2(rows per TMA chunk)
+    int seg;           // 2D: nodes per task (a line is split into segments); 3D: unused
+    int ctas_per_sm;
+    size_t smem_bytes;
+};
+
+struct ApplyArgs {
+    LevelView L;
+    ApplyConfig cfg;
+    int64_t nunits;
+    const double* tab;         // host pointer: StencilTab<DIM> of the level (copied into the parameter block)
+    const double* coef;        // [nunits][CS][W]  |J| P (upper triangle) and |J|, element-interleaved
+    const uint16_t* cmask;     // [nunits * W]
+    const uint8_t* mult;       // [nunits][16][W] owners of the cell of every node class (dot weights), or null
+    const double* x;           // input
+    double* y;                 // output
+    const double* b;           // rhs for APPLY_RESIDUAL
+    double alpha, lambda;
+    int mode;
+    // fused reduction  sum_entries owners(entry) * x * y  ( = dot(x, broadcast(y)) over all stored entries,
+    // src/multigrid.jl:62 ) -> Reducer post-op; only with APPLY_AX
+    int dot_post;              // -1: none
+    Reducer red;
+};
+
 // launchers (all asynchronous on `st`); return the number of kernels launched
-int launch_apply(int dim, const ApplyArgs& a, int ctas_per_sm, size_t smem_bytes, cudaStream_t st);
+int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st);
+ApplyConfig make_apply_config(int dim, int m, int nf, int W);
 int launch_interface_sum(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
 int launch_zero_all_but_one(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
 int launch_apply_constraint(int dim, const LevelView& L, int64_t nbelems, const int32_t* belems, const uint16_t* cmask,

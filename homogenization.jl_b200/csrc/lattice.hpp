@@ -1,9 +1,16 @@
 // Lattice index arithmetic shared by the kernels and the host-side verification code.
 //
 // The refined reference simplex of level l is the set of integer points (i, j[, k]) >= 0 with
-// i + j [+ k] <= m, m = 2^(l-1) (reference vertex 1 = origin, vertex 2 = m e_1, ...).  Nodes are
-// stored in lexicographic order, last coordinate fastest ("packed" index).  The operator couples a
-// node with its neighbours along 7 (3D) / 3 (2D) lattice directions and their opposites.
+// i + j [+ k] <= m, m = 2^(l-1) (reference vertex 1 = origin, vertex 2 = m e_1, ...).  The operator
+// couples a node with its neighbours along 7 (3D) / 3 (2D) lattice directions and their opposites.
+//
+// "Packed" node order of the device vectors:
+//   2D  lexicographic (i, j), j fastest: line i has m - i + 1 nodes.
+//   3D  DIAGONAL-PLANE order (t = i + j, then i, then k), k fastest: plane t holds the t + 1 lines
+//       (i, t - i), i = 0..t, which ALL have the same length m - t + 1.  The stencil of a node only
+//       reaches planes t - 1, t, t + 1, and a plane has at most (m/2 + 1)^2 nodes (vs (m+1)(m+2)/2 for
+//       planes i = const), so the streaming window of the apply kernel is half as large, and the
+//       lines of a plane are interchangeable work items.
 #pragma once
 #ifdef __CUDACC__
 #define HMG_HD __host__ __device__ __forceinline__
@@ -16,10 +23,14 @@ namespace hmg {
 HMG_HD int lat_tri(int q) { return (q + 1) * (q + 2) / 2; }
 HMG_HD int lat_tot3(int q) { return (q + 1) * (q + 2) * (q + 3) / 6; }
 HMG_HD int lat_pack2(int m, int i, int j) { return lat_tri(m) - lat_tri(m - i) + j; }
+// first packed index of diagonal plane t: sum_{s<t} (s + 1)(m - s + 1)
+HMG_HD int lat_off3(int m, int t) { return (m + 1) * t * (t + 1) / 2 - (t - 1) * t * (t + 1) / 3; }
 HMG_HD int lat_pack3(int m, int i, int j, int k) {
-    const int n1 = m - i;
-    return lat_tot3(m) - lat_tot3(n1) + lat_tri(n1) - lat_tri(n1 - j) + k;
+    const int t = i + j;
+    return lat_off3(m, t) + i * (m - t + 1) + k;
 }
+// first packed index of line i (2D)
+HMG_HD int lat_off2(int m, int i) { return i * (m + 1) - i * (i - 1) / 2; }
 
 template <int DIM> struct Dims;
 template <> struct Dims<3> { static constexpr int NDIR = 15, NC = 7, NCLS = 16, CS = 8; };
@@ -42,14 +53,16 @@ HMG_HD void lat_dir2(int d, int& di, int& dj) {
 // packed-index offsets of the stencil neighbours of node (i, j, *) at lattice size m
 template <int DIM> HMG_HD void neighbour_offsets(int m, int i, int j, int* off);
 template <> HMG_HD void neighbour_offsets<3>(int m, int i, int j, int* off) {
-    const int n1 = m - i;
-    const int A = n1 - j + 1;                       // length of row (i, j)
-    const int U = (n1 + 1) * (n1 + 2) / 2 - j;      // (i+1, j, k) - (i, j, k)
-    const int V = U + n1 + 2;                       // (i, j, k) - (i-1, j, k)
-    off[0] = 0;           off[1] = U;       off[2] = -V;
-    off[3] = A;           off[4] = -(A + 1); off[5] = 1;       off[6] = -1;
-    off[7] = A + 1 - V;   off[8] = U - A;   off[9] = 1 - V;   off[10] = U - 1;
-    off[11] = -A;         off[12] = A - 1;  off[13] = U - A + 1; off[14] = A - V;
+    const int t = i + j;
+    const int L = m - t + 1;                        // length of every line of plane t
+    const int D = (t + 2) * L - 1 - i;              // (i+1, j, k) - (i, j, k): plane t+1, line i+1
+    const int E = (t + 1) * L - i;                  // (i, j+1, k) - (i, j, k): plane t+1, line i
+    const int F = i - (t + 1) * (L + 1);            // (i-1, j, k) - (i, j, k): plane t-1, line i-1
+    const int G = i - t * (L + 1);                  // (i, j-1, k) - (i, j, k): plane t-1, line i
+    off[0] = 0;       off[1] = D;      off[2] = F;
+    off[3] = E;       off[4] = G;      off[5] = 1;       off[6] = -1;
+    off[7] = -L;      off[8] = L;      off[9] = F + 1;   off[10] = D - 1;
+    off[11] = G + 1;  off[12] = E - 1; off[13] = L + 1;  off[14] = -L - 1;
 }
 template <> HMG_HD void neighbour_offsets<2>(int m, int i, int, int* off) {
     const int B = m - i + 1;                        // length of row i

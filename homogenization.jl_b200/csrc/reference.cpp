@@ -15,6 +15,7 @@
 
 #include "hmg_host.hpp"
 #include "lattice.hpp"
+#include "apply_core.cuh"
 
 namespace hmg {
 
@@ -146,6 +147,51 @@ void lattice_gradients(int dim, const I3* v, int g[4][3]) {
         for (int d = dim; d < 3; ++d) g[a][d] = 0;
 }
 
+// integer stencil of a refined reference mesh: acc[p][dir][c] (stiffness components, then mass)
+template <class Lat, class Pack>
+std::vector<int> integer_stencil(int dim, const IntMesh& mesh, int nf, Lat lat, Pack pack) {
+    const int nv = dim + 1, ndir = dim == 3 ? NDIR3 : NDIR2, nc = dim == 3 ? NC3 : NC2;
+    std::vector<int> acc((size_t)nf * ndir * nc, 0);
+    for (const auto& el : mesh.elems) {
+        I3 v[4];
+        for (int a = 0; a < nv; ++a) v[a] = lat(el[a]);
+        int g[4][3];
+        lattice_gradients(dim, v, g);
+        for (int a = 0; a < nv; ++a) {
+            int pa = pack(v[a]);
+            for (int b = 0; b < nv; ++b) {
+                int d = dir_index(dim, v[b][0] - v[a][0], v[b][1] - v[a][1], v[b][2] - v[a][2]);
+                HMG_CHECK(d >= 0, "fine-element edge is not one of the stencil directions");
+                int* dst = &acc[((size_t)pa * ndir + d) * nc];
+                int c = 0;
+                for (int k = 0; k < dim; ++k)
+                    for (int q = k; q < dim; ++q, ++c)
+                        dst[c] += g[a][k] * g[b][q] + (k != q ? g[a][q] * g[b][k] : 0);
+                dst[c] += (a == b ? 2 : 1);
+            }
+        }
+    }
+    return acc;
+}
+
+// the interior stencil in lattice units, taken from the m = 4 refinement (the coarsest one that has
+// an interior node in 2D and 3D); every level is checked against it
+std::vector<int> interior_stencil(int dim) {
+    const int nv = dim + 1, ndir = dim == 3 ? NDIR3 : NDIR2, nc = dim == 3 ? NC3 : NC2;
+    IntMesh mesh;
+    mesh.nodes.push_back({0, 0, 0});
+    mesh.nodes.push_back({4, 0, 0});
+    mesh.nodes.push_back({0, 4, 0});
+    if (dim == 3) mesh.nodes.push_back({0, 0, 4});
+    mesh.elems.push_back(dim == 3 ? I4{0, 1, 2, 3} : I4{0, 1, 2, -1});
+    for (int l = 0; l < 2; ++l) mesh = refine(mesh, edge_graph(mesh, nv), dim);
+    auto lat = [&](int n) -> I3 { return mesh.nodes[n]; };
+    auto pack = [&](const I3& c) { return dim == 3 ? pack3(4, c[0], c[1], c[2]) : pack2(4, c[0], c[1]); };
+    const std::vector<int> acc = integer_stencil(dim, mesh, (int)mesh.nodes.size(), lat, pack);
+    const int p = dim == 3 ? pack3(4, 1, 1, 1) : pack2(4, 1, 1);
+    return std::vector<int>(acc.begin() + (size_t)p * ndir * nc, acc.begin() + (size_t)(p + 1) * ndir * nc);
+}
+
 }  // namespace
 
 RefElement build_reference(int dim, int nlevels) {
@@ -178,6 +224,8 @@ RefElement build_reference(int dim, int nlevels) {
         static const int tab2[4] = {0, 3, 1, 5};                    // index = pi*2 + pj
         return tab2[pi * 2 + pj];
     };
+
+    const std::vector<int> interior = interior_stencil(dim);
 
     ref.lv.resize(nlevels);
     for (int l = 1; l <= nlevels; ++l) {
@@ -220,26 +268,7 @@ RefElement build_reference(int dim, int nlevels) {
 
         // (2) integer stencil: acc[p][dir][c]
         const int ndir = ref.ndir, nc = ref.nc;
-        std::vector<int> acc((size_t)L.nf * ndir * nc, 0);
-        for (const auto& el : mesh.elems) {
-            I3 v[4];
-            for (int a = 0; a < nv; ++a) v[a] = lat(el[a]);
-            int g[4][3];
-            lattice_gradients(dim, v, g);
-            for (int a = 0; a < nv; ++a) {
-                int pa = pack(v[a]);
-                for (int b = 0; b < nv; ++b) {
-                    int d = dir_index(dim, v[b][0] - v[a][0], v[b][1] - v[a][1], v[b][2] - v[a][2]);
-                    HMG_CHECK(d >= 0, "fine-element edge is not one of the stencil directions");
-                    int* dst = &acc[((size_t)pa * ndir + d) * nc];
-                    int c = 0;
-                    for (int k = 0; k < dim; ++k)
-                        for (int q = k; q < dim; ++q, ++c)
-                            dst[c] += g[a][k] * g[b][q] + (k != q ? g[a][q] * g[b][k] : 0);
-                    dst[c] += (a == b ? 2 : 1);
-                }
-            }
-        }
+        const std::vector<int> acc = integer_stencil(dim, mesh, L.nf, lat, pack);
         // class invariance + table
         double fact = dim == 3 ? 6.0 : 2.0;
         double s_stiff = dim == 3 ? 1.0 / (fact * m) : 1.0 / fact;
@@ -263,20 +292,72 @@ RefElement build_reference(int dim, int nlevels) {
             }
         }
         L.mass_total = mass_int * s_mass;
-        // facts the apply kernel relies on: the interior stencil is symmetric (one coefficient per
-        // +-direction pair) and the stencil of a node in the interior of ONE reference face is the
-        // interior stencil with weights 0 (outward) / 1/2 (inside the face, centre) / 1 (inward)
-        if (rep[0] >= 0)
-            for (int d = 1; d < ndir; ++d)
-                for (int c = 0; c < nc; ++c)
-                    HMG_CHECK(L.G[(size_t)d * nc + c] == L.G[(size_t)(d & 1 ? d + 1 : d - 1) * nc + c],
-                              "interior stencil is not symmetric");
-        for (int cls = 1; cls < ref.ncls; cls <<= 1) {
-            if (rep[cls] < 0 || rep[0] < 0) continue;
-            for (int d = 0; d < ndir; ++d)
-                for (int c = 0; c < nc; ++c)
-                    HMG_CHECK(L.G[((size_t)cls * ndir + d) * nc + c] == face_weight(dim, cls, d) * L.G[(size_t)d * nc + c],
-                              "face stencil is not the weighted interior stencil");
+        // The rule the apply kernel is compiled with (apply_core.cuh): the coefficient of the lattice
+        // segment (n, n+d) is the interior one (segment inside the simplex), one half of it (segment in
+        // exactly one reference face) or a tabulated value (segment along a reference edge); the diagonal
+        // is the interior one, one half of it (one face) or a tabulated value.  Verified node by node in
+        // exact integer arithmetic; the interior stencil itself is symmetric.
+        for (int d = 1; d < ndir; ++d)
+            for (int c = 0; c < nc; ++c)
+                HMG_CHECK(interior[(size_t)d * nc + c] == interior[(size_t)(d & 1 ? d + 1 : d - 1) * nc + c],
+                          "interior stencil is not symmetric");
+        std::vector<int> edge_int((size_t)ref.ncls * nc, 0);
+        std::vector<char> edge_set(ref.ncls, 0);
+        for (int p = 0; p < L.nf; ++p) {
+            const uint32_t info = L.nodeinfo[p];
+            const int i = info & 255, j = (info >> 8) & 255, k = (info >> 16) & 255, cls = info >> 24;
+            const int* row = &acc[(size_t)p * ndir * nc];
+            int off[NDIR3];
+            if (dim == 3) neighbour_offsets<3>(m, i, j, off); else neighbour_offsets<2>(m, i, j, off);
+            const int npc = popc4(cls);
+            for (int c = 0; c < nc; ++c) {
+                if (npc == 0) HMG_CHECK(row[c] == interior[c], "interior diagonal differs between levels");
+                if (npc == 1) HMG_CHECK(2 * row[c] == interior[c], "face diagonal is not half the interior one");
+            }
+            for (int d = 1; d < ndir; ++d) {
+                const bool in = dim == 3 ? neighbour_inside<3>(m, i, j, k, d) : neighbour_inside<2>(m, i, j, k, d);
+                const int om = dim == 3 ? out_mask<3>(d) : out_mask<2>(d);
+                HMG_CHECK(in == ((cls & om) == 0), "out_mask disagrees with the lattice");
+                const int* e = row + d * nc;
+                if (!in) {
+                    for (int c = 0; c < nc; ++c) HMG_CHECK(e[c] == 0, "stencil entry towards a node outside the simplex");
+                    continue;
+                }
+                const int q = p + off[d];
+                HMG_CHECK(q >= 0 && q < L.nf, "neighbour offset leaves the element");
+                const uint32_t qi = L.nodeinfo[q];
+                int dv[3] = {0, 0, 0};
+                for (int a = 0; a < dim; ++a) dv[a] = dim == 3 ? DIRS3[d][a] : DIRS2[d][a];
+                HMG_CHECK((int)(qi & 255) == i + dv[0] && (int)((qi >> 8) & 255) == j + dv[1] &&
+                              (int)((qi >> 16) & 255) == k + dv[2], "neighbour offset points to the wrong node");
+                const int seg = cls & (int)(qi >> 24);
+                HMG_CHECK(seg == (dim == 3 ? seg_class<3>(cls, d) : seg_class<2>(cls, d)), "segment class rule violated");
+                const int ns = popc4(seg);
+                for (int c = 0; c < nc; ++c) {
+                    if (ns == 0) HMG_CHECK(e[c] == interior[(size_t)d * nc + c], "interior segment coefficient differs");
+                    else if (ns == 1) HMG_CHECK(2 * e[c] == interior[(size_t)d * nc + c], "face segment is not half the interior one");
+                }
+                if (ns == 2) {
+                    if (!edge_set[seg]) { edge_set[seg] = 1; std::copy(e, e + nc, &edge_int[(size_t)seg * nc]); }
+                    else HMG_CHECK(std::equal(e, e + nc, &edge_int[(size_t)seg * nc]), "edge segment coefficient is not unique");
+                }
+                HMG_CHECK(ns <= 2, "a lattice segment lies in three reference faces");
+            }
+        }
+        {
+            const int npair = dim == 3 ? Pairs<3>::N : Pairs<2>::N;
+            L.gi.assign((size_t)npair * nc, 0.0);
+            L.gc.assign((size_t)ref.ncls * nc, 0.0);
+            L.ge.assign((size_t)ref.ncls * nc, 0.0);
+            for (int r = 0; r < npair; ++r) {
+                const int d = dim == 3 ? pair_dir<3>(r) : pair_dir<2>(r);
+                for (int c = 0; c < nc; ++c) L.gi[(size_t)r * nc + c] = interior[(size_t)d * nc + c] * (c == nc - 1 ? s_mass : s_stiff);
+            }
+            for (int cls = 0; cls < ref.ncls; ++cls)
+                for (int c = 0; c < nc; ++c) {
+                    L.gc[(size_t)cls * nc + c] = L.G[((size_t)cls * ndir) * nc + c];
+                    L.ge[(size_t)cls * nc + c] = edge_int[(size_t)cls * nc + c] * (c == nc - 1 ? s_mass : s_stiff);
+                }
         }
 
         // (3) pairing rule: on every reference face / edge the ascending hierarchical order is the

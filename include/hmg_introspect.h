@@ -36,11 +36,12 @@ int hmg_host_class_of(int dim, int kind, int lid);
 int hmg_host_element_coefficients(int dim, int64_t ne, int64_t nn, const double* nodes, const int64_t* elems1,
                                   const double* sigma, double* coef, int stride);
 
-/* executes the streaming plan of the apply kernel (csrc/plan.cpp) for one element on the host:
- * y = A x in lattice order, coef = |J| P (upper triangle), lambda |J|; info[9] = nchunks, nslots,
- * slot_nodes, ntasks, nwarps, ctas_per_sm, smem_bytes, nodes computed by sweeps, by the generic path */
-int hmg_host_apply_plan(int dim, int nlevels, int level, int W, const double* coef, const double* x, double* y,
-                        int64_t* info);
+/* runs the apply kernel's task enumeration and line sweeps (csrc/apply_core.cuh, the templates the
+ * device kernel instantiates) for one element on the host: y = A x in lattice order, coef = |J| P (upper
+ * triangle), lambda |J|; 2D lines are split into segments of 2^seg_shift nodes; info[4] = tasks, largest
+ * row window of a task, ring rows, shared-memory bytes of the launch configuration */
+int hmg_host_apply_sweep(int dim, int nlevels, int level, int seg_shift, const double* coef, const double* x,
+                         double* y, int64_t* info);
 
 #ifdef __cplusplus
 }

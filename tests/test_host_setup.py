@@ -40,9 +40,13 @@ def test_lattice_numbering_is_a_permutation_matching_node_coordinates(dim, nleve
         m = 2 ** (level - 1)
         assert sizes[0] == m and sizes[1] == mesh.nnodes
         assert sorted(h2l) == list(range(mesh.nnodes))
-        # lexicographic order of the lattice coordinates, last coordinate fastest
+        # 2D: lexicographic order of the lattice coordinates (i, j), j fastest;
+        # 3D: diagonal-plane order (i + j, i, k), k fastest (csrc/lattice.hpp)
         lat = np.rint(mesh.nodes * m).astype(int)
-        order = np.lexsort(tuple(lat[:, d] for d in range(dim - 1, -1, -1)))
+        if dim == 2:
+            order = np.lexsort((lat[:, 1], lat[:, 0]))
+        else:
+            order = np.lexsort((lat[:, 2], lat[:, 0], lat[:, 0] + lat[:, 1]))
         expect = np.empty(mesh.nnodes, dtype=int)
         expect[order] = np.arange(mesh.nnodes)
         assert np.array_equal(h2l, expect)
@@ -200,10 +204,11 @@ def test_element_coefficients_match_oracle():
         assert np.allclose(coef[:, c], g.det, rtol=1e-14)
 
 
-@pytest.mark.parametrize("dim,nlevels,W", [(2, 8, 16), (2, 6, 8), (3, 5, 16), (3, 6, 8), (3, 4, 8)])
-def test_apply_plan_reproduces_the_local_operator(dim, nlevels, W):
-    """The streaming plan of the apply kernel (chunks, line sweeps with face weights, generic
-    edge/vertex nodes), executed on the host for one element, equals the dense local operator
+@pytest.mark.parametrize("dim,nlevels,seg_shift", [(2, 8, 4), (2, 6, 5), (2, 4, 2), (3, 6, 4), (3, 4, 4)])
+def test_apply_sweeps_reproduce_the_local_operator(dim, nlevels, seg_shift):
+    """The task enumeration and line sweeps of the apply kernel (csrc/apply_core.cuh: class dispatch,
+    compile-time segment weights, register sliding windows, row geometry in the diagonal-plane order),
+    executed on the host for one element, equal the dense local operator
     sum_kl |J| P_kl ops[k,l] + lambda |J| mass (src/apply_local_operators.jl:105-118) times x."""
     rng = np.random.default_rng(11)
     for level in range(1, nlevels + 1):
@@ -218,9 +223,9 @@ def test_apply_plan_reproduces_the_local_operator(dim, nlevels, W):
         x_l = np.empty(nf)
         x_l[h2l] = x_h                      # lattice order
         y_l = np.full(nf, np.nan)
-        info = np.zeros(9, dtype=np.int64)
-        L.check_host(lib.hmg_host_apply_plan(dim, nlevels, level, W, vp(coef), vp(x_l), vp(y_l), vp(info)))
+        info = np.zeros(4, dtype=np.int64)
+        L.check_host(lib.hmg_host_apply_sweep(dim, nlevels, level, seg_shift, vp(coef), vp(x_l), vp(y_l), vp(info)))
         expect = dense @ x_h
         assert np.abs(y_l[h2l] - expect).max() <= 1e-13 * np.abs(expect).max(), (level, info)
-        assert info[7] + info[8] == nf
-        assert 4 <= info[1] <= 8 and info[6] <= 227 * 1024
+        # the row window of every task fits the ring, the ring fits one SM
+        assert 0 < info[1] + 64 <= info[2] and info[3] <= 227 * 1024, info
