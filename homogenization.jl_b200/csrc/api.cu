@@ -801,6 +801,23 @@ int hmg_time_op(hmg_ctx* c, int op, int level, int steps, int reps, float* ms_ou
             do_apply(c, level, APPLY_AX, 1.0, c->vecp(level, HMG_P), c->vecp(level, HMG_AP), nullptr);
         } else if (op == 4) {
             do_broadcast(c, level, c->vecp(level, HMG_AP));
+        } else if (op == 5) {
+            do_apply(c, level, APPLY_RESIDUAL, 1.0, c->vecp(level, HMG_X), c->vecp(level, HMG_R), c->vecp(level, HMG_B));
+        } else if (op == 6) {
+            check_launch(c, launch_cg_update(c->red, c->vecp(level, HMG_X), c->vecp(level, HMG_P), c->vecp(level, HMG_R),
+                                             c->vecp(level, HMG_AP), c->nstored(level), c->stream));
+        } else if (op == 7) {
+            check_launch(c, launch_p_update(c->red, c->vecp(level, HMG_P), c->vecp(level, HMG_R), c->nstored(level), c->stream));
+        } else if (op == 8) {
+            check_launch(c, launch_copy_dot(c->red, c->vecp(level, HMG_R), c->vecp(level, HMG_P), c->nstored(level), c->stream));
+        } else if (op == 9) {
+            check_launch(c, launch_restrict(c->dim, c->level(level).view, c->level(level - 1).view, c->nunits,
+                                            c->vecp(level, HMG_R), c->vecp(level - 1, HMG_B), c->stream));
+        } else if (op == 10) {
+            check_launch(c, launch_interp_add(c->dim, c->level(level).view, c->level(level - 1).view, c->nunits,
+                                              c->vecp(level, HMG_X), c->vecp(level - 1, HMG_X), c->stream));
+        } else if (op == 11) {
+            do_apply(c, level, APPLY_AX, 1.0, c->vecp(level, HMG_P), c->vecp(level, HMG_AP), nullptr, POST_STORE);
         } else {
             throw Error("hmg: unknown op for hmg_time_op");
         }

@@ -200,19 +200,21 @@ HMG_HD void sweep_line(const LaneOp<DIM>& op, const StencilTab<DIM>& T, const Me
         }
     }
     const int kend = g.k1 < g.L - 1 ? g.k1 : g.L - 1;
-#pragma unroll 2
-    for (; k < kend; ++k) {
-        xp = mem(g.bc + (k + 1) * RS);
+    auto node = [&](int kk) {
+        xp = mem(g.bc + (kk + 1) * RS);
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
-            if (uses_minus_k<DIM, MID>(q) || uses_minus_km<DIM, MID>(q) || uses_minus_km<DIM, LAST>(q)) Mk[q] = mem(g.bm[q] + k * RS);
-            if (uses_plus_kp<DIM, MID>(q) || uses_plus_k<DIM, MID>(q) || uses_plus_k<DIM, LAST>(q)) Pp[q] = mem(g.bp[q] + (k + 1) * RS);
+            if (uses_minus_k<DIM, MID>(q) || uses_minus_km<DIM, MID>(q) || uses_minus_km<DIM, LAST>(q)) Mk[q] = mem(g.bm[q] + kk * RS);
+            if (uses_plus_kp<DIM, MID>(q) || uses_plus_k<DIM, MID>(q) || uses_plus_k<DIM, LAST>(q)) Pp[q] = mem(g.bp[q] + (kk + 1) * RS);
         }
-        out.template put<MID>(k, eval_node<DIM, MID>(op, T, xm, x0, xp, Mm, Mk, Pk, Pp), x0);
+        out.template put<MID>(kk, eval_node<DIM, MID>(op, T, xm, x0, xp, Mm, Mk, Pk, Pp), x0);
         xm = x0; x0 = xp;
 #pragma unroll
         for (int q = 0; q < NP; ++q) { Mm[q] = Mk[q]; Pk[q] = Pp[q]; }
-    }
+    };
+#pragma unroll 1
+    for (; k + 1 < kend; k += 2) { node(k); node(k + 1); }
+    if (k < kend) { node(k); ++k; }
     if (g.k1 == g.L) {     // k == L - 1
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
@@ -267,7 +269,7 @@ HMG_HD LineRows2 line_rows2(int m, int i, int k0, int k1) {
     const int kn = k1 - 1 < L - 2 ? k1 - 1 : L - 2;            // last node of the next line that is read
     r.need = i < m ? (kn >= 0 ? r.rm[0] + kn : r.c + k1 - 1) : r.c;
     if (r.need < r.c + (k1 < L ? k1 : L - 1)) r.need = r.c + (k1 < L ? k1 : L - 1);
-    r.behind = i > 0 ? r.rp[0] + k0 : r.c + (k0 > 0 ? k0 - 1 : 0);
+    r.behind = i > 0 ? r.rp[0] + k0 : r.c;      // monotone in task order (line 0 stays resident until line 1 starts)
     return r;
 }
 

@@ -131,7 +131,7 @@ template <int DIM> struct ApplyParams {
     const uint8_t* mult;
     int64_t nunits;
     double sa, lambda;
-    int m, nf, nwarps, R, SP, cs, seg_shift;
+    int m, nf, nwarps, R, SP, cs, seg_shift, run;
     int dot_post;
     Reducer red;
 };
@@ -164,12 +164,26 @@ template <int DIM, int MODE, bool DOT> struct OutDev {
         if (CLS == 8) return mw[3];
         return (double)(unsigned)((CLS < 8 ? (ml >> (8 * (CLS & 7))) : (mh >> (8 * (CLS & 7)))) & 255ull);
     }
+    // b / y of the next two nodes travel in registers (they come from L2, where the producer's bulk
+    // prefetch put them): the load of node k + 2 is issued before node k is finished
+    double tq0, tq1;
+    int klast;
+    __device__ __forceinline__ void begin(int k0, int k1) {
+        if (MODE == APPLY_AX) return;
+        klast = k1 - 1;
+        tq0 = __ldcs(tl + k0 * APPLY_W);
+        tq1 = __ldcs(tl + min(k0 + 1, klast) * APPLY_W);
+    }
     template <int CLS> __device__ __forceinline__ void put(int k, double acc, double x0) {
         const bool fixed = MODE != APPLY_MULADD && ((cm >> CLS) & 1u);
         double v;
         if (MODE == APPLY_AX) v = fixed ? 0.0 : acc;
-        else if (MODE == APPLY_RESIDUAL) v = fixed ? 0.0 : __ldcs(tl + k * APPLY_W) - acc;
-        else v = fma(sa, acc, __ldcs(tl + k * APPLY_W));
+        else {
+            const double tv = tq0;
+            tq0 = tq1;
+            tq1 = __ldcs(tl + min(k + 2, klast) * APPLY_W);
+            v = MODE == APPLY_RESIDUAL ? (fixed ? 0.0 : tv - acc) : fma(sa, acc, tv);
+        }
         yl[k * APPLY_W] = v;
         if (DOT) dsum = fma(weight<CLS>() * x0, v, dsum);
     }
@@ -187,7 +201,8 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
     __shared__ __align__(8) uint64_t full_bar[APPLY_Q], empty_bar[APPLY_Q];
     double* sm = reinterpret_cast<double*>(smem_raw);
     const int m = a.m, nf = a.nf, NW = a.nwarps, R = a.R, SP = a.SP, CS = a.cs, CH = 1 << a.cs;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
     const int NPL = m + 1;
 
     if (threadIdx.x == 0) {
@@ -251,8 +266,10 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
         out.dsum = 0.0;
         out.cm = 0; out.ml = out.mh = 0ull;
         LaneOp<DIM> op;
+        const int RL = DIM == 3 ? a.run : 1;     // 3D: consecutive lines of a plane per task
+        const int SEGS = a.seg_shift;           // 2D: log2(nodes per task)
         int64_t u = u0, ucur = -1;
-        int t = t0, i = 0;                 // 3D: line i of plane t; 2D: segment i of line t
+        int t = t0, i = 0;                 // 3D: run i of plane t; 2D: segment i of line t
         int su = 0;                        // stream row of node 0 of the current group
         int waited = 0, released = 0;
         int sb = 0, pb = 0;                // stream row / ring row of the oldest row of the current window
@@ -263,7 +280,7 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
             // advance the cursor by `step` tasks
             i += step;
             for (;;) {
-                const int cnt = DIM == 3 ? t + 1 : ((m - t + 1 + (1 << a.seg_shift) - 1) >> a.seg_shift);
+                const int cnt = DIM == 3 ? (t + RL) / RL : ((m - t + (1 << SEGS)) >> SEGS);
                 if (i < cnt) break;
                 i -= cnt;
                 if (++t > m) { t = 0; ++u; }
@@ -297,37 +314,45 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
                 ybase = a.y + u * (int64_t)nf * APPLY_W + lane;
                 tbase = MODE == APPLY_AX ? nullptr : a.t + u * (int64_t)nf * APPLY_W + lane;
             }
-            // rows of the task
+            // rows of the task: first line, number of lines, row window [behind, need]
             LineGeo<DIM> g;
-            int rc, rm[Sweep<DIM>::NP], rp[Sweep<DIM>::NP], need, behind;
+            int rc, rm[Sweep<DIM>::NP], rp[Sweep<DIM>::NP], need, behind, nl = 1, il = 0;
             if constexpr (DIM == 3) {
-                const LineRows3 r = line_rows3(m, t, i, lat_off3(m, t));
+                il = i * RL;
+                nl = min(RL, t + 1 - il);
+                const LineRows3 r = line_rows3(m, t, il, lat_off3(m, t));
                 g.L = r.L; g.k0 = 0; g.k1 = r.L;
-                rc = r.c; need = r.need; behind = r.behind;
+                rc = r.c; behind = r.behind;
+                need = t < m ? r.need + (nl - 1) * (r.L - 1) : min(r.c + nl, plane_off<3>(m, m + 1) - 1);
 #pragma unroll
                 for (int q = 0; q < Sweep<DIM>::NP; ++q) { rm[q] = r.rm[q]; rp[q] = r.rp[q]; }
             } else {
-                const int k0 = i << a.seg_shift;
-                const LineRows2 r = line_rows2(m, t, k0, min(m - t + 1, k0 + (1 << a.seg_shift)));
-                g.L = r.L; g.k0 = k0; g.k1 = min(r.L, k0 + (1 << a.seg_shift));
+                const int k0 = i << SEGS;
+                const LineRows2 r = line_rows2(m, t, k0, min(m - t + 1, k0 + (1 << SEGS)));
+                g.L = r.L; g.k0 = k0; g.k1 = min(r.L, k0 + (1 << SEGS));
                 rc = r.c; need = r.need; behind = r.behind;
                 rm[0] = r.rm[0]; rp[0] = r.rp[0];
             }
-            // observe every chunk up to the one holding the last row this task reads, hand back the chunks
-            // below its window (an arrival on an empty barrier must not overtake the phase of the previous
-            // user of the slot, which is guaranteed once the chunk itself has been seen).
-            // A slot is handed back only after its chunk was seen, and hand-backs are not postponed behind a
-            // wait (the producer may need them to load what this warp waits for).
+            // Observe every chunk up to the one holding the last row this task reads and hand back the chunks
+            // below its window.  A slot is handed back only after its chunk was seen (an arrival on an empty
+            // barrier must not overtake the phase of the previous user of the slot), and hand-backs are not
+            // postponed behind a wait (the producer may need them to load what this warp waits for).
             {
                 const int qn = (su + need) >> CS, qb = (su + behind) >> CS;
-                while (waited <= qn || released < qb) {
-                    if (released < qb && released < waited) {
+                const int r0 = min(qb, waited);
+                if (released < r0) {
+                    __syncwarp();
+                    if (lane == 0)
+                        for (int c = released; c < r0; ++c) mbar_arrive(&empty_bar[c & (APPLY_Q - 1)]);
+                    released = r0;
+                }
+                while (waited <= qn) {
+                    mbar_wait(&full_bar[waited & (APPLY_Q - 1)], (waited >> APPLY_QS) & 1u);
+                    ++waited;
+                    if (released < qb) {
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty_bar[released & (APPLY_Q - 1)]);
                         ++released;
-                    } else {
-                        mbar_wait(&full_bar[waited & (APPLY_Q - 1)], (waited >> APPLY_QS) & 1u);
-                        ++waited;
                     }
                 }
             }
@@ -338,15 +363,35 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
             auto ring = [&](int row) {
                 int p = pb + (row - behind);
                 if (p >= R) p -= R;
-                return p * APPLY_W + lane;
+                return p;
             };
-            g.bc = ring(rc);
+            int qc = ring(rc), qm[Sweep<DIM>::NP], qp[Sweep<DIM>::NP];
 #pragma unroll
-            for (int q = 0; q < Sweep<DIM>::NP; ++q) { g.bm[q] = ring(rm[q]); g.bp[q] = ring(rp[q]); }
+            for (int q = 0; q < Sweep<DIM>::NP; ++q) { qm[q] = ring(rm[q]); qp[q] = ring(rp[q]); }
             out.yl = ybase + (int64_t)rc * APPLY_W;
             out.tl = MODE == APPLY_AX ? nullptr : tbase + (int64_t)rc * APPLY_W;
-            if constexpr (DIM == 3) run_line3(op, a.T, mem, APPLY_W, g, t, i, out);
-            else run_line2(op, a.T, mem, APPLY_W, g, t, out);
+            if constexpr (DIM == 3) {
+                const int L = g.L;
+                for (int li = 0; li < nl; ++li) {
+                    g.bc = qc * APPLY_W + lane;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { g.bm[q] = qm[q] * APPLY_W + lane; g.bp[q] = qp[q] * APPLY_W + lane; }
+                    out.begin(0, L);
+                    run_line3(op, a.T, mem, APPLY_W, g, t, il + li, out);
+                    // the next line of the plane: every base moves by one line of its own plane
+                    auto adv = [&](int& p, int d) { p += d; if (p >= R) p -= R; };
+                    adv(qc, L); adv(qm[0], L - 1); adv(qm[1], L - 1); adv(qm[2], L);
+                    adv(qp[0], L + 1); adv(qp[1], L + 1); adv(qp[2], L);
+                    out.yl += L * APPLY_W;
+                    if (MODE != APPLY_AX) out.tl += L * APPLY_W;
+                }
+            } else {
+                g.bc = qc * APPLY_W + lane;
+                g.bm[0] = qm[0] * APPLY_W + lane;
+                g.bp[0] = qp[0] * APPLY_W + lane;
+                out.begin(g.k0, g.k1);
+                run_line2(op, a.T, mem, APPLY_W, g, t, out);
+            }
         }
         // hand every remaining chunk back (other warps may still need the slots they occupy)
         while (released < nchunks) {
@@ -371,34 +416,51 @@ ApplyConfig make_apply_config(int dim, int m, int nf, int W) {
         return v ? atoi(v) : dflt;
     };
     c.nwarps = std::max(1, std::min(15, envi("HMG_APPLY_WARPS", 15)));
-    c.chunk_shift = std::max(2, std::min(7, envi("HMG_APPLY_CHUNK_SHIFT", 5)));
     c.ctas_per_sm = 1;
-    int seg_shift = std::max(2, std::min(8, envi("HMG_APPLY_SEG_SHIFT", 4)));
-    c.seg = dim == 2 ? seg_shift : 30;
+    c.seg = dim == 2 ? std::max(2, std::min(8, envi("HMG_APPLY_SEG_SHIFT", 5))) : 30;
     c.spill_rows = m + 3;
-    // the largest window of a task: rows from the oldest to the newest row it reads
-    int window = 1;
-    if (dim == 3) {
-        for (int t = 0; t <= m; ++t)
-            for (int i = 0; i <= t; ++i) {
-                const LineRows3 r = line_rows3(m, t, i, lat_off3(m, t));
-                window = std::max(window, r.need - r.behind + 1);
-            }
-    } else {
-        for (int i = 0; i <= m; ++i) {
-            const LineRows2 r = line_rows2(m, i, 0, m - i + 1);
-            window = std::max(window, r.need - r.behind + 1);
-        }
-    }
-    const int CH = 1 << c.chunk_shift;
     const int rowb = W * 8;
-    const int max_rows = (227 * 1024 - 2048) / rowb - c.spill_rows;
-    const int min_rows = window + 2 * CH;
-    int R = envi("HMG_APPLY_RING_ROWS", max_rows);
-    R = std::min(R, std::min(max_rows, (APPLY_Q - 2) * CH));
-    if (R < min_rows) R = min_rows;
-    c.ring_rows = R <= max_rows ? R : -1;        // -1: the level does not fit (refused by the launcher)
-    c.smem_bytes = (size_t)(R + c.spill_rows) * rowb;
+    const int max_rows = std::min((227 * 1024 - 2048) / rowb - c.spill_rows, envi("HMG_APPLY_RING_ROWS", 1 << 20));
+    // the largest row window of a task, for `run` lines per task (3D)
+    auto window = [&](int run) {
+        int w = 1;
+        if (dim == 3) {
+            for (int t = 0; t <= m; ++t)
+                for (int i = 0; i <= t; i += run) {
+                    const LineRows3 r = line_rows3(m, t, i, lat_off3(m, t));
+                    const int nl = std::min(run, t + 1 - i);
+                    const int need = t < m ? r.need + (nl - 1) * (r.L - 1) : r.c + nl;
+                    w = std::max(w, need - r.behind + 1);
+                }
+        } else {
+            for (int i = 0; i <= m; ++i) {
+                const LineRows2 r = line_rows2(m, i, 0, m - i + 1);
+                w = std::max(w, r.need - r.behind + 1);
+            }
+        }
+        return w;
+    };
+    // prefer long runs (per-task overhead) and large chunks (every warp observes every chunk), as long as
+    // the ring keeps `slack` rows of prefetch beyond the window: bytes in flight hide the HBM latency
+    const int slack = 160;
+    const int run_env = envi("HMG_APPLY_RUN", 0), cs_env = envi("HMG_APPLY_CHUNK_SHIFT", 0);
+    c.run = 1; c.chunk_shift = 5;
+    bool found = false;
+    for (int run : {4, 2, 1}) {
+        if (dim == 2 && run != 1) continue;
+        if (run_env && run != run_env) continue;
+        for (int cs : {7, 6, 5}) {
+            if (cs_env && cs != cs_env) continue;
+            if (window(run) + 2 * (1 << cs) + slack <= max_rows) { c.run = run; c.chunk_shift = cs; found = true; break; }
+        }
+        if (found) break;
+    }
+    if (!found) { c.run = run_env ? run_env : 1; c.chunk_shift = cs_env ? cs_env : 5; }
+    const int CH = 1 << c.chunk_shift;
+    const int min_rows = window(c.run) + 2 * CH;
+    int R = std::min(max_rows, (APPLY_Q - 2) * CH);
+    c.ring_rows = R >= min_rows ? R : -1;        // -1: the level does not fit (refused by the launcher)
+    c.smem_bytes = (size_t)(std::max(R, 1) + c.spill_rows) * rowb;
     (void)nf;
     return c;
 }
@@ -428,6 +490,7 @@ static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
     p.m = a.L.m; p.nf = a.L.nf;
     p.nwarps = a.cfg.nwarps; p.R = a.cfg.ring_rows; p.SP = a.cfg.spill_rows; p.cs = a.cfg.chunk_shift;
     p.seg_shift = a.cfg.seg;
+    p.run = a.cfg.run;
     p.dot_post = a.dot_post;
     p.red = a.red;
     const int64_t planes = a.nunits * (a.L.m + 1);

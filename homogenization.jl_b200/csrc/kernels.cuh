@@ -53,7 +53,8 @@ struct ApplyConfig {
     int ring_rows;     // rows (W doubles each) of the shared-memory ring
     int spill_rows;    // rows mirrored behind the ring so that a line never wraps
     int chunk_shift;   // log2(rows per TMA chunk)
-    int seg;           // 2D: nodes per task (a line is split into segments); 3D: unused
+    int seg;           // 2D: log2(nodes per task) (a line is split into segments); 3D: unused
+    int run;           // 3D: consecutive lines of a plane per task
     int ctas_per_sm;
     size_t smem_bytes;
 };

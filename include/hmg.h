@@ -138,7 +138,10 @@ int hmg_next_rhs(hmg_ctx* ctx, int which_b, int which_x);
 int hmg_synchronize(hmg_ctx* ctx);
 /* device time in milliseconds of `reps` repetitions of an operation, measured with CUDA events
  * on the context's stream: op 0 = hmg_apply_global(top, P -> AP), 1 = hmg_vcycle(top, steps),
- * 2 = hmg_mul(top, 1.0, P, AP).  The operation is launched `reps` times back to back. */
+ * 2 = hmg_mul(top, 1.0, P, AP), 3 = local apply AP = constraint(A P), 4 = interface sum of AP,
+ * 5 = local residual, 6 / 7 / 8 = the fused CG vector kernels (x,r update; p update; p = r with
+ * rho), 9 = restriction level -> level-1, 10 = interpolation level-1 -> level, 11 = local apply with
+ * the fused owner-weighted dot.  The operation is launched `reps` times back to back. */
 int hmg_time_op(hmg_ctx* ctx, int op, int level, int steps, int reps, float* ms_out);
 /* number of kernel launches issued on the context's stream since creation */
 int64_t hmg_launch_count(const hmg_ctx* ctx);

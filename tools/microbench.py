@@ -30,11 +30,17 @@ def main():
     x = np.asfortranarray(rng.random((nf, mesh.nelements)))
     st.x.set(x); st.b.set(x); st.p.set(x)
     hmg.broadcast_interfaces(st.p, g, levels)
-    out = {"dim": dim, "c": c, "levels": levels, "dofs": dofs, "regs": os.environ.get("HMG_APPLY_REGS", "64")}
-    for op, name in ((3, "apply"), (4, "interface"), (0, "fused_product"), (2, "mul")):
+    out = {"dim": dim, "c": c, "levels": levels, "dofs": dofs, "env": {k: v for k, v in os.environ.items() if k.startswith("HMG_")}}
+    # (op, name, algorithmic bytes per stored DOF)
+    ops = ((3, "apply", 16), (11, "apply_dot", 16), (4, "interface", 16), (0, "global_product", 16), (5, "residual", 24),
+           (2, "mul", 24), (6, "cg_update", 48), (7, "p_update", 24), (8, "copy_dot", 16), (9, "restrict", 9), (10, "interp", 17))
+    for op, name, bpd in ops:
+        if levels < 2 and op in (9, 10):
+            continue
         g.time_op(op, levels, 0, 3)
         ms = g.time_op(op, levels, 0, reps) / reps
-        out[name] = {"ms": round(ms, 4), "gdofs": round(dofs / ms / 1e6, 2), "hbm16_frac": round(16 * dofs / ms / 1e6 / peak, 3)}
+        out[name] = {"ms": round(ms, 4), "gdofs": round(dofs / ms / 1e6, 2), "bytes_per_dof": bpd,
+                     "hbm_frac": round(bpd * dofs / ms / 1e6 / peak, 3)}
     if len(sys.argv) > 5 and sys.argv[5] == "v":
         bl = hmg.BaseLevel(g)
         g.time_op(1, levels, 3, 2)
