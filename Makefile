@@ -13,7 +13,7 @@ OBJS      := $(patsubst $(CSRC)/%,build/%.o,$(SRCS))
 all: $(LIB) oracle
 
 $(LIB): $(OBJS)
-	$(NVCC) -shared -o $@ $(OBJS) -L$(CUDA_LIB) -lcusolver -lcublas -lnccl \
+	$(NVCC) -shared -o $@ $(OBJS) -L$(CUDA_LIB) -lcusolver -lcublas -ldl \
 	    -Xlinker -rpath=$(CUDA_LIB)
 
 build/%.cu.o: $(CSRC)/%.cu $(HDRS)

@@ -70,6 +70,8 @@ HOST_PROTOTYPES = {
     "hmg_host_topology": (_i32, [_i32, _i64, _i64, _p, _i32, C.POINTER(_i64), C.POINTER(_i64), _p, _p, _p]),
     "hmg_host_boundary": (_i32, [_i32, _i64, _i64, _p, _p, _p]),
     "hmg_host_class_of": (_i32, [_i32, _i32, _i32]),
+    "hmg_host_partition_elements": (_i32, [_i32, _i64, _i64, _p, _p, _i32, _i32, C.POINTER(_i64), _p, _p, _p, _p, _p]),
+    "hmg_host_partition_cells": (_i32, [_i32, _i64, _i64, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "hmg_host_element_coefficients": (_i32, [_i32, _i64, _i64, _p, _p, _p, _p, _i32]),
     "hmg_host_apply_sweep": (_i32, [_i32, _i32, _i32, _i32, _p, _p, _p, _p]),
 }
@@ -81,6 +83,23 @@ class HmgError(RuntimeError):
     pass
 
 
+def _point_at_torch_nccl():
+    """Partitioned contexts bind NCCL at run time; make them pick the copy PyTorch ships (the one a
+    torchrun process has loaded anyway) unless the caller chose another through HMG_NCCL_LIB."""
+    if os.environ.get("HMG_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["HMG_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
 def load():
     """Load libhmg_b200.so and declare every prototype.  Raises if the library is not built."""
     global _lib
@@ -90,6 +109,7 @@ def load():
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()). "
             "homogenization.jl_b200 has no CPU fallback.")
+    _point_at_torch_nccl()
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     for name, (res, args) in list(PROTOTYPES.items()) + list(HOST_PROTOTYPES.items()):
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported

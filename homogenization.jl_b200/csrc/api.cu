@@ -9,6 +9,8 @@
 
 #include <cuda_runtime.h>
 #include <cusolverDn.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include "../../include/hmg.h"
 #include "hmg_host.hpp"
@@ -26,12 +28,55 @@ thread_local std::string g_err;
         if (e_ != cudaSuccess)                                                               \
             throw Error(std::string("hmg: CUDA error: ") + cudaGetErrorString(e_) + " in " #call); \
     } while (0)
+#define NCCL_OK(call)                                                                        \
+    do {                                                                                     \
+        ncclResult_t r_ = (call);                                                            \
+        if (r_ != ncclSuccess)                                                               \
+            throw Error(std::string("hmg: NCCL error: ") + nccl().GetErrorString(r_) + " in " #call); \
+    } while (0)
 #define CUSOLVER_OK(call)                                                                    \
     do {                                                                                     \
         cusolverStatus_t s_ = (call);                                                        \
         if (s_ != CUSOLVER_STATUS_SUCCESS)                                                   \
             throw Error(std::string("hmg: cuSOLVER error ") + std::to_string((int)s_) + " in " #call); \
     } while (0)
+
+// NCCL is bound at run time (dlopen), never at link time: the process usually holds PyTorch's bundled
+// libnccl already, and two NCCL builds in one process do not mix.  Order: the copy already loaded,
+// $HMG_NCCL_LIB (the Python binding points it at PyTorch's copy), the system library.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+const NcclApi& nccl() {
+    static NcclApi api;
+    static bool loaded = false;
+    if (loaded) return api;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h)
+        if (const char* path = getenv("HMG_NCCL_LIB")) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) throw Error("hmg: cannot load libnccl.so.2 (set HMG_NCCL_LIB): partitioned contexts need NCCL");
+    auto sym = [&](const char* name) {
+        void* f = dlsym(h, name);
+        if (!f) throw Error(std::string("hmg: NCCL symbol missing: ") + name);
+        return f;
+    };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.Reduce = reinterpret_cast<decltype(api.Reduce)>(sym("ncclReduce"));
+    api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    loaded = true;
+    return api;
+}
 
 struct LevelDev {
     LevelView view{};
@@ -52,14 +97,24 @@ struct hmg_ctx {
     double lambda = 1.0;
     cudaStream_t stream = nullptr;
     RefElement ref;
-    Topology topo;
-    std::vector<int64_t> elems;          // local elements, 0-based, (dim+1) x ne
+    Topology topo;                       // of the WHOLE base mesh
+    Partition part;                      // this rank's share (the whole mesh on one GPU)
+    std::vector<int64_t> elems;          // local elements, 0-based global node ids, (dim+1) x ne
+    std::vector<int64_t> elems_global;   // all elements (coarse operator on rank 0)
+    std::vector<double> sigma_global;    // dim x ne_global
     std::vector<double> nodes;           // dim x nn
     std::vector<int64_t> local_to_global;
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    CutView cutv[3] = {};
+    int64_t cut_nglobal[3] = {0, 0, 0};
+    std::vector<double*> cut_send;       // per level: packed partial sums, slots of foreign cells stay zero
+    double* cut_recv = nullptr;
+    uint8_t* node_contrib = nullptr;
     std::vector<LevelDev> lv;
     TopoView tview{};
     double* elem_coef = nullptr;         // [nunits][CS][W]
-    std::vector<double> elem_coef_host;  // [ne][CS]
+    std::vector<double> elem_coef_host;  // [ne][CS] (local elements)
     uint16_t* cmask = nullptr;           // [nunits * W]
     uint8_t* mult = nullptr;             // [nunits][16][W] owners of the cell of every node class
     int32_t* belems = nullptr;           // elements touching the domain boundary
@@ -109,6 +164,13 @@ struct hmg_ctx {
     }
     // stored entries of a level vector including the zero columns that pad the last unit
     int64_t nstored(int l) { return (int64_t)level(l).view.nf * W * nunits; }
+    // packed cut buffer of a level: [cut faces x npf][cut edges x npe][cut vertices]
+    int64_t cut_base(int l, int kind) {
+        const LevelView& V = level(l).view;
+        const int64_t f = cut_nglobal[0] * V.npf, e = cut_nglobal[1] * V.npe;
+        return kind == 0 ? 0 : (kind == 1 ? f : f + e);
+    }
+    int64_t cut_slots(int l) { return cut_base(l, 2) + cut_nglobal[2]; }
 };
 
 namespace {
@@ -118,9 +180,13 @@ void check_launch(hmg_ctx* c, int n) {
     CUDA_OK(cudaGetLastError());
 }
 
-void upload_operator(hmg_ctx* c, const double* sigma) {
-    const int cs = c->dim == 3 ? 8 : 4;
-    element_coefficients(c->dim, c->ne, c->nodes.data(), c->elems.data(), sigma, c->elem_coef_host, cs);
+void upload_operator(hmg_ctx* c, const double* sigma /* dim x ne_global */) {
+    const int cs = c->dim == 3 ? 8 : 4, dim = c->dim;
+    c->sigma_global.assign(sigma, sigma + (size_t)c->ne_global * dim);
+    std::vector<double> sl((size_t)c->ne * dim);
+    for (int64_t e = 0; e < c->ne; ++e)
+        for (int d = 0; d < dim; ++d) sl[(size_t)e * dim + d] = sigma[(size_t)c->local_to_global[e] * dim + d];
+    element_coefficients(c->dim, c->ne, c->nodes.data(), c->elems.data(), sl.data(), c->elem_coef_host, cs);
     const int W = c->W;
     std::vector<double> inter((size_t)c->nunits * cs * W, 0.0);     // [unit][component][lane]
     for (int64_t e = 0; e < c->ne; ++e)
@@ -130,10 +196,13 @@ void upload_operator(hmg_ctx* c, const double* sigma) {
     CUDA_OK(cudaStreamSynchronize(c->stream));
 }
 
-hmg_ctx* create_impl(int dim, int nlevels, int64_t ne, int64_t nn, const double* base_nodes,
-                     const int64_t* base_elems, const double* sigma, double lambda, int device) {
+hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const double* base_nodes,
+                     const int64_t* base_elems, const double* sigma, double lambda, int device, int rank, int nranks,
+                     const int32_t* owner_rank, const void* nccl_id) {
     HMG_CHECK(base_nodes && base_elems && sigma, "null input array");
-    HMG_CHECK(ne > 0 && nn > 0, "empty base mesh");
+    HMG_CHECK(ne_global > 0 && nn > 0, "empty base mesh");
+    HMG_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank");
+    HMG_CHECK(nranks == 1 || (owner_rank && nccl_id), "a partitioned context needs owner_rank and the NCCL id");
     int ndev = 0;
     cudaError_t de = cudaGetDeviceCount(&ndev);
     if (de != cudaSuccess || ndev == 0)
@@ -144,7 +213,9 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne, int64_t nn, const double*
     c->dim = dim;
     c->nlevels = nlevels;
     c->device = device;
-    c->ne = c->ne_global = ne;
+    c->rank = rank;
+    c->nranks = nranks;
+    c->ne_global = ne_global;
     c->nn = nn;
     c->lambda = lambda;
     CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -152,14 +223,27 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne, int64_t nn, const double*
     CUDA_OK(cudaEventCreate(&c->ev1));
 
     const int nv = dim + 1;
-    c->elems.resize((size_t)ne * nv);
-    for (size_t q = 0; q < c->elems.size(); ++q) c->elems[q] = base_elems[q] - 1;   // Julia is 1-based
+    c->elems_global.resize((size_t)ne_global * nv);
+    for (size_t q = 0; q < c->elems_global.size(); ++q) c->elems_global[q] = base_elems[q] - 1;   // Julia is 1-based
     c->nodes.assign(base_nodes, base_nodes + (size_t)nn * dim);
-    c->local_to_global.resize(ne);
-    for (int64_t e = 0; e < ne; ++e) c->local_to_global[e] = e;
 
     c->ref = build_reference(dim, nlevels);
-    c->topo = build_topology(dim, ne, nn, c->elems.data());
+    c->topo = build_topology(dim, ne_global, nn, c->elems_global.data());
+    c->part = build_partition(c->topo, nranks > 1 ? owner_rank : nullptr, rank, nranks);
+    const Partition& P = c->part;
+    c->local_to_global = P.local_to_global;
+    const int64_t ne = (int64_t)P.local_to_global.size();
+    HMG_CHECK(ne > 0, "this rank owns no coarse element");
+    c->ne = ne;
+    c->elems.resize((size_t)ne * nv);
+    for (int64_t e = 0; e < ne; ++e)
+        for (int a = 0; a < nv; ++a) c->elems[(size_t)e * nv + a] = c->elems_global[(size_t)P.local_to_global[e] * nv + a];
+    if (nranks > 1) {
+        ncclUniqueId id;
+        static_assert(sizeof(ncclUniqueId) == 128, "NCCL unique id size");
+        std::memcpy(&id, nccl_id, sizeof(id));
+        NCCL_OK(nccl().CommInitRank(&c->comm, nranks, id, rank));
+    }
     // interleave width: one warp lane per element of a unit
     c->W = 32;
     c->wshift = 5;
@@ -191,10 +275,9 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne, int64_t nn, const double*
         L.tab.insert(L.tab.end(), R.ge.begin(), R.ge.end());
         for (int w = 0; w <= HMG_AP; ++w) L.vec[w] = c->dalloc<double>((size_t)V.nf * c->W * c->nunits);
     }
-    // topology
-    const Topology& T = c->topo;
+    // topology of the cells whose owners are all local
     {
-        const CellMap& pairs = dim == 3 ? T.faces : T.edges;     // codimension-1 cells: exactly two owners
+        const CellMap& pairs = dim == 3 ? P.faces : P.edges;     // codimension-1 cells: exactly two owners
         std::vector<int32_t> partner((size_t)ne * 4, -1);
         for (int64_t q = 0; q < pairs.ncells(); ++q) {
             HMG_CHECK(pairs.offset[q + 1] - pairs.offset[q] == 2, "a face of the base mesh is shared by more than two elements");
@@ -206,42 +289,52 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne, int64_t nn, const double*
         c->tview.partner = c->dupload(partner);
         static const std::vector<int64_t> empty_off(1, 0);
         static const std::vector<int32_t> empty_own;
-        c->tview.nedges = dim == 3 ? T.edges.ncells() : 0;
-        c->tview.edge_off = c->dupload(dim == 3 ? T.edges.offset : empty_off);
-        c->tview.edge_own = c->dupload(dim == 3 ? T.edges.owner : empty_own);
-        c->tview.nverts = T.verts.ncells();
-        c->tview.vert_off = c->dupload(T.verts.offset);
-        c->tview.vert_own = c->dupload(T.verts.owner);
+        c->tview.nedges = dim == 3 ? P.edges.ncells() : 0;
+        c->tview.edge_off = c->dupload(dim == 3 ? P.edges.offset : empty_off);
+        c->tview.edge_own = c->dupload(dim == 3 ? P.edges.owner : empty_own);
+        c->tview.nverts = P.verts.ncells();
+        c->tview.vert_off = c->dupload(P.verts.offset);
+        c->tview.vert_own = c->dupload(P.verts.owner);
+    }
+    // cut cells (owners on several ranks): packed exchange buffers, one layout per level
+    if (nranks > 1) {
+        int64_t max_slots = 1;
+        c->cut_send.assign(nlevels, nullptr);
+        for (int kind = 0; kind < 3; ++kind) {
+            const CutCells& C = P.cut[kind];
+            c->cut_nglobal[kind] = C.nglobal;
+            c->cutv[kind].ncells = C.ncells();
+            c->cutv[kind].slot = c->dupload(C.slot);
+            c->cutv[kind].off = c->dupload(C.offset);
+            c->cutv[kind].own = c->dupload(C.owner);
+            c->cutv[kind].first_local = c->dupload(C.first_local);
+        }
+        for (int l = 1; l <= nlevels; ++l) {
+            const int64_t slots = c->cut_slots(l);
+            max_slots = std::max(max_slots, slots);
+            c->cut_send[l - 1] = c->dalloc<double>((size_t)std::max<int64_t>(slots, 1));
+        }
+        c->cut_recv = c->dalloc<double>((size_t)max_slots);
+        c->node_contrib = c->dupload(P.node_contrib);
     }
     {
         std::vector<uint16_t> cm((size_t)c->nunits * c->W, 0);
         std::vector<int32_t> be;
         for (int64_t e = 0; e < ne; ++e) {
-            cm[e] = T.cmask[e];
-            if (T.cmask[e]) be.push_back((int32_t)e);
+            cm[e] = P.cmask[e];
+            if (P.cmask[e]) be.push_back((int32_t)e);
         }
         c->cmask = c->dupload(cm);
         c->nbelems = (int64_t)be.size();
         c->belems = c->dupload(be);
-        // owners of the base-mesh cell behind every node class (weights of the fused dot products)
+        // owners (on all ranks) of the base-mesh cell behind every node class: weights of the fused dot products
         std::vector<uint8_t> mult((size_t)c->nunits * 16 * c->W, 1);
-        auto owners = [&](int64_t e, int slot) -> int {
-            const int32_t id = T.elem_cells[(size_t)e * 16 + slot];
-            if (id < 0) return 1;
-            const int64_t n = T.cell_off[id + 1] - T.cell_off[id];
-            HMG_CHECK(n <= 255, "a base-mesh cell has more than 255 owners");
-            return (int)n;
-        };
-        const int nfl = dim == 3 ? 4 : 0, nel = dim == 3 ? 6 : 3;
-        for (int64_t e = 0; e < ne; ++e) {
-            uint8_t* dst = &mult[(size_t)(e / c->W) * 16 * c->W + e % c->W];
-            for (int q = 0; q < nfl; ++q) dst[(size_t)class_of_face(q) * c->W] = (uint8_t)owners(e, q);
-            for (int q = 0; q < nel; ++q) dst[(size_t)class_of_edge(dim, q) * c->W] = (uint8_t)owners(e, nfl + q);
-            for (int q = 0; q < nv; ++q) dst[(size_t)class_of_vertex(dim, q) * c->W] = (uint8_t)owners(e, nfl + nel + q);
-        }
+        for (int64_t e = 0; e < ne; ++e)
+            for (int q = 0; q < 16; ++q)
+                mult[((size_t)(e / c->W) * 16 + q) * c->W + e % c->W] = P.mult[(size_t)e * 16 + q];
         c->mult = c->dupload(mult);
     }
-    c->node_first = c->dupload(T.node_first);
+    c->node_first = c->dupload(P.node_first);
     std::vector<int32_t> e32(c->elems.begin(), c->elems.end());
     c->elems32 = c->dupload(e32);
     upload_operator(c.get(), sigma);
@@ -275,8 +368,37 @@ void do_apply(hmg_ctx* c, int l, int mode, double alpha, const double* x, double
     HMG_CHECK(n >= 0, "apply kernel refused the launch configuration");
     check_launch(c, n);
 }
+// cut cells: pack the partial sums of the local owners, all-reduce the packed buffer over the ranks
+// (only interface partial sums move, NCCL over NVLink), write the totals back
+void do_cut_exchange(hmg_ctx* c, int l, double* x) {
+    const int64_t slots = c->cut_slots(l);
+    if (c->nranks == 1 || slots == 0) return;
+    const LevelView& V = c->level(l).view;
+    double* send = c->cut_send[l - 1];
+    for (int kind = 0; kind < 3; ++kind)
+        check_launch(c, launch_cut(c->dim, CUT_PACK, kind, V, c->cutv[kind], c->cut_base(l, kind), x, send, c->stream));
+    NCCL_OK(nccl().AllReduce(send, c->cut_recv, (size_t)slots, ncclDouble, ncclSum, c->comm, c->stream));
+    for (int kind = 0; kind < 3; ++kind)
+        check_launch(c, launch_cut(c->dim, CUT_UNPACK, kind, V, c->cutv[kind], c->cut_base(l, kind), x, c->cut_recv, c->stream));
+}
 void do_broadcast(hmg_ctx* c, int l, double* x) {
     check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->stream));
+    do_cut_exchange(c, l, x);
+}
+void do_zero_all_but_one(hmg_ctx* c, int l, double* x) {
+    check_launch(c, launch_zero_all_but_one(c->dim, c->level(l).view, c->tview, x, c->stream));
+    if (c->nranks > 1)
+        for (int kind = 0; kind < 3; ++kind)
+            check_launch(c, launch_cut(c->dim, CUT_ZERO_BUT_FIRST, kind, c->level(l).view, c->cutv[kind], 0, x, nullptr, c->stream));
+}
+// post-op of a reduction kernel: on one GPU the kernel's last block derives the CG scalars itself; with
+// several ranks the kernel stores the local sum in S_TMP, the sums are all-reduced and a one-thread
+// kernel derives the scalars
+int kernel_post(hmg_ctx* c, int post) { return c->nranks > 1 ? (int)POST_STORE : post; }
+void finish_reduction(hmg_ctx* c, int post, int slot) {
+    if (c->nranks == 1) return;
+    NCCL_OK(nccl().AllReduce(c->red.scalars + S_TMP, c->red.scalars + S_TMP, 1, ncclDouble, ncclSum, c->comm, c->stream));
+    check_launch(c, launch_scalar_post(c->red, post, slot, c->stream));
 }
 void do_local_residual(hmg_ctx* c, int l) {
     do_apply(c, l, APPLY_RESIDUAL, 1.0, c->vecp(l, HMG_X), c->vecp(l, HMG_R), c->vecp(l, HMG_B));
@@ -284,7 +406,8 @@ void do_local_residual(hmg_ctx* c, int l) {
 // y = broadcast(constraint(A x)); with dot_post >= 0 the apply kernel also reduces
 // sum_entries owners(entry) * x * y_local = dot(x, y) over all stored entries (x consistent across owners)
 void do_global_product(hmg_ctx* c, int l, const double* x, double* y, int dot_post = -1) {
-    do_apply(c, l, APPLY_AX, 1.0, x, y, nullptr, dot_post);      // y = constraint(A x), column-local
+    do_apply(c, l, APPLY_AX, 1.0, x, y, nullptr, dot_post >= 0 ? kernel_post(c, dot_post) : -1);   // y = constraint(A x), column-local
+    if (dot_post >= 0) finish_reduction(c, dot_post, S_TMP);
     do_broadcast(c, l, y);                                       // interface sums
 }
 void do_smoothing(hmg_ctx* c, int l, int steps) {
@@ -293,24 +416,36 @@ void do_smoothing(hmg_ctx* c, int l, int steps) {
     // r = broadcast(constraint(b - A x)); p = r and rho = r.r in one pass
     do_apply(c, l, APPLY_RESIDUAL, 1.0, x, r, c->vecp(l, HMG_B));
     do_broadcast(c, l, r);
-    check_launch(c, launch_copy_dot(c->red, r, p, n, c->stream));
+    check_launch(c, launch_copy_dot(c->red, r, p, n, kernel_post(c, POST_RHO), c->stream));
+    finish_reduction(c, POST_RHO, S_TMP);
     for (int i = 0; i < steps; ++i) {
         do_global_product(c, l, p, Ap, POST_PAP);                     // Ap = broadcast(constraint(A p)), alpha = rho / p.Ap
-        check_launch(c, launch_cg_update(c->red, x, p, r, Ap, n, c->stream));
+        check_launch(c, launch_cg_update(c->red, x, p, r, Ap, n, kernel_post(c, POST_RSQR), c->stream));
+        finish_reduction(c, POST_RSQR, S_TMP);
         // the reference also updates p after the last step, but that value is never used
         // (src/multigrid.jl:68; the next smoothing call starts from a fresh residual)
         if (i + 1 < steps) check_launch(c, launch_p_update(c->red, p, r, n, c->stream));
     }
 }
 void do_coarse_solve(hmg_ctx* c) {
-    HMG_CHECK(c->Ainv != nullptr, "coarse matrix not set: call hmg_set_coarse_matrix or hmg_assemble_coarse first");
+    HMG_CHECK(c->n_interior > 0, "coarse matrix not set: call hmg_set_coarse_matrix or hmg_assemble_coarse first");
     LevelDev& L1 = c->level(1);
     do_broadcast(c, 1, c->vecp(1, HMG_B));
-    check_launch(c, launch_copy_to_base(L1.view, c->nn, c->node_first, c->vecp(1, HMG_B), c->ubase, c->stream));
-    check_launch(c, launch_gather(c->interior_idx, c->n_interior, c->ubase, c->bint, c->stream));
-    check_launch(c, launch_symv_full(c->Ainv, c->n_interior, c->bint, c->xint, c->stream));
-    check_launch(c, launch_fill(c->ubase, 0.0, c->nn, c->stream));
-    check_launch(c, launch_scatter(c->interior_idx, c->n_interior, c->xint, c->ubase, c->stream));
+    if (c->nranks == 1) {
+        check_launch(c, launch_copy_to_base(L1.view, c->nn, c->node_first, c->vecp(1, HMG_B), c->ubase, c->stream));
+    } else {
+        // every base node is reported by one rank; the sum over ranks lands on rank 0, which solves
+        check_launch(c, launch_masked_copy_to_base(L1.view, c->nn, c->node_first, c->node_contrib, c->vecp(1, HMG_B), c->ubase,
+                                                   c->stream));
+        NCCL_OK(nccl().Reduce(c->ubase, c->ubase, (size_t)c->nn, ncclDouble, ncclSum, 0, c->comm, c->stream));
+    }
+    if (c->rank == 0) {
+        check_launch(c, launch_gather(c->interior_idx, c->n_interior, c->ubase, c->bint, c->stream));
+        check_launch(c, launch_symv_full(c->Ainv, c->n_interior, c->bint, c->xint, c->stream));
+        check_launch(c, launch_fill(c->ubase, 0.0, c->nn, c->stream));
+        check_launch(c, launch_scatter(c->interior_idx, c->n_interior, c->xint, c->ubase, c->stream));
+    }
+    if (c->nranks > 1) NCCL_OK(nccl().Broadcast(c->ubase, c->ubase, (size_t)c->nn, ncclDouble, 0, c->comm, c->stream));
     check_launch(c, launch_distribute(c->dim, L1.view, c->ne, c->elems32, c->ubase, c->vecp(1, HMG_X), c->stream));
 }
 void do_vcycle(hmg_ctx* c, int k, int steps) {
@@ -347,6 +482,7 @@ void set_coarse_dense(hmg_ctx* c, int64_t n, const std::vector<int64_t>& colptr,
     if (c->bint) { c->dfree(c->bint); c->bint = nullptr; }
     if (c->xint) { c->dfree(c->xint); c->xint = nullptr; }
     c->n_interior = n;
+    if (c->rank != 0) return;            // the coarsest-grid solve stays on rank 0
     c->interior_idx = c->dupload(interior0);
     c->bint = c->dalloc<double>(n);
     c->xint = c->dalloc<double>(n);
@@ -415,20 +551,25 @@ int hmg_create(int dim, int nlevels, int64_t ne, int64_t nn, const double* base_
     HMG_API_BEGIN
     HMG_CHECK(out != nullptr, "null output pointer");
     *out = nullptr;
-    *out = create_impl(dim, nlevels, ne, nn, base_nodes, base_elems, sigma, lambda, device);
+    *out = create_impl(dim, nlevels, ne, nn, base_nodes, base_elems, sigma, lambda, device, 0, 1, nullptr, nullptr);
     HMG_API_END
 }
 
-int hmg_create_partitioned(int, int, int64_t, int64_t, const double*, const int64_t*, const double*, double, int, int,
-                           int, const int32_t*, const void*, hmg_ctx** out) {
+int hmg_create_partitioned(int dim, int nlevels, int64_t ne, int64_t nn, const double* base_nodes, const int64_t* base_elems,
+                           const double* sigma, double lambda, int device, int rank, int nranks, const int32_t* owner_rank,
+                           const void* nccl_id, hmg_ctx** out) {
     HMG_API_BEGIN
-    if (out) *out = nullptr;
-    throw Error("hmg: partitioned contexts are not available in this build");
+    HMG_CHECK(out != nullptr, "null output pointer");
+    *out = nullptr;
+    *out = create_impl(dim, nlevels, ne, nn, base_nodes, base_elems, sigma, lambda, device, rank, nranks, owner_rank, nccl_id);
     HMG_API_END
 }
-int hmg_nccl_unique_id(void*) {
+int hmg_nccl_unique_id(void* out128) {
     HMG_API_BEGIN
-    throw Error("hmg: partitioned contexts are not available in this build");
+    HMG_CHECK(out128 != nullptr, "null output pointer");
+    ncclUniqueId id;
+    NCCL_OK(nccl().GetUniqueId(&id));
+    std::memcpy(out128, &id, sizeof(id));
     HMG_API_END
 }
 
@@ -437,6 +578,7 @@ int hmg_destroy(hmg_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->comm) nccl().CommDestroy(c->comm);
     for (void* p : c->allocs) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -549,6 +691,7 @@ int hmg_dot(hmg_ctx* c, int level, int a, int b, double* out) {
     NEED_CTX(c);
     CUDA_OK(cudaSetDevice(c->device));
     check_launch(c, launch_dot(c->red, c->vecp(level, a), c->vecp(level, b), c->nstored(level), POST_STORE, S_TMP, c->stream));
+    finish_reduction(c, POST_STORE, S_TMP);
     *out = read_scalar(c, S_TMP);
     HMG_API_END
 }
@@ -588,7 +731,7 @@ int hmg_zero_out_all_but_one(hmg_ctx* c, int level, int which) {
     HMG_API_BEGIN
     NEED_CTX(c);
     CUDA_OK(cudaSetDevice(c->device));
-    check_launch(c, launch_zero_all_but_one(c->dim, c->level(level).view, c->tview, c->vecp(level, which), c->stream));
+    do_zero_all_but_one(c, level, c->vecp(level, which));
     HMG_API_END
 }
 int hmg_local_residual(hmg_ctx* c, int level) {
@@ -648,8 +791,8 @@ int hmg_assemble_coarse(hmg_ctx* c) {
     CUDA_OK(cudaSetDevice(c->device));
     // P1 assembly of lambda*M + K(sigma) on the base mesh, restricted to the interior nodes
     const int dim = c->dim, nv = dim + 1, cs = dim == 3 ? 8 : 4, nc = dim == 3 ? 7 : 4;
-    const std::vector<double>& coef = c->elem_coef_host;
-    HMG_CHECK(coef.size() == (size_t)c->ne * cs, "element coefficients missing");
+    std::vector<double> coef;            // of ALL elements: the coarse operator couples the whole base mesh
+    element_coefficients(dim, c->ne_global, c->nodes.data(), c->elems_global.data(), c->sigma_global.data(), coef, cs);
     const std::vector<int64_t>& interior = c->topo.interior_nodes;
     const int64_t n = (int64_t)interior.size();
     HMG_CHECK(n > 0, "base mesh has no interior nodes");
@@ -659,7 +802,8 @@ int hmg_assemble_coarse(hmg_ctx* c) {
     const double fact = dim == 3 ? 6.0 : 2.0;
     const double gref[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
     std::vector<std::map<int64_t, double>> cols(n);
-    for (int64_t e = 0; e < c->ne; ++e) {
+    if (c->rank != 0) { c->n_interior = n; return 0; }
+    for (int64_t e = 0; e < c->ne_global; ++e) {
         const double* ec = &coef[(size_t)e * cs];
         double P[3][3];
         int q = 0;
@@ -667,10 +811,10 @@ int hmg_assemble_coarse(hmg_ctx* c) {
             for (int l = k; l < dim; ++l, ++q) P[k][l] = P[l][k] = ec[q];
         const double detJ = ec[nc - 1];
         for (int a = 0; a < nv; ++a) {
-            const int64_t ra = pos[c->elems[e * nv + a]];
+            const int64_t ra = pos[c->elems_global[e * nv + a]];
             if (ra < 0) continue;
             for (int b = 0; b < nv; ++b) {
-                const int64_t rb = pos[c->elems[e * nv + b]];
+                const int64_t rb = pos[c->elems_global[e * nv + b]];
                 if (rb < 0) continue;
                 double s = 0.0;
                 for (int k = 0; k < dim; ++k)
@@ -694,7 +838,13 @@ int hmg_copy_to_base(hmg_ctx* c, int which, double* u_host) {
     HMG_API_BEGIN
     NEED_CTX(c);
     CUDA_OK(cudaSetDevice(c->device));
-    check_launch(c, launch_copy_to_base(c->level(1).view, c->nn, c->node_first, c->vecp(1, which), c->ubase, c->stream));
+    if (c->nranks == 1) {
+        check_launch(c, launch_copy_to_base(c->level(1).view, c->nn, c->node_first, c->vecp(1, which), c->ubase, c->stream));
+    } else {      // every rank receives the whole base vector
+        check_launch(c, launch_masked_copy_to_base(c->level(1).view, c->nn, c->node_first, c->node_contrib, c->vecp(1, which),
+                                                   c->ubase, c->stream));
+        NCCL_OK(nccl().AllReduce(c->ubase, c->ubase, (size_t)c->nn, ncclDouble, ncclSum, c->comm, c->stream));
+    }
     CUDA_OK(cudaMemcpyAsync(u_host, c->ubase, c->nn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     HMG_API_END
@@ -713,8 +863,10 @@ static void vcycle_with_norm(hmg_ctx* c, int top, int steps, bool want_norm, int
     do_vcycle(c, top, steps);
     if (want_norm) {
         double* r = c->vecp(top, HMG_R);
-        check_launch(c, launch_zero_all_but_one(c->dim, c->level(top).view, c->tview, r, c->stream));
-        check_launch(c, launch_dot(c->red, r, r, c->nstored(top), POST_STORE, slot, c->stream));
+        do_zero_all_but_one(c, top, r);
+        check_launch(c, launch_dot(c->red, r, r, c->nstored(top), POST_STORE, S_TMP, c->stream));
+        finish_reduction(c, POST_STORE, S_TMP);
+        CUDA_OK(cudaMemcpyAsync(c->red.scalars + slot, c->red.scalars + S_TMP, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     }
 }
 
@@ -805,11 +957,11 @@ int hmg_time_op(hmg_ctx* c, int op, int level, int steps, int reps, float* ms_ou
             do_apply(c, level, APPLY_RESIDUAL, 1.0, c->vecp(level, HMG_X), c->vecp(level, HMG_R), c->vecp(level, HMG_B));
         } else if (op == 6) {
             check_launch(c, launch_cg_update(c->red, c->vecp(level, HMG_X), c->vecp(level, HMG_P), c->vecp(level, HMG_R),
-                                             c->vecp(level, HMG_AP), c->nstored(level), c->stream));
+                                             c->vecp(level, HMG_AP), c->nstored(level), POST_RSQR, c->stream));
         } else if (op == 7) {
             check_launch(c, launch_p_update(c->red, c->vecp(level, HMG_P), c->vecp(level, HMG_R), c->nstored(level), c->stream));
         } else if (op == 8) {
-            check_launch(c, launch_copy_dot(c->red, c->vecp(level, HMG_R), c->vecp(level, HMG_P), c->nstored(level), c->stream));
+            check_launch(c, launch_copy_dot(c->red, c->vecp(level, HMG_R), c->vecp(level, HMG_P), c->nstored(level), POST_RHO, c->stream));
         } else if (op == 9) {
             check_launch(c, launch_restrict(c->dim, c->level(level).view, c->level(level - 1).view, c->nunits,
                                             c->vecp(level, HMG_R), c->vecp(level - 1, HMG_B), c->stream));

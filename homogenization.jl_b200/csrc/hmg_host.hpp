@@ -103,6 +103,33 @@ struct Topology {
 // elems: (dim+1) x ne, 0-based, sorted per element
 Topology build_topology(int dim, int64_t ne, int64_t nn, const int64_t* elems);
 
+// ---- partition of the coarse elements over ranks (one process per GPU) ---------------------
+// A rank keeps the columns of its own elements (global order preserved).  Interface cells whose owners
+// all live on one rank are summed locally; CUT cells (owners on >= 2 ranks) are summed through a packed
+// buffer that every rank fills with the partial sum over ITS owners and that is all-reduced: slot
+// layout per level = [cut faces x npf][cut edges x npe][cut vertices], cells in global cell order, so
+// every rank derives the same layout from the global topology without communication.
+struct CutCells {                      // the cut cells of one kind this rank takes part in
+    int64_t nglobal = 0;               // cut cells of this kind on all ranks (slot space)
+    std::vector<int64_t> slot;         // per participating cell: ordinal among the global cut cells of the kind
+    std::vector<int64_t> offset;       // CSR over the LOCAL owners of the cell
+    std::vector<int32_t> owner;        // local element * 8 + local id, ascending global element
+    std::vector<uint8_t> first_local;  // 1 if the globally first owner of the cell is owner[offset[c]]
+    int64_t ncells() const { return (int64_t)slot.size(); }
+};
+struct Partition {
+    int rank = 0, nranks = 1;
+    std::vector<int64_t> local_to_global;   // local element -> global element
+    std::vector<int32_t> global_to_local;   // global element -> local element, -1 if remote
+    CellMap faces, edges, verts;            // interface cells with all owners on this rank (local ids)
+    CutCells cut[3];                        // 0 faces (3D), 1 edges, 2 vertices
+    std::vector<uint16_t> cmask;            // per local element
+    std::vector<uint8_t> mult;              // [ne_local][16] owners (on all ranks) of the cell behind every node class
+    std::vector<int32_t> node_first;        // per base node: first LOCAL owner (local element*8+local id), -1 if none
+    std::vector<uint8_t> node_contrib;      // per base node: 1 if this rank reports the node to the coarse solve
+};
+Partition build_partition(const Topology& T, const int32_t* owner_rank, int rank, int nranks);
+
 // class bitmask of the reference-face set containing a local cell
 int class_of_face(int lf);              // 3D face 0..3
 int class_of_edge(int dim, int le);     // edge local id

@@ -246,6 +246,61 @@ int hmg_host_boundary(int dim, int64_t ne, int64_t nn, const int64_t* elems1, ui
     HOST_END
 }
 
+// ---- partition of the coarse elements over ranks (multi-GPU host logic, no GPU needed) ----
+namespace {
+Partition host_partition(int dim, int64_t ne, int64_t nn, const int64_t* elems1, const int32_t* owner_rank, int rank, int nranks) {
+    std::vector<int64_t> el((size_t)ne * (dim + 1));
+    for (size_t q = 0; q < el.size(); ++q) el[q] = elems1[q] - 1;
+    Topology T = build_topology(dim, ne, nn, el.data());
+    return build_partition(T, owner_rank, rank, nranks);
+}
+}  // namespace
+
+// local elements of `rank`: local_to_global[ne_local] (0-based), per local element the Dirichlet class mask and
+// the owner counts mult[ne_local][16], per base node the first local owner (element*8+local id, -1 none) and
+// whether this rank reports the node to the coarse solve.  Arrays may be NULL.
+int hmg_host_partition_elements(int dim, int64_t ne, int64_t nn, const int64_t* elems1, const int32_t* owner_rank, int rank,
+                                int nranks, int64_t* ne_local, int64_t* local_to_global, uint16_t* cmask, uint8_t* mult,
+                                int32_t* node_first, uint8_t* node_contrib) {
+    HOST_BEGIN
+    const Partition P = host_partition(dim, ne, nn, elems1, owner_rank, rank, nranks);
+    if (ne_local) *ne_local = (int64_t)P.local_to_global.size();
+    if (local_to_global) std::copy(P.local_to_global.begin(), P.local_to_global.end(), local_to_global);
+    if (cmask) std::copy(P.cmask.begin(), P.cmask.end(), cmask);
+    if (mult) std::copy(P.mult.begin(), P.mult.end(), mult);
+    if (node_first) std::copy(P.node_first.begin(), P.node_first.end(), node_first);
+    if (node_contrib) std::copy(P.node_contrib.begin(), P.node_contrib.end(), node_contrib);
+    HOST_END
+}
+// interface cells of one kind (0 faces, 1 edges, 2 vertices) as seen by `rank`.
+//   cut == 0: cells whose owners are all local: sizes[2] = cells, entries; CSR offset / element (LOCAL index) / local_id
+//   cut == 1: cut cells this rank takes part in: sizes[3] = cells, entries, cut cells of the kind on ALL ranks;
+//             slot[cells] = ordinal in the global cut enumeration, first_local[cells]
+int hmg_host_partition_cells(int dim, int64_t ne, int64_t nn, const int64_t* elems1, const int32_t* owner_rank, int rank,
+                             int nranks, int kind, int cut, int64_t* sizes, int64_t* offset, int64_t* element, int64_t* local_id,
+                             int64_t* slot, uint8_t* first_local) {
+    HOST_BEGIN
+    HMG_CHECK(kind >= 0 && kind < 3, "kind must be 0, 1 or 2");
+    const Partition P = host_partition(dim, ne, nn, elems1, owner_rank, rank, nranks);
+    const std::vector<int64_t>* off;
+    const std::vector<int32_t>* own;
+    if (cut) {
+        const CutCells& C = P.cut[kind];
+        off = &C.offset; own = &C.owner;
+        if (sizes) { sizes[0] = C.ncells(); sizes[1] = (int64_t)C.owner.size(); sizes[2] = C.nglobal; }
+        if (slot) std::copy(C.slot.begin(), C.slot.end(), slot);
+        if (first_local) std::copy(C.first_local.begin(), C.first_local.end(), first_local);
+    } else {
+        const CellMap& m = kind == 0 ? P.faces : kind == 1 ? P.edges : P.verts;
+        off = &m.offset; own = &m.owner;
+        if (sizes) { sizes[0] = m.ncells(); sizes[1] = (int64_t)m.owner.size(); }
+    }
+    if (offset) std::copy(off->begin(), off->end(), offset);
+    if (element) for (size_t q = 0; q < own->size(); ++q) element[q] = (*own)[q] >> 3;
+    if (local_id) for (size_t q = 0; q < own->size(); ++q) local_id[q] = (*own)[q] & 7;
+    HOST_END
+}
+
 // class bitmask of a local face / edge / vertex
 int hmg_host_class_of(int dim, int kind, int lid) {
     return kind == 0 ? class_of_face(lid) : kind == 1 ? class_of_edge(dim, lid) : class_of_vertex(dim, lid);

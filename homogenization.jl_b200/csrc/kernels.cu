@@ -61,6 +61,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ void scalar_post(double* S, int post, int slot, double tot) {
+    if (post == POST_STORE) S[slot] = tot;
+    else if (post == POST_RHO) S[S_RHO] = tot;
+    else if (post == POST_PAP) { S[S_PAP] = tot; S[S_ALPHA] = S[S_RHO] / tot; }
+    else if (post == POST_RSQR) { S[S_RSQR] = tot; S[S_BETA] = tot / S[S_RHO]; S[S_RHO] = tot; }
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -95,11 +101,7 @@ __device__ __forceinline__ void block_reduce_finish(double v, const Reducer& R, 
     if (threadIdx.x == 0) {
         double tot = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += wsum[w];
-        double* S = R.scalars;
-        if (post == POST_STORE) S[slot] = tot;
-        else if (post == POST_RHO) S[S_RHO] = tot;
-        else if (post == POST_PAP) { S[S_PAP] = tot; S[S_ALPHA] = S[S_RHO] / tot; }
-        else if (post == POST_RSQR) { S[S_RSQR] = tot; S[S_BETA] = tot / S[S_RHO]; S[S_RHO] = tot; }
+        scalar_post(R.scalars, post, slot, tot);
         *R.ticket = 0u;
     }
 }
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
         }
         dsum = out.dsum;
     }
-    if (DOT) block_reduce_finish(dsum, a.red, a.dot_post, 0);
+    if (DOT) block_reduce_finish(dsum, a.red, a.dot_post, S_TMP);
 }
 
 // ring size and launch shape of one level
@@ -621,6 +623,43 @@ int launch_zero_all_but_one(int dim, const LevelView& L, const TopoView& T, doub
     return launch_interface<1>(dim, L, T, x, st);
 }
 
+// Cut cells (owners on several ranks): pack the partial sum over the local owners into the level's
+// packed buffer / write the all-reduced total back to the local owners / zero all but the globally
+// first owner.  One thread per (cell, paired node).
+template <int OP>
+__global__ void __launch_bounds__(256) cut_kernel(const LevelView L, const CutView C, int npc, const uint16_t* __restrict__ tab,
+                                                  int64_t buf_base, double* __restrict__ x, double* __restrict__ buf) {
+    const int64_t total = C.ncells * npc;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t cell = t / npc;
+        const int k = (int)(t - cell * npc);
+        const int64_t b = C.off[cell], en = C.off[cell + 1];
+        const int64_t s = buf_base + C.slot[cell] * npc + k;
+        double acc = OP == CUT_UNPACK ? buf[s] : 0.0;
+        for (int64_t o = b; o < en; ++o) {
+            const int32_t id = C.own[o];
+            const int64_t el = id >> 3;
+            double* ptr = x + ((el >> L.wshift) * (int64_t)L.nf + __ldg(tab + (id & 7) * npc + k)) * L.W + (el & (L.W - 1));
+            if (OP == CUT_PACK) acc += *ptr;
+            else if (OP == CUT_UNPACK) *ptr = acc;
+            else if (!(o == b && C.first_local[cell])) *ptr = 0.0;
+        }
+        if (OP == CUT_PACK) buf[s] = acc;
+    }
+}
+int launch_cut(int dim, int op, int kind, const LevelView& L, const CutView& C, int64_t buf_base, double* x, double* buf,
+               cudaStream_t st) {
+    const int nfl = dim == 3 ? 4 : 0, nel = dim == 3 ? 6 : 3;
+    const int npc = kind == 0 ? L.npf : (kind == 1 ? L.npe : 1);
+    const uint16_t* tab = L.iface_idx + (kind == 0 ? 0 : (kind == 1 ? nfl * L.npf : nfl * L.npf + nel * L.npe));
+    if (C.ncells * npc == 0) return 0;
+    const unsigned grid = grid_for(C.ncells * npc, 256);
+    if (op == CUT_PACK) cut_kernel<CUT_PACK><<<grid, 256, 0, st>>>(L, C, npc, tab, buf_base, x, buf);
+    else if (op == CUT_UNPACK) cut_kernel<CUT_UNPACK><<<grid, 256, 0, st>>>(L, C, npc, tab, buf_base, x, buf);
+    else cut_kernel<CUT_ZERO_BUT_FIRST><<<grid, 256, 0, st>>>(L, C, npc, tab, buf_base, x, buf);
+    return 1;
+}
+
 // apply_constraint!: zero every stored node whose class is on the domain boundary; only elements
 // that touch the domain boundary are visited (belems)
 __global__ void __launch_bounds__(256) constraint_kernel(const LevelView L, int64_t nbelems, const int32_t* __restrict__ belems,
@@ -697,6 +736,12 @@ int launch_interp_add(int, const LevelView& Lf, const LevelView& Lc, int64_t nun
 // ------------------------------------------------------------------------------------------
 // K3: reductions and fused CG vector updates (scalars stay on the device)
 // ------------------------------------------------------------------------------------------
+__global__ void scalar_post_kernel(double* S, int post, int slot) { scalar_post(S, post, slot, S[S_TMP]); }
+int launch_scalar_post(const Reducer& R, int post, int slot, cudaStream_t st) {
+    scalar_post_kernel<<<1, 1, 0, st>>>(R.scalars, post, slot);
+    return 1;
+}
+
 __global__ void __launch_bounds__(256) dot_kernel(const Reducer R, const double* __restrict__ a, const double* __restrict__ b,
                                                   int64_t n, int post, int slot) {
     double s = 0.0;
@@ -713,7 +758,7 @@ __global__ void __launch_bounds__(256) dot_kernel(const Reducer R, const double*
 }
 
 // p = r ; rho = dot(r, r)   (src/multigrid.jl:53-54)
-__global__ void __launch_bounds__(256) copy_dot_kernel(const Reducer R, const double* __restrict__ r, double* __restrict__ p, int64_t n) {
+__global__ void __launch_bounds__(256) copy_dot_kernel(const Reducer R, const double* __restrict__ r, double* __restrict__ p, int64_t n, int post) {
     double s = 0.0;
     const int64_t n2 = n >> 1;
     const double2* r2 = reinterpret_cast<const double2*>(r);
@@ -724,12 +769,12 @@ __global__ void __launch_bounds__(256) copy_dot_kernel(const Reducer R, const do
         s = fma(v.x, v.x, s);
         s = fma(v.y, v.y, s);
     }
-    block_reduce_finish(s, R, POST_RHO, 0);
+    block_reduce_finish(s, R, post, S_TMP);
 }
 
 // x += alpha p ; r -= alpha Ap ; rsqr = dot(r, r) -> beta, rho   (src/multigrid.jl:64-68)
 __global__ void __launch_bounds__(256) cg_update_kernel(const Reducer R, double* __restrict__ x, const double* __restrict__ p,
-                                                        double* __restrict__ r, const double* __restrict__ Ap, int64_t n) {
+                                                        double* __restrict__ r, const double* __restrict__ Ap, int64_t n, int post) {
     const double alpha = R.scalars[S_ALPHA];
     double s = 0.0;
     const int64_t n2 = n >> 1;
@@ -745,7 +790,7 @@ __global__ void __launch_bounds__(256) cg_update_kernel(const Reducer R, double*
         x2[t] = xv; r2[t] = rv;
         s = fma(rv.x, rv.x, s); s = fma(rv.y, rv.y, s);
     }
-    block_reduce_finish(s, R, POST_RSQR, 0);
+    block_reduce_finish(s, R, post, S_TMP);
 }
 
 // p = r + beta p   (src/multigrid.jl:68)
@@ -777,12 +822,12 @@ int launch_dot(const Reducer& R, const double* a, const double* b, int64_t n, in
     dot_kernel<<<grid_for(n / 2 + 1, 256, R.max_blocks), 256, 0, st>>>(R, a, b, n, post, slot);
     return 1;
 }
-int launch_copy_dot(const Reducer& R, const double* r, double* p, int64_t n, cudaStream_t st) {
-    copy_dot_kernel<<<grid_for(n / 2 + 1, 256, R.max_blocks), 256, 0, st>>>(R, r, p, n);
+int launch_copy_dot(const Reducer& R, const double* r, double* p, int64_t n, int post, cudaStream_t st) {
+    copy_dot_kernel<<<grid_for(n / 2 + 1, 256, R.max_blocks), 256, 0, st>>>(R, r, p, n, post);
     return 1;
 }
-int launch_cg_update(const Reducer& R, double* x, const double* p, double* r, const double* Ap, int64_t n, cudaStream_t st) {
-    cg_update_kernel<<<grid_for(n / 2 + 1, 256, R.max_blocks), 256, 0, st>>>(R, x, p, r, Ap, n);
+int launch_cg_update(const Reducer& R, double* x, const double* p, double* r, const double* Ap, int64_t n, int post, cudaStream_t st) {
+    cg_update_kernel<<<grid_for(n / 2 + 1, 256, R.max_blocks), 256, 0, st>>>(R, x, p, r, Ap, n, post);
     return 1;
 }
 int launch_p_update(const Reducer& R, double* p, const double* r, int64_t n, cudaStream_t st) {
@@ -883,6 +928,24 @@ __global__ void gather_kernel(const int64_t* __restrict__ idx, int64_t n, const 
 }
 __global__ void scatter_kernel(const int64_t* __restrict__ idx, int64_t n, const double* __restrict__ src, double* __restrict__ dst) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) dst[idx[t]] = src[t];
+}
+// multi-GPU: every base node is reported by exactly one rank (the others contribute zero to the reduction)
+__global__ void masked_copy_to_base_kernel(const LevelView L1, int64_t nn, const int32_t* __restrict__ first,
+                                           const uint8_t* __restrict__ contrib, const double* __restrict__ v, double* __restrict__ u) {
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t id = first[n];
+        double val = 0.0;
+        if (id >= 0 && contrib[n]) {
+            const int64_t e = id >> 3;
+            val = v[((e >> L1.wshift) * (int64_t)L1.nf + L1.vpos[id & 7]) * L1.W + (e & (L1.W - 1))];
+        }
+        u[n] = val;
+    }
+}
+int launch_masked_copy_to_base(const LevelView& L1, int64_t nn, const int32_t* node_first, const uint8_t* contrib, const double* v,
+                               double* u, cudaStream_t st) {
+    masked_copy_to_base_kernel<<<grid_for(nn, 256), 256, 0, st>>>(L1, nn, node_first, contrib, v, u);
+    return 1;
 }
 int launch_copy_to_base(const LevelView& L1, int64_t nn, const int32_t* first, const double* v, double* u, cudaStream_t st) {
     copy_to_base_kernel<<<grid_for(nn, 256), 256, 0, st>>>(L1, nn, first, v, u);

@@ -45,6 +45,16 @@ struct Reducer {
     int max_blocks;
 };
 
+// cut cells of one kind (faces / edges / vertices) this rank takes part in (multi-GPU, hmg_host.hpp)
+struct CutView {
+    int64_t ncells;
+    const int64_t* slot;        // ordinal of the cell among the global cut cells of the kind
+    const int64_t* off;         // CSR over the local owners
+    const int32_t* own;         // local element * 8 + local id
+    const uint8_t* first_local; // the globally first owner is own[off[c]]
+};
+enum CutOp { CUT_PACK = 0, CUT_UNPACK = 1, CUT_ZERO_BUT_FIRST = 2 };
+
 enum ApplyMode { APPLY_AX = 0, APPLY_RESIDUAL = 1, APPLY_MULADD = 2 };
 
 // launch configuration of the streaming apply kernel for one level (chosen on the host, api.cu)
@@ -83,13 +93,20 @@ int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st);
 ApplyConfig make_apply_config(int dim, int m, int nf, int W);
 int launch_interface_sum(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
 int launch_zero_all_but_one(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
+// kind 0 faces / 1 edges / 2 vertices; buf_base = first slot of the kind in the level's packed buffer
+int launch_cut(int dim, int op, int kind, const LevelView& L, const CutView& C, int64_t buf_base, double* x, double* buf,
+               cudaStream_t st);
+// derived CG scalars after a cross-rank all-reduce of the raw dot product in S_TMP
+int launch_scalar_post(const Reducer& R, int post, int slot, cudaStream_t st);
+int launch_masked_copy_to_base(const LevelView& L1, int64_t nn, const int32_t* node_first, const uint8_t* contrib, const double* v,
+                               double* u, cudaStream_t st);
 int launch_apply_constraint(int dim, const LevelView& L, int64_t nbelems, const int32_t* belems, const uint16_t* cmask,
                             double* x, cudaStream_t st);
 int launch_restrict(int dim, const LevelView& Lf, const LevelView& Lc, int64_t nunits, const double* rf, double* bc, cudaStream_t st);
 int launch_interp_add(int dim, const LevelView& Lf, const LevelView& Lc, int64_t nunits, double* xf, const double* xc, cudaStream_t st);
 int launch_dot(const Reducer& R, const double* a, const double* b, int64_t n, int post, int slot, cudaStream_t st);
-int launch_copy_dot(const Reducer& R, const double* r, double* p, int64_t n, cudaStream_t st);
-int launch_cg_update(const Reducer& R, double* x, const double* p, double* r, const double* Ap, int64_t n, cudaStream_t st);
+int launch_copy_dot(const Reducer& R, const double* r, double* p, int64_t n, int post, cudaStream_t st);
+int launch_cg_update(const Reducer& R, double* x, const double* p, double* r, const double* Ap, int64_t n, int post, cudaStream_t st);
 int launch_p_update(const Reducer& R, double* p, const double* r, int64_t n, cudaStream_t st);
 int launch_axpy(double alpha, const double* x, double* y, int64_t n, cudaStream_t st);
 int launch_fill(double* x, double v, int64_t n, cudaStream_t st);

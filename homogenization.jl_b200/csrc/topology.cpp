@@ -168,6 +168,93 @@ Topology build_topology(int dim, int64_t ne, int64_t nn, const int64_t* elems) {
     return T;
 }
 
+Partition build_partition(const Topology& T, const int32_t* owner_rank, int rank, int nranks) {
+    HMG_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / number of ranks");
+    Partition P;
+    P.rank = rank;
+    P.nranks = nranks;
+    const int dim = T.dim;
+    const int64_t ne = T.ne;
+    P.global_to_local.assign(ne, -1);
+    for (int64_t e = 0; e < ne; ++e) {
+        const int r = owner_rank ? owner_rank[e] : 0;
+        HMG_CHECK(r >= 0 && r < nranks, "owner_rank out of range");
+        if (r == rank) {
+            P.global_to_local[e] = (int32_t)P.local_to_global.size();
+            P.local_to_global.push_back(e);
+        }
+    }
+    const int64_t nel = (int64_t)P.local_to_global.size();
+    auto rank_of = [&](int32_t id) { return owner_rank ? owner_rank[id >> 3] : 0; };
+    const CellMap* maps[3] = {&T.faces, &T.edges, &T.verts};
+    CellMap* locals[3] = {&P.faces, &P.edges, &P.verts};
+    for (int kind = 0; kind < 3; ++kind) {
+        const CellMap& m = *maps[kind];
+        CellMap& loc = *locals[kind];
+        CutCells& cut = P.cut[kind];
+        loc.offset.assign(1, 0);
+        cut.offset.assign(1, 0);
+        for (int64_t c = 0; c < m.ncells(); ++c) {
+            const int64_t b = m.offset[c], en = m.offset[c + 1];
+            int nlocal = 0;
+            bool is_cut = false;
+            for (int64_t o = b; o < en; ++o) {
+                if (rank_of(m.owner[o]) == rank) ++nlocal;
+                if (rank_of(m.owner[o]) != rank_of(m.owner[b])) is_cut = true;
+            }
+            if (!is_cut) {
+                if (nlocal == 0) continue;
+                for (int64_t o = b; o < en; ++o)
+                    loc.owner.push_back(P.global_to_local[m.owner[o] >> 3] * 8 + (m.owner[o] & 7));
+                loc.cell_key.push_back(m.cell_key[c]);
+                loc.offset.push_back((int64_t)loc.owner.size());
+                continue;
+            }
+            const int64_t slot = cut.nglobal++;
+            if (nlocal == 0) continue;
+            cut.slot.push_back(slot);
+            cut.first_local.push_back(rank_of(m.owner[b]) == rank ? 1 : 0);
+            for (int64_t o = b; o < en; ++o)
+                if (rank_of(m.owner[o]) == rank)
+                    cut.owner.push_back(P.global_to_local[m.owner[o] >> 3] * 8 + (m.owner[o] & 7));
+            cut.offset.push_back((int64_t)cut.owner.size());
+        }
+    }
+    // Dirichlet classes and owner counts of the local elements (from the GLOBAL topology)
+    P.cmask.resize(nel);
+    P.mult.assign((size_t)nel * 16, 1);
+    const int nv = dim + 1, nfl = dim == 3 ? 4 : 0, ned = dim == 3 ? 6 : 3;
+    for (int64_t l = 0; l < nel; ++l) {
+        const int64_t e = P.local_to_global[l];
+        P.cmask[l] = T.cmask[e];
+        auto owners = [&](int slot) -> int {
+            const int32_t id = T.elem_cells[(size_t)e * 16 + slot];
+            if (id < 0) return 1;
+            const int64_t n = T.cell_off[id + 1] - T.cell_off[id];
+            HMG_CHECK(n <= 255, "a base-mesh cell has more than 255 owners");
+            return (int)n;
+        };
+        uint8_t* dst = &P.mult[(size_t)l * 16];
+        for (int q = 0; q < nfl; ++q) dst[class_of_face(q)] = (uint8_t)owners(q);
+        for (int q = 0; q < ned; ++q) dst[class_of_edge(dim, q)] = (uint8_t)owners(nfl + q);
+        for (int q = 0; q < nv; ++q) dst[class_of_vertex(dim, q)] = (uint8_t)owners(nfl + ned + q);
+    }
+    // base nodes: first local owner; the lowest rank that owns a copy reports the node to the coarse solve
+    P.node_first.assign(T.nn, -1);
+    P.node_contrib.assign(T.nn, 0);
+    for (int64_t n = 0; n < T.nn; ++n) {
+        int lowest = nranks;
+        for (int64_t o = T.nodeown_off[n]; o < T.nodeown_off[n + 1]; ++o) {
+            const int32_t id = T.nodeown[o];
+            const int r = rank_of(id);
+            lowest = std::min(lowest, r);
+            if (r == rank && P.node_first[n] < 0) P.node_first[n] = P.global_to_local[id >> 3] * 8 + (id & 7);
+        }
+        P.node_contrib[n] = lowest == rank ? 1 : 0;
+    }
+    return P;
+}
+
 void element_coefficients(int dim, int64_t ne, const double* nodes, const int64_t* elems,
                           const double* sigma, std::vector<double>& coef, int stride) {
     const int nv = dim + 1;

@@ -33,6 +33,21 @@ int hmg_host_topology(int dim, int64_t ne, int64_t nn, const int64_t* elems1, in
 /* Dirichlet classes per element and interior-node flags (src/interface.jl:207-284, src/grid.jl:176-202) */
 int hmg_host_boundary(int dim, int64_t ne, int64_t nn, const int64_t* elems1, uint16_t* cmask, uint8_t* interior);
 int hmg_host_class_of(int dim, int kind, int lid);
+/* partition of the coarse elements over ranks (the host logic behind hmg_create_partitioned): local elements of
+ * `rank` with their Dirichlet class masks, owner counts mult[ne_local][16] (owners on all ranks of the cell behind
+ * every node class), per base node the first local owner (element*8+local id, -1 none) and whether this rank
+ * reports the node to the coarse solve on rank 0.  Arrays may be NULL. */
+int hmg_host_partition_elements(int dim, int64_t ne, int64_t nn, const int64_t* elems1, const int32_t* owner_rank, int rank,
+                                int nranks, int64_t* ne_local, int64_t* local_to_global, uint16_t* cmask, uint8_t* mult,
+                                int32_t* node_first, uint8_t* node_contrib);
+/* interface cells of one kind (0 faces, 1 edges, 2 vertices) as seen by `rank`.  cut == 0: cells whose owners are
+ * all local, sizes[2] = cells, entries, CSR offset / element (LOCAL index) / local_id.  cut == 1: cut cells (owners
+ * on several ranks) this rank takes part in, sizes[3] = cells, entries, cut cells of the kind on ALL ranks;
+ * slot[cells] = ordinal in the global cut enumeration (the packed exchange buffer), first_local[cells] = 1 if the
+ * globally first owner is this rank's first entry. */
+int hmg_host_partition_cells(int dim, int64_t ne, int64_t nn, const int64_t* elems1, const int32_t* owner_rank, int rank,
+                             int nranks, int kind, int cut, int64_t* sizes, int64_t* offset, int64_t* element, int64_t* local_id,
+                             int64_t* slot, uint8_t* first_local);
 int hmg_host_element_coefficients(int dim, int64_t ne, int64_t nn, const double* nodes, const int64_t* elems1,
                                   const double* sigma, double* coef, int stride);
 
