@@ -3,7 +3,7 @@
 matrix-free global product A*x) on synthetic checkerboard inputs, with the HBM roofline of the
 dominant kernel and the CPU baseline timed beside it.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C1..C4|custom]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload auto|C1..C4] [--cells c]
 
 One JSON line is printed by rank 0.  See DESIGN.md ("Measurement") for the byte model.
 """
@@ -25,7 +25,9 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 # dim, cells per side, grids (= refinements + 1); BASELINE.md section 4
 WORKLOADS = {
     "C1": dict(dim=2, c=48, levels=5, name="C1: 2D Tri64 checkerboard c=48 refinements=4 (README example shape)"),
-    "C2": dict(dim=2, c=256, levels=8, name="C2: 2D Tri64 checkerboard c=256 refinements=7"),
+    # c = 192 is the largest "large base mesh" whose coarsest-grid problem (191^2 interior nodes) fits the
+    # exact dense coarse solver on GPU 0 (n < 46 340, cuSOLVER's 32-bit potri); BASELINE.md proposed c = 256
+    "C2": dict(dim=2, c=192, levels=8, name="C2: 2D Tri64 checkerboard c=192 refinements=7"),
     "C3": dict(dim=3, c=20, levels=5, name="C3: 3D Tet64 checkerboard c=20 refinements=4"),
     "C4": dict(dim=3, c=32, levels=6, name="C4: 3D Tet64 checkerboard c=32 refinements=5"),
 }
@@ -168,6 +170,161 @@ def cpu_reference_run(w, steps, warmup, target_seconds=20.0):
 
 
 # ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def host_memory_available():
+    try:
+        import psutil
+        return int(psutil.virtual_memory().available)
+    except Exception:
+        return 1 << 40
+
+
+def traffic_per_launch(name, dofs_local):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the finest-level apply kernel from the committed
+    `ncu --set full` capture (profiles/apply_traffic.json: measured bytes per stored DOF per launch)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "apply_traffic.json")))
+        return float(t[name]["dram_bytes_per_dof"]) * dofs_local, t[name].get("source")
+    except Exception:
+        return None, None
+
+
+def measure(w, args, torch, hmg, dist, rank, world, device, steps, warmup, with_e2e, with_clocks):
+    """One workload on this process' GPU (its share of the coarse elements when world > 1)."""
+    dim, levels = w["dim"], w["levels"]
+    mesh, sigma = build_inputs(w)
+    if world > 1:
+        owner = hmg.inputs.spatial_partition(mesh, world)
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = (__import__("ctypes").c_ubyte * 128)()
+            hmg._lib.check(hmg.load().hmg_nccl_unique_id(raw))
+            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+        idbuf = idbuf.cuda()
+        dist.broadcast(idbuf, 0)
+        nccl_id = bytes(idbuf.cpu().tolist())
+        g = hmg.ImplicitFineGrid(mesh, levels, sigma, lam=1.0, device=device, owner_rank=owner, rank=rank,
+                                 nranks=world, nccl_id=nccl_id)
+    else:
+        g = hmg.ImplicitFineGrid(mesh, levels, sigma, lam=1.0, device=device)
+    nf = g.nf(levels)
+    ne_local = g.ne_local
+    dofs_total = nf * mesh.nelements
+    dofs_local = nf * ne_local
+
+    # inputs: x0 ~ U(0,1) then interface-sum + zero Dirichlet; b = local functional of 1 (un-summed)
+    rng = np.random.default_rng(1234 + rank)
+    st = g.state(levels)
+    hx = torch.empty((ne_local, nf), dtype=torch.float64, pin_memory=True)      # column-major Nf x Ne
+    chunk = max(1, (1 << 24) // nf)
+    for c0 in range(0, ne_local, chunk):
+        hx[c0:c0 + chunk] = torch.from_numpy(rng.random((min(chunk, ne_local - c0), nf)))
+    X = hx.numpy().T
+    st.x.set(X)
+    bval = 1.0 / (nf * (2 if dim == 2 else 6))
+    st.b.fill(bval)
+    hmg.broadcast_interfaces(st.x, g, levels)
+    hmg.apply_constraint(st.x, levels, g)
+    st.p.copy_from(st.x)
+    t_setup = time.perf_counter()
+    bl = hmg.BaseLevel(g)
+    t_setup = time.perf_counter() - t_setup
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        g.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # --- V-cycle, inputs resident in HBM -------------------------------------------------------
+    for _ in range(warmup):
+        hmg.vcycle(g, bl, levels, SMOOTHING_STEPS)
+    barrier()
+    launches_w = g.launch_count()
+    sampler = ClockSampler(device) if with_clocks else None
+    if sampler:
+        sampler.start()
+    barrier()
+    ms = g.time_op(1, levels, SMOOTHING_STEPS, steps)         # CUDA events on the library's stream
+    barrier()
+    ms = max_over_ranks(ms)
+    launches = g.launch_count() - launches_w
+    vcycle_gdofs = dofs_total * steps / (ms * 1e-3) / 1e9
+
+    # --- A*x (global product), and the dominant kernel alone ------------------------------------
+    reps = 20
+    g.time_op(0, levels, 0, 3)
+    barrier()
+    ms_ax = max_over_ranks(g.time_op(0, levels, 0, reps)) / reps
+    g.time_op(3, levels, 0, 3)
+    barrier()
+    ms_apply = max_over_ranks(g.time_op(3, levels, 0, reps)) / reps
+    clocks = sampler.summary() if sampler else None
+    peak, peak_src = measured_peak()
+    apply_bytes = 16.0 * dofs_local                            # read p once, write Ap once
+    achieved = apply_bytes / (ms_apply * 1e-3) / 1e9
+    traffic, traffic_src = traffic_per_launch(w["key"], dofs_local)
+
+    # --- end to end through the public API with host buffers ------------------------------------
+    e2e = None
+    if with_e2e:
+        hb = torch.empty((ne_local, nf), dtype=torch.float64, pin_memory=True)
+        hout = torch.empty((ne_local, nf), dtype=torch.float64, pin_memory=True)
+        hb.fill_(bval)
+        B, OUT = hb.numpy().T, hout.numpy().T
+
+        def e2e_step():
+            st.x.set(X)
+            st.b.set(B)
+            hmg.vcycle(g, bl, levels, SMOOTHING_STEPS)
+            st.x.get(OUT)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(steps, 3))
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        t_e2e = max_over_ranks((time.perf_counter() - t0) / n_e2e)
+        e2e = {"value": dofs_total / t_e2e / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 2 * 8 * dofs_local,
+               "d2h_bytes_per_step": 8 * dofs_local, "steps": n_e2e,
+               "what": "upload x and b from pinned host memory through hmg_upload, one V-cycle, download x"}
+        del hb, hout
+    bv = vcycle_bytes_per_dof(dim, levels)
+    out = {
+        "value": vcycle_gdofs, "ms_per_step": ms / steps,
+        "config": {"workload": w["name"], "dim": dim, "grids": levels, "coarse_elements": int(mesh.nelements),
+                   "stored_dofs": int(dofs_total), "smoothing_steps": SMOOTHING_STEPS,
+                   "field": "checkerboard sigma in {1,9} per axis, seed 1", "lambda": 1.0,
+                   "l2": f"inputs larger than L2 ({8 * dofs_local / 1e6:.0f} MB per vector per GPU vs 126 MB)",
+                   "partition": "spatial blocks of whole cells, strong scaling" if world > 1 else "single GPU",
+                   "coarse_solver_setup_s": t_setup},
+        "ax": {"value": dofs_total / (ms_ax * 1e-3) / 1e9, "unit": "GDOF/s", "ms": ms_ax,
+               "what": "Ap = broadcast(constraint(A p)) on the finest level, 16 B per stored DOF",
+               "hbm_frac_of_measured": 16.0 * dofs_local / (ms_ax * 1e-3) / 1e9 / peak,
+               "hbm_frac_of_nominal_8TBs": 16.0 * dofs_local / (ms_ax * 1e-3) / 1e9 / 8000.0},
+        "vcycle_model": {"bytes_per_dof": bv, "achieved_gbs": bv * dofs_local / (ms / steps * 1e-3) / 1e9,
+                         "hbm_frac_of_measured": bv * dofs_local / (ms / steps * 1e-3) / 1e9 / peak,
+                         "hbm_frac_of_nominal_8TBs": bv * dofs_local / (ms / steps * 1e-3) / 1e9 / 8000.0},
+        "roofline": {"kernel": "apply_kernel (local operator apply, finest level)", "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": apply_bytes, "ms_per_launch": ms_apply},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+    }
+    g.close()
+    del hx
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,19 +335,27 @@ def main():
     ap.add_argument("--cells", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary (3D) workload")
     args = ap.parse_args()
     warmup = max(3, args.warmup)
     steps = max(1, args.steps)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    name = args.workload
-    if name == "auto":
-        name = "C4" if args.gpus > 1 else "C3"
-    w = dict(WORKLOADS[name])
+    # The metric is quoted on BASELINE.json configs[1] (C2: 2D Tri64, refinements = 7, large base mesh);
+    # the same problem is sharded over the ranks for N > 1 (strong scaling).  The 3D Tet64 scaling
+    # configuration (C4) is measured in the same run and reported under "also".
+    name = "C2" if args.workload == "auto" else args.workload
+    w = dict(WORKLOADS[name], key=name)
     if args.cells:
         w["c"] = args.cells
         w["name"] = w["name"].replace(f"c={WORKLOADS[name]['c']}", f"c={args.cells}")
+    elif args.impl == "b200" and args.workload == "auto":
+        # three pinned host matrices of the local share (x, b, result) must fit the host comfortably
+        need = 3 * 8 * nf_of(w["dim"], w["levels"]) * 2 * w["c"] ** 2 // max(1, world)
+        if need * 1.5 > host_memory_available():
+            w["c"] = 128
+            w["name"] = w["name"].replace("c=192", "c=128 (host memory too small for c=192)")
     dim, levels = w["dim"], w["levels"]
 
     if args.impl == "reference":
@@ -224,109 +389,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = local_rank
 
-    mesh, sigma = build_inputs(w)
-    if world > 1:
-        owner = hmg.inputs.spatial_partition(mesh, world)
-        idbuf = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            raw = (__import__("ctypes").c_ubyte * 128)()
-            hmg._lib.check(hmg.load().hmg_nccl_unique_id(raw))
-            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
-        idbuf = idbuf.cuda()
-        dist.broadcast(idbuf, 0)
-        nccl_id = bytes(idbuf.cpu().tolist())
-        g = hmg.ImplicitFineGrid(mesh, levels, sigma, lam=1.0, device=device, owner_rank=owner, rank=rank,
-                                 nranks=world, nccl_id=nccl_id)
-    else:
-        g = hmg.ImplicitFineGrid(mesh, levels, sigma, lam=1.0, device=device)
-    nf = g.nf(levels)
-    ne_local = g.ne_local
-    dofs_total = nf * mesh.nelements
-    dofs_local = nf * ne_local
-
-    # inputs: x0 ~ U(0,1) then interface-sum + zero Dirichlet; b = local functional of 1 (un-summed)
-    rng = np.random.default_rng(1234 + rank)
-    hx = torch.empty((ne_local, nf), dtype=torch.float64, pin_memory=True)      # column-major Nf x Ne
-    hb = torch.empty((ne_local, nf), dtype=torch.float64, pin_memory=True)
-    hout = torch.empty((ne_local, nf), dtype=torch.float64, pin_memory=True)
-    chunk = max(1, (1 << 24) // nf)
-    for c0 in range(0, ne_local, chunk):
-        hx[c0:c0 + chunk] = torch.from_numpy(rng.random((min(chunk, ne_local - c0), nf)))
-    hb.fill_(1.0 / (nf * (2 if dim == 2 else 6)))
-    st = g.state(levels)
-    X = hx.numpy().T
-    B = hb.numpy().T
-    OUT = hout.numpy().T
-    st.x.set(X)
-    st.b.set(B)
-    hmg.broadcast_interfaces(st.x, g, levels)
-    hmg.apply_constraint(st.x, levels, g)
-    st.p.copy_from(st.x)
-    t_setup = time.perf_counter()
-    bl = hmg.BaseLevel(g)
-    t_setup = time.perf_counter() - t_setup
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        g.synchronize()
-
-    def max_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # --- V-cycle, inputs resident in HBM -------------------------------------------------------
-    launches0 = g.launch_count()
-    for _ in range(warmup):
-        hmg.vcycle(g, bl, levels, SMOOTHING_STEPS)
-    barrier()
-    launches_w = g.launch_count()
-    sampler = ClockSampler(device)
-    sampler.start()
-    barrier()
-    ms = g.time_op(1, levels, SMOOTHING_STEPS, steps)         # CUDA events on the library's stream
-    barrier()
-    ms = max_over_ranks(ms)
-    launches = g.launch_count() - launches_w
-    vcycle_gdofs = dofs_total * steps / (ms * 1e-3) / 1e9
-
-    # --- A*x (global product), and the dominant kernel alone ------------------------------------
-    reps = 20
-    g.time_op(0, levels, 0, 3)
-    barrier()
-    ms_ax = max_over_ranks(g.time_op(0, levels, 0, reps)) / reps
-    g.time_op(3, levels, 0, 3)
-    barrier()
-    ms_apply = max_over_ranks(g.time_op(3, levels, 0, reps)) / reps
-    clocks = sampler.summary()
-    ax_gdofs = dofs_total / (ms_ax * 1e-3) / 1e9
-    peak, peak_src = measured_peak()
-    apply_bytes = 16.0 * dofs_local                            # read p once, write Ap once
-    achieved = apply_bytes / (ms_apply * 1e-3) / 1e9
-
-    # --- end to end through the public API with host buffers ------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        def e2e_step():
-            st.x.set(X)
-            st.b.set(B)
-            hmg.vcycle(g, bl, levels, SMOOTHING_STEPS)
-            st.x.get(OUT)
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        n_e2e = max(1, min(steps, 3))
-        for _ in range(n_e2e):
-            e2e_step()
-        barrier()
-        t_e2e = max_over_ranks((time.perf_counter() - t0) / n_e2e)
-        e2e = {"value": dofs_total / t_e2e / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 2 * 8 * dofs_local,
-               "d2h_bytes_per_step": 8 * dofs_local, "steps": n_e2e,
-               "what": "upload x and b from pinned host memory, one V-cycle, download x"}
+    main_r = measure(w, args, torch, hmg, dist, rank, world, device, steps, warmup, not args.no_e2e, True)
+    also = None
+    if args.workload == "auto" and not args.no_also:
+        w3 = dict(WORKLOADS["C4"], key="C4")
+        r3 = measure(w3, args, torch, hmg, dist, rank, world, device, min(steps, 5), 3, False, False)
+        also = {"C4": {k: r3[k] for k in ("value", "ms_per_step", "config", "ax", "vcycle_model", "roofline", "gpu_launches")}}
+        also["C4"]["unit"] = "GDOF/s"
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -335,36 +404,16 @@ def main():
                "ax_gdofs": r["ax_gdofs"], "note": "threaded C restatement of the reference's CPU algorithm, not Julia"}
 
     if rank == 0:
-        bv = vcycle_bytes_per_dof(dim, levels)
         line = {
             "metric": "fine-grid GDOF/s, multigrid V-cycle (stored finest-level DOFs per second)",
-            "value": vcycle_gdofs, "unit": "GDOF/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "value": main_r["value"], "unit": "GDOF/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": main_r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["name"], "dim": dim, "grids": levels, "coarse_elements": int(mesh.nelements),
-                       "stored_dofs": int(dofs_total), "smoothing_steps": SMOOTHING_STEPS,
-                       "field": "checkerboard sigma in {1,9} per axis, seed 1", "lambda": 1.0,
-                       "l2": f"inputs larger than L2 ({8 * dofs_local / 1e6:.0f} MB per vector per GPU vs 126 MB)",
-                       "partition": "spatial blocks of whole cells" if world > 1 else "single GPU",
-                       "coarse_solver_setup_s": t_setup},
-            "ax": {"value": ax_gdofs, "unit": "GDOF/s", "ms": ms_ax,
-                   "what": "Ap = broadcast(constraint(A p)) on the finest level, 16 B per stored DOF",
-                   "hbm_frac_of_measured": 16.0 * dofs_local / (ms_ax * 1e-3) / 1e9 / peak,
-                   "hbm_frac_of_nominal_8TBs": 16.0 * dofs_local / (ms_ax * 1e-3) / 1e9 / 8000.0},
-            "vcycle_model": {"bytes_per_dof": bv, "achieved_gbs": bv * dofs_local / (ms / steps * 1e-3) / 1e9,
-                             "hbm_frac_of_measured": bv * dofs_local / (ms / steps * 1e-3) / 1e9 / peak,
-                             "hbm_frac_of_nominal_8TBs": bv * dofs_local / (ms / steps * 1e-3) / 1e9 / 8000.0},
-            "roofline": {"kernel": "apply_kernel (local operator apply, finest level)", "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": apply_bytes,
-                         "ms_per_launch": ms_apply},
-            "clocks": clocks,
-            "e2e": e2e,
-            "gpu_launches": int(launches),
-            "cpu_baseline": cpu,
+            "config": main_r["config"], "ax": main_r["ax"], "vcycle_model": main_r["vcycle_model"],
+            "roofline": main_r["roofline"], "clocks": main_r["clocks"], "e2e": main_r["e2e"],
+            "gpu_launches": main_r["gpu_launches"], "cpu_baseline": cpu, "also": also,
         }
         print(json.dumps(line))
-    g.close()
     if dist is not None:
         dist.destroy_process_group()
 
