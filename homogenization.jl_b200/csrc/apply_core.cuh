@@ -84,37 +84,56 @@ template <int DIM> struct StencilTab {
     double ge[Dims<DIM>::NCLS][Dims<DIM>::NC];        // segment along the reference edge of a 2-face class
 };
 
-// per-lane (= per coarse element) operator data
+// per-lane (= per coarse element) operator data.  The interior stencil lives in registers; the element's
+// |J| P / lambda |J| components are only needed again for the few "special" coefficients of edge and
+// vertex nodes, so a kernel short of registers may leave them in memory (LaneOpMem).
 template <int DIM> struct LaneOp {
+    static constexpr int dim = DIM;
     double ec[Dims<DIM>::NC];                             // |J| P (upper triangle), lambda |J|
     double c0, cz, ca[Sweep<DIM>::NP], cb[Sweep<DIM>::NP];   // interior stencil, one value per +-pair
+    HMG_HD double coef(int q) const { return ec[q]; }
+};
+template <int DIM> struct LaneOpMem {
+    static constexpr int dim = DIM;
+    const double* ecp;                                    // component q at ecp[q * stride]
+    int stride;
+    double lambda;                                        // scales the last component
+    double c0, cz, ca[Sweep<DIM>::NP], cb[Sweep<DIM>::NP];
+    HMG_HD double coef(int q) const {
+#ifdef __CUDA_ARCH__
+        const double v = __ldg(ecp + q * stride);
+#else
+        const double v = ecp[q * stride];
+#endif
+        return q == Dims<DIM>::NC - 1 ? v * lambda : v;
+    }
 };
 
-template <int DIM> HMG_HD double combine(const LaneOp<DIM>& op, const double* g) {
+template <class Op> HMG_HD double combine(const Op& op, const double* g) {
     double c = 0.0;
 #pragma unroll
-    for (int q = 0; q < Dims<DIM>::NC; ++q) c = fma(op.ec[q], g[q], c);
+    for (int q = 0; q < Dims<Op::dim>::NC; ++q) c = fma(op.coef(q), g[q], c);
     return c;
 }
-template <int DIM> HMG_HD void interior_coefficients(LaneOp<DIM>& op, const StencilTab<DIM>& T) {
+template <class Op> HMG_HD void interior_coefficients(Op& op, const StencilTab<Op::dim>& T) {
     op.c0 = combine(op, T.gi[0]);
     op.cz = combine(op, T.gi[1]);
 #pragma unroll
-    for (int q = 0; q < Sweep<DIM>::NP; ++q) {
+    for (int q = 0; q < Sweep<Op::dim>::NP; ++q) {
         op.ca[q] = combine(op, T.gi[2 + 2 * q]);
         op.cb[q] = combine(op, T.gi[3 + 2 * q]);
     }
 }
 
-template <int DIM, int CLS, int DIR>
-HMG_HD void acc_tap(const LaneOp<DIM>& op, const StencilTab<DIM>& T, double c, double v, double& a1, double& ah) {
+template <int DIM, int CLS, int DIR, class Op>
+HMG_HD void acc_tap(const Op& op, const StencilTab<DIM>& T, double c, double v, double& a1, double& ah) {
     constexpr int w = wcode<DIM>(CLS, DIR);
     if (w == W_FULL) a1 = fma(c, v, a1);
     else if (w == W_HALF) ah = fma(c, v, ah);
     else if (w == W_SPEC_E) a1 = fma(combine(op, T.ge[seg_class<DIM>(CLS, DIR)]), v, a1);
 }
-template <int DIM, int CLS, int Q>
-HMG_HD void acc_lines(const LaneOp<DIM>& op, const StencilTab<DIM>& T, const double* Mm, const double* Mk,
+template <int DIM, int CLS, int Q, class Op>
+HMG_HD void acc_lines(const Op& op, const StencilTab<DIM>& T, const double* Mm, const double* Mk,
                       const double* Pk, const double* Pp, double& a1, double& ah) {
     using S = Sweep<DIM>;
     acc_tap<DIM, CLS, S::m0(Q)>(op, T, op.ca[Q], Mk[Q], a1, ah);
@@ -126,8 +145,8 @@ HMG_HD void acc_lines(const LaneOp<DIM>& op, const StencilTab<DIM>& T, const dou
 
 // (A x) at one node of class CLS.  xm/x0/xp: centre line at k-1, k, k+1; Mm/Mk: minus lines at k-1, k;
 // Pk/Pp: plus lines at k, k+1.  Taps that do not exist for the class are never read.
-template <int DIM, int CLS>
-HMG_HD double eval_node(const LaneOp<DIM>& op, const StencilTab<DIM>& T, double xm, double x0, double xp,
+template <int DIM, int CLS, class Op>
+HMG_HD double eval_node(const Op& op, const StencilTab<DIM>& T, double xm, double x0, double xp,
                         const double* Mm, const double* Mk, const double* Pk, const double* Pp) {
     using S = Sweep<DIM>;
     if (CLS == 0) {
@@ -169,8 +188,8 @@ template <int DIM> struct LineGeo {
 // Sweep nodes [k0, k1) of a line with L >= 2 nodes.  Classes: FIRST at k = 0, LAST at k = L - 1, MID
 // in between.  RS = distance (in doubles) between consecutive nodes of a line.  Mem(addr) reads the
 // input value, out.template put<CLS>(k, acc, x0) consumes the result.
-template <int DIM, int MID, int FIRST, int LAST, class Mem, class Out>
-HMG_HD void sweep_line(const LaneOp<DIM>& op, const StencilTab<DIM>& T, const Mem& mem, int RS, const LineGeo<DIM>& g, Out& out) {
+template <int DIM, int MID, int FIRST, int LAST, class Op, class Mem, class Out>
+HMG_HD void sweep_line(const Op& op, const StencilTab<DIM>& T, const Mem& mem, int RS, const LineGeo<DIM>& g, Out& out) {
     using S = Sweep<DIM>;
     constexpr int NP = S::NP;
     int k = g.k0;
@@ -226,8 +245,8 @@ HMG_HD void sweep_line(const LaneOp<DIM>& op, const StencilTab<DIM>& T, const Me
 }
 
 // a line with a single node (the last plane / line of the simplex)
-template <int DIM, int CLS, class Mem, class Out>
-HMG_HD void single_node(const LaneOp<DIM>& op, const StencilTab<DIM>& T, const Mem& mem, int RS, const LineGeo<DIM>& g, Out& out) {
+template <int DIM, int CLS, class Op, class Mem, class Out>
+HMG_HD void single_node(const Op& op, const StencilTab<DIM>& T, const Mem& mem, int RS, const LineGeo<DIM>& g, Out& out) {
     using S = Sweep<DIM>;
     constexpr int NP = S::NP;
     double Mm[NP], Mk[NP], Pk[NP], Pp[NP];
@@ -274,8 +293,8 @@ HMG_HD LineRows2 line_rows2(int m, int i, int k0, int k1) {
 }
 
 // dispatch of one task to the sweep of its line type
-template <class Mem, class Out>
-HMG_HD void run_line3(const LaneOp<3>& op, const StencilTab<3>& T, const Mem& mem, int RS, const LineGeo<3>& g, int t, int i, Out& out) {
+template <class Op, class Mem, class Out>
+HMG_HD void run_line3(const Op& op, const StencilTab<3>& T, const Mem& mem, int RS, const LineGeo<3>& g, int t, int i, Out& out) {
     constexpr int K = 1, J = 2, I = 4, S = 8;
     if (g.L == 1) {
         if (i == 0) single_node<3, I | K | S>(op, T, mem, RS, g, out);
@@ -286,8 +305,8 @@ HMG_HD void run_line3(const LaneOp<3>& op, const StencilTab<3>& T, const Mem& me
     else if (i == t) sweep_line<3, J, J | K, J | S>(op, T, mem, RS, g, out);
     else sweep_line<3, 0, K, S>(op, T, mem, RS, g, out);
 }
-template <class Mem, class Out>
-HMG_HD void run_line2(const LaneOp<2>& op, const StencilTab<2>& T, const Mem& mem, int RS, const LineGeo<2>& g, int i, Out& out) {
+template <class Op, class Mem, class Out>
+HMG_HD void run_line2(const Op& op, const StencilTab<2>& T, const Mem& mem, int RS, const LineGeo<2>& g, int i, Out& out) {
     constexpr int J = 1, I = 2, S = 4;
     if (g.L == 1) single_node<2, J | S>(op, T, mem, RS, g, out);
     else if (i == 0) sweep_line<2, I, I | J, I | S>(op, T, mem, RS, g, out);

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <type_traits>
 
 #include "kernels.cuh"
 #include "lattice.hpp"
@@ -267,7 +268,8 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
         out.sa = a.sa;
         out.dsum = 0.0;
         out.cm = 0; out.ml = out.mh = 0ull;
-        LaneOp<DIM> op;
+        // the fused-dot variant is short of registers: it re-reads |J| P for the rare special coefficients
+        typename std::conditional<DOT, LaneOpMem<DIM>, LaneOp<DIM>>::type op;
         const int RL = DIM == 3 ? a.run : 1;     // 3D: consecutive lines of a plane per task
         const int SEGS = a.seg_shift;           // 2D: log2(nodes per task)
         int64_t u = u0, ucur = -1;
@@ -293,9 +295,15 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
             if (u != ucur) {
                 ucur = u;
                 const int64_t e = u * APPLY_W + lane;
+                if constexpr (DOT) {
+                    op.ecp = a.coef + u * D::CS * APPLY_W + lane;
+                    op.stride = APPLY_W;
+                    op.lambda = a.lambda;
+                } else {
 #pragma unroll
-                for (int q = 0; q < D::NC; ++q) op.ec[q] = __ldg(a.coef + (u * D::CS + q) * APPLY_W + lane);
-                op.ec[D::NC - 1] *= a.lambda;
+                    for (int q = 0; q < D::NC; ++q) op.ec[q] = __ldg(a.coef + (u * D::CS + q) * APPLY_W + lane);
+                    op.ec[D::NC - 1] *= a.lambda;
+                }
                 interior_coefficients(op, a.T);
                 if (MODE != APPLY_MULADD) out.cm = (unsigned)__ldg(a.cmask + e);
                 if (DOT) {
@@ -495,8 +503,13 @@ static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
     p.run = a.cfg.run;
     p.dot_post = a.dot_post;
     p.red = a.red;
+    // more CTAs than SMs when the problem is large: the hardware hands the next CTA to whichever SM finishes
+    // first (SMs do not all see the same memory latency); every CTA still streams >= 8192 rows
     const int64_t planes = a.nunits * (a.L.m + 1);
-    int64_t grid = std::min<int64_t>((int64_t)sms * a.cfg.ctas_per_sm, planes);
+    const int64_t rows_per_sm = a.nunits * a.L.nf / sms;
+    static const int over_env = getenv("HMG_APPLY_OVERSUB") ? atoi(getenv("HMG_APPLY_OVERSUB")) : 0;
+    const int64_t over = over_env > 0 ? over_env : std::max<int64_t>(1, std::min<int64_t>(8, rows_per_sm / 8192));
+    int64_t grid = std::min<int64_t>((int64_t)sms * a.cfg.ctas_per_sm * over, planes);
     if (DOT) grid = std::min<int64_t>(grid, a.red.max_blocks);
     kern<<<(unsigned)grid, (a.cfg.nwarps + 1) * 32, a.cfg.smem_bytes, st>>>(p);
     return 1;
@@ -543,14 +556,32 @@ __global__ void __launch_bounds__(256) interface_kernel(const LevelView L, const
         double* B = x + (pe >> ws) * (int64_t)nf * W + (pe & (W - 1));
         const uint16_t* ta = tab + f * npc;
         const uint16_t* tb = tab + pf * npc;
-        for (int k = ks; k < npc; k += nk) {
-            const int64_t oa = (int64_t)__ldg(ta + k) * W, ob = (int64_t)__ldg(tb + k) * W;
+        // four nodes per step: all eight loads are in flight before the first store (the kernel is bound by
+        // memory latency, not by bytes)
+        constexpr int U = 4;
+        for (int k0 = ks; k0 < npc; k0 += nk * U) {
+            int64_t oa[U], ob[U];
+            double va[U], vb[U];
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int k = min(k0 + q * nk, npc - 1);
+                oa[q] = (int64_t)__ldg(ta + k) * W;
+                ob[q] = (int64_t)__ldg(tb + k) * W;
+            }
             if (OP == 0) {
-                const double s = A[oa] + B[ob];
-                A[oa] = s;
-                B[ob] = s;
-            } else {
-                B[ob] = 0.0;
+#pragma unroll
+                for (int q = 0; q < U; ++q) { va[q] = A[oa[q]]; vb[q] = B[ob[q]]; }
+            }
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                if (k0 + q * nk >= npc) break;
+                if (OP == 0) {
+                    const double sum = va[q] + vb[q];
+                    A[oa[q]] = sum;
+                    B[ob[q]] = sum;
+                } else {
+                    B[ob[q]] = 0.0;
+                }
             }
         }
         return;
