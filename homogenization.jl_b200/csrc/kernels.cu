@@ -167,24 +167,27 @@ template <int DIM, int MODE, bool DOT> struct OutDev {
         if (CLS == 8) return mw[3];
         return (double)(unsigned)((CLS < 8 ? (ml >> (8 * (CLS & 7))) : (mh >> (8 * (CLS & 7)))) & 255ull);
     }
-    // b / y of the next two nodes travel in registers (they come from L2, where the producer's bulk
-    // prefetch put them): the load of node k + 2 is issued before node k is finished
-    double tq0, tq1;
+    // b / y of the next TD nodes travel in registers (they come from L2, where the producer's bulk prefetch
+    // put them): the load of node k + TD is issued before node k is finished, which keeps
+    // warps x TD x 256 bytes in flight per SM
+    static constexpr int TD = DIM == 2 ? 4 : 3;
+    double tq[TD];
     int klast;
     __device__ __forceinline__ void begin(int k0, int k1) {
         if (MODE == APPLY_AX) return;
         klast = k1 - 1;
-        tq0 = __ldcs(tl + k0 * APPLY_W);
-        tq1 = __ldcs(tl + min(k0 + 1, klast) * APPLY_W);
+#pragma unroll
+        for (int q = 0; q < TD; ++q) tq[q] = __ldcs(tl + min(k0 + q, klast) * APPLY_W);
     }
     template <int CLS> __device__ __forceinline__ void put(int k, double acc, double x0) {
         const bool fixed = MODE != APPLY_MULADD && ((cm >> CLS) & 1u);
         double v;
         if (MODE == APPLY_AX) v = fixed ? 0.0 : acc;
         else {
-            const double tv = tq0;
-            tq0 = tq1;
-            tq1 = __ldcs(tl + min(k + 2, klast) * APPLY_W);
+            const double tv = tq[0];
+#pragma unroll
+            for (int q = 0; q + 1 < TD; ++q) tq[q] = tq[q + 1];
+            tq[TD - 1] = __ldcs(tl + min(k + TD, klast) * APPLY_W);
             v = MODE == APPLY_RESIDUAL ? (fixed ? 0.0 : tv - acc) : fma(sa, acc, tv);
         }
         yl[k * APPLY_W] = v;
@@ -268,8 +271,9 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
         out.sa = a.sa;
         out.dsum = 0.0;
         out.cm = 0; out.ml = out.mh = 0ull;
-        // the fused-dot variant is short of registers: it re-reads |J| P for the rare special coefficients
-        typename std::conditional<DOT, LaneOpMem<DIM>, LaneOp<DIM>>::type op;
+        // variants short of registers re-read |J| P for the rare special coefficients
+        constexpr bool LEAN = DOT || (DIM == 3 && MODE != APPLY_AX);
+        typename std::conditional<LEAN, LaneOpMem<DIM>, LaneOp<DIM>>::type op;
         const int RL = DIM == 3 ? a.run : 1;     // 3D: consecutive lines of a plane per task
         const int SEGS = a.seg_shift;           // 2D: log2(nodes per task)
         int64_t u = u0, ucur = -1;
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
             if (u != ucur) {
                 ucur = u;
                 const int64_t e = u * APPLY_W + lane;
-                if constexpr (DOT) {
+                if constexpr (LEAN) {
                     op.ecp = a.coef + u * D::CS * APPLY_W + lane;
                     op.stride = APPLY_W;
                     op.lambda = a.lambda;

@@ -22,6 +22,11 @@ def main():
     except Exception:
         pass
     mesh, sigma = hmg.inputs.checkerboard_problem(dim, c)
+    if os.environ.get("HMG_MB_SORT"):      # experiment: elements grouped by their type inside the cell
+        k = 2 if dim == 2 else 6
+        order = np.arange(mesh.nelements).reshape(-1, k).T.reshape(-1)
+        mesh = hmg.Mesh(mesh.nodes, mesh.elements[order])
+        sigma = np.ascontiguousarray(sigma[order])
     g = hmg.ImplicitFineGrid(mesh, levels, sigma, lam=1.0)
     nf = g.nf(levels)
     dofs = nf * mesh.nelements

@@ -1,18 +1,11 @@
 #!/bin/bash
-# development helper: launch-shape sweep (one B200)
+# development helper: per-op timings on three shapes (one B200)
 out=gpurun_out/sweep_r2.log
 : > $out
 run() { echo "## $DIMC $*" >> $out; env "$@" timeout 300 python tools/microbench.py $DIMC 10 >> $out 2>&1; }
 DIMC="3 20 5"
 run HMG_X=0
-run HMG_APPLY_OVERSUB=1
-run HMG_APPLY_OVERSUB=2
-run HMG_APPLY_OVERSUB=4
 DIMC="2 96 8"
 run HMG_X=0
-run HMG_APPLY_OVERSUB=1
-run HMG_APPLY_OVERSUB=4
 DIMC="3 16 6"
 run HMG_X=0
-run HMG_APPLY_OVERSUB=1
-run HMG_APPLY_OVERSUB=4
