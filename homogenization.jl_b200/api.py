@@ -249,6 +249,50 @@ def distribute(implicit, v, u):
     return v
 
 
+# ---- driver functionals on the finest level (src/examples/homogenized_coefficients.jl) -----------
+def _xi(implicit, xi):
+    xi = np.ascontiguousarray(xi, dtype=np.float64)
+    if xi.shape != (implicit.dim,):
+        raise ValueError("xi must have dim entries")
+    return xi
+
+
+def rhs_a_xi_grad_v(b, implicit, xi):
+    """rhs_aξ∇v!(b, ∂ϕ∂xᵢs, implicit, σs, ξ) (:449-474): b[i, e] = dot(∫∇ϕ_i, -|J| J⁻¹(σ_e .* ξ)), un-summed."""
+    xi = _xi(implicit, xi)
+    check(implicit.lib.hmg_rhs_axi_grad(implicit.ctx, xi.ctypes.data_as(C.c_void_p), b.which))
+    return b
+
+
+def integrate_first_term(v0, implicit, nsubset, xi):
+    """integrate_first_term(v₀, ∂ϕ∂xᵢs, implicit, 1:nsubset, ops, σs, ξ) (:592-632)."""
+    xi = _xi(implicit, xi)
+    out = C.c_double()
+    check(implicit.lib.hmg_integrate_first_term(implicit.ctx, v0.which, xi.ctypes.data_as(C.c_void_p), int(nsubset),
+                                                C.byref(out)))
+    return float(out.value)
+
+
+def integrate_terms(vk, vkm1, implicit, nsubset):
+    """integrate_terms(vₖ, vₖ₋₁, implicit, 1:nsubset, ops) (:634-667)."""
+    out = C.c_double()
+    check(implicit.lib.hmg_integrate_terms(implicit.ctx, vk.which, vkm1.which, int(nsubset), C.byref(out)))
+    return float(out.value)
+
+
+def integrate_area(implicit, nsubset):
+    """integrate_area(ops, implicit, 1:nsubset) (:673-689)."""
+    out = C.c_double()
+    check(implicit.lib.hmg_integrate_area(implicit.ctx, int(nsubset), C.byref(out)))
+    return float(out.value)
+
+
+def next_rhs(b, x, implicit):
+    """next_rhs!(b, x, implicit, ops) (:695-713): b = λ |J| M x, local."""
+    check(implicit.lib.hmg_next_rhs(implicit.ctx, b.which, x.which))
+    return b
+
+
 class BaseLevel:
     """BaseLevel(Float64, F, nnodes, interior) (src/multigrid.jl:30-41).  Instead of a CHOLMOD
     factor the library takes the sparse matrix A[interior, interior] itself (scipy CSC), or

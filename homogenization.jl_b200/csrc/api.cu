@@ -111,6 +111,12 @@ struct hmg_ctx {
     std::vector<double*> cut_send;       // per level: packed partial sums, slots of foreign cells stay zero
     double* cut_recv = nullptr;
     uint8_t* node_contrib = nullptr;
+    // driver functionals (finest level)
+    double* dphi = nullptr;              // [nf][dim]
+    double* flux = nullptr;              // [nunits][dim][W]  -|J| J^-1 (sigma .* xi)
+    double* coef_mass1 = nullptr;        // element coefficients of the bare reference mass matrix (P = 0, last = 1)
+    double* coef_massJ = nullptr;        // ... of |J| M (P = 0, last = |J|)
+    int32_t* gidx = nullptr;             // [nunits * W] global element index of a column, -1 for padding
     std::vector<LevelDev> lv;
     TopoView tview{};
     double* elem_coef = nullptr;         // [nunits][CS][W]
@@ -901,29 +907,116 @@ int hmg_vcycles(hmg_ctx* c, int top_level, int steps, int ncycles, double* resno
     HMG_API_END
 }
 
-int hmg_rhs_axi_grad(hmg_ctx*, const double*, int) {
+// ---- driver functionals on the finest level ---------------------------
+namespace {
+void ensure_functional_tables(hmg_ctx* c) {
+    if (c->dphi) return;
+    const int dim = c->dim, cs = dim == 3 ? 8 : 4, nc = dim == 3 ? 7 : 4, W = c->W;
+    c->dphi = c->dupload(c->ref.lv[c->nlevels - 1].dphi);
+    std::vector<double> m1((size_t)c->nunits * cs * W, 0.0), mJ((size_t)c->nunits * cs * W, 0.0);
+    std::vector<int32_t> gi((size_t)c->nunits * W, -1);
+    for (int64_t e = 0; e < c->ne; ++e) {
+        const size_t at = ((size_t)(e / W) * cs + (nc - 1)) * W + e % W;
+        m1[at] = 1.0;
+        mJ[at] = c->elem_coef_host[(size_t)e * cs + nc - 1];
+        gi[e] = (int32_t)c->local_to_global[e];
+    }
+    c->coef_mass1 = c->dupload(m1);
+    c->coef_massJ = c->dupload(mJ);
+    c->gidx = c->dupload(gi);
+    c->flux = c->dalloc<double>((size_t)c->nunits * dim * W);
+}
+void upload_flux(hmg_ctx* c, const double* xi) {
+    const int dim = c->dim, W = c->W;
+    std::vector<double> sl((size_t)c->ne * dim), fl;
+    for (int64_t e = 0; e < c->ne; ++e)
+        for (int d = 0; d < dim; ++d) sl[(size_t)e * dim + d] = c->sigma_global[(size_t)c->local_to_global[e] * dim + d];
+    element_flux_vectors(dim, c->ne, c->nodes.data(), c->elems.data(), sl.data(), xi, fl);
+    std::vector<double> inter((size_t)c->nunits * dim * W, 0.0);
+    for (int64_t e = 0; e < c->ne; ++e)
+        for (int d = 0; d < dim; ++d) inter[((size_t)(e / W) * dim + d) * W + e % W] = fl[(size_t)e * dim + d];
+    CUDA_OK(cudaMemcpyAsync(c->flux, inter.data(), inter.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+}
+// y = (reference mass matrix or |J| * lambda * it) * x, column-local, through the apply kernel
+void mass_apply(hmg_ctx* c, const double* coef, double lambda, const double* x, double* y) {
+    const int l = c->nlevels;
+    LevelDev& L = c->level(l);
+    check_launch(c, launch_fill(y, 0.0, c->nstored(l), c->stream));
+    ApplyArgs a;
+    a.L = L.view; a.cfg = L.cfg; a.nunits = c->nunits; a.tab = L.tab.data();
+    a.coef = coef; a.cmask = c->cmask; a.mult = c->mult;
+    a.x = x; a.y = y; a.b = nullptr;
+    a.alpha = 1.0; a.lambda = lambda; a.mode = APPLY_MULADD; a.dot_post = -1; a.red = c->red;
+    const int n = launch_apply(c->dim, a, c->stream);
+    HMG_CHECK(n >= 0, "apply kernel refused the launch configuration");
+    check_launch(c, n);
+}
+double integrate(hmg_ctx* c, const double* v, const double* v2, const double* flux, int64_t nsubset) {
+    const int l = c->nlevels;
+    HMG_CHECK(nsubset >= 0 && nsubset <= c->ne_global, "element subset out of range");
+    double* Mv = c->vecp(l, HMG_W);
+    HMG_CHECK(v != Mv && v2 != Mv, "the work vector w cannot be an argument of an integral");
+    mass_apply(c, c->coef_mass1, 1.0, v, Mv);
+    check_launch(c, launch_integrate(c->dim, c->red, c->level(l).view, c->nunits, nsubset, c->gidx, c->elem_coef, c->dphi,
+                                     flux, v, v2, Mv, c->stream));
+    finish_reduction(c, POST_STORE, S_TMP);
+    return read_scalar(c, S_TMP);
+}
+}  // namespace
+
+int hmg_rhs_axi_grad(hmg_ctx* c, const double* xi, int which_b) {
     HMG_API_BEGIN
-    throw Error("hmg: hmg_rhs_axi_grad is not implemented yet");
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    HMG_CHECK(xi != nullptr, "null xi");
+    ensure_functional_tables(c);
+    upload_flux(c, xi);
+    const int l = c->nlevels;
+    check_launch(c, launch_rhs_flux(c->dim, c->level(l).view, c->nunits, c->dphi, c->flux, c->vecp(l, which_b), c->stream));
     HMG_API_END
 }
-int hmg_integrate_first_term(hmg_ctx*, int, const double*, int64_t, double*) {
+int hmg_integrate_first_term(hmg_ctx* c, int which_v, const double* xi, int64_t nsubset, double* out) {
     HMG_API_BEGIN
-    throw Error("hmg: hmg_integrate_first_term is not implemented yet");
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    HMG_CHECK(xi != nullptr && out != nullptr, "null argument");
+    ensure_functional_tables(c);
+    upload_flux(c, xi);
+    *out = integrate(c, c->vecp(c->nlevels, which_v), nullptr, c->flux, nsubset);
     HMG_API_END
 }
-int hmg_integrate_terms(hmg_ctx*, int, int, int64_t, double*) {
+int hmg_integrate_terms(hmg_ctx* c, int which_vk, int which_vkm1, int64_t nsubset, double* out) {
     HMG_API_BEGIN
-    throw Error("hmg: hmg_integrate_terms is not implemented yet");
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    HMG_CHECK(out != nullptr, "null argument");
+    ensure_functional_tables(c);
+    *out = integrate(c, c->vecp(c->nlevels, which_vk), c->vecp(c->nlevels, which_vkm1), nullptr, nsubset);
     HMG_API_END
 }
-int hmg_integrate_area(hmg_ctx*, int64_t, double*) {
+int hmg_integrate_area(hmg_ctx* c, int64_t nsubset, double* out) {
     HMG_API_BEGIN
-    throw Error("hmg: hmg_integrate_area is not implemented yet");
+    NEED_CTX(c);
+    HMG_CHECK(out != nullptr, "null argument");
+    HMG_CHECK(nsubset >= 0 && nsubset <= c->ne_global, "element subset out of range");
+    // 1' M 1 under the selected base cells: sum(mass) * |J_e|, summed in element order like the reference
+    const int dim = c->dim, cs = dim == 3 ? 8 : 4, nc = dim == 3 ? 7 : 4;
+    std::vector<double> coef;
+    element_coefficients(dim, nsubset, c->nodes.data(), c->elems_global.data(), c->sigma_global.data(), coef, cs);
+    const double mtot = c->ref.lv[c->nlevels - 1].mass_total;
+    double area = 0.0;
+    for (int64_t e = 0; e < nsubset; ++e) area += mtot * coef[(size_t)e * cs + nc - 1];
+    *out = area;
     HMG_API_END
 }
-int hmg_next_rhs(hmg_ctx*, int, int) {
+int hmg_next_rhs(hmg_ctx* c, int which_b, int which_x) {
     HMG_API_BEGIN
-    throw Error("hmg: hmg_next_rhs is not implemented yet");
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    HMG_CHECK(which_b != which_x, "next_rhs!: b and x must be different vectors");
+    ensure_functional_tables(c);
+    mass_apply(c, c->coef_massJ, c->lambda, c->vecp(c->nlevels, which_x), c->vecp(c->nlevels, which_b));
     HMG_API_END
 }
 

@@ -58,6 +58,7 @@ struct RefLevel {
     // the tables the apply kernel is launched with (StencilTab of apply_core.cuh): interior rows
     // [npair][nc], diagonal of every class [ncls][nc], reference-edge segment of 2-face classes [ncls][nc]
     std::vector<double> gi, gc, ge;
+    std::vector<double> dphi;        // [nf][dim] int d phi_p / d x_j over the refined reference element (lattice order)
     std::vector<uint16_t> face_bary; // 3D: interior nodes of a face, barycentric a | b<<8
     // packed index of the t-th paired node of every local cell: faces [4][npf] (3D), then edges
     // [6|3][npe], then vertices [4|3]
@@ -137,6 +138,10 @@ int class_of_vertex(int dim, int lv);
 
 // per element geometry: coef[e][c] = |J| * P_c (c < nc-1), coef[e][nc-1] = |J| with
 // P = J^-1 diag(sigma) J^-T (src/apply_local_operators.jl:101-105, src/cell_values.jl:104-127)
+// flux[e][k] = -|J| (J^-1 (sigma_e .* xi))_k : the vector P of rhs_a_xi_grad_v! / integrate_first_term
+// (src/examples/homogenized_coefficients.jl:468, 612)
+void element_flux_vectors(int dim, int64_t ne, const double* nodes, const int64_t* elems, const double* sigma,
+                          const double* xi, std::vector<double>& flux /*ne x dim*/);
 void element_coefficients(int dim, int64_t ne, const double* nodes /*dim x nn*/,
                           const int64_t* elems /*0-based*/, const double* sigma /*dim x ne*/,
                           std::vector<double>& coef /*ne x stride*/, int stride);

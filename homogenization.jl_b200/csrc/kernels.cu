@@ -899,6 +899,73 @@ int launch_fill_columns(const LevelView& L, int64_t ne, double* x, double v, cud
 }
 
 // ------------------------------------------------------------------------------------------
+// driver functionals on the finest level (src/examples/homogenized_coefficients.jl:449-474, 592-667)
+// ------------------------------------------------------------------------------------------
+// b[p, e] = dot(dphi[p], flux_e): rhs_a_xi_grad_v! (un-summed, local)
+template <int DIM>
+__global__ void __launch_bounds__(256) rhs_flux_kernel(const LevelView L, int64_t nunits, const double* __restrict__ dphi,
+                                                       const double* __restrict__ flux, double* __restrict__ b) {
+    const int W = L.W, ws = L.wshift;
+    const int l = threadIdx.x & (W - 1);
+    const int64_t rows = nunits * L.nf;
+    const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> ws;
+    for (int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> ws; it < rows; it += stride) {
+        const int64_t u = it / L.nf;
+        const int p = (int)(it - u * L.nf);
+        double s = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) s = fma(__ldg(dphi + p * DIM + d), __ldg(flux + (u * DIM + d) * W + l), s);
+        b[it * W + l] = s;
+    }
+}
+int launch_rhs_flux(int dim, const LevelView& L, int64_t nunits, const double* dphi, const double* flux, double* b, cudaStream_t st) {
+    if (nunits == 0) return 0;
+    const unsigned grid = grid_for(nunits * L.nf * L.W, 256, 148 * 32);
+    if (dim == 3) rhs_flux_kernel<3><<<grid, 256, 0, st>>>(L, nunits, dphi, flux, b);
+    else rhs_flux_kernel<2><<<grid, 256, 0, st>>>(L, nunits, dphi, flux, b);
+    return 1;
+}
+// sum_e w_e sum_p (v[p,e] + v2[p,e]) * (dot(dphi[p], flux_e) + Mv[p,e]),  w_e = |J_e| if the element's global index
+// is below nsubset else 0; v2 / flux may be null.  integrate_first_term / integrate_terms.
+template <int DIM>
+__global__ void __launch_bounds__(256) integrate_kernel(const Reducer R, const LevelView L, int64_t nunits, int64_t nsubset,
+                                                        const int32_t* __restrict__ gidx, const double* __restrict__ coef,
+                                                        const double* __restrict__ dphi, const double* __restrict__ flux,
+                                                        const double* __restrict__ v, const double* __restrict__ v2,
+                                                        const double* __restrict__ Mv) {
+    using D = Dims<DIM>;
+    const int W = L.W, ws = L.wshift;
+    const int l = threadIdx.x & (W - 1);
+    const int64_t rows = nunits * L.nf;
+    const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> ws;
+    double acc = 0.0;
+    for (int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> ws; it < rows; it += stride) {
+        const int64_t u = it / L.nf;
+        const int p = (int)(it - u * L.nf);
+        const int32_t gi = __ldg(gidx + u * W + l);
+        if (gi < 0 || gi >= nsubset) continue;
+        const double w = __ldg(coef + (u * D::CS + D::NC - 1) * W + l);
+        double t = Mv[it * W + l];
+        if (flux) {
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) t = fma(__ldg(dphi + p * DIM + d), __ldg(flux + (u * DIM + d) * W + l), t);
+        }
+        double a = v[it * W + l];
+        if (v2) a += v2[it * W + l];
+        acc = fma(w * a, t, acc);
+    }
+    block_reduce_finish(acc, R, POST_STORE, S_TMP);
+}
+int launch_integrate(int dim, const Reducer& R, const LevelView& L, int64_t nunits, int64_t nsubset, const int32_t* gidx,
+                     const double* coef, const double* dphi, const double* flux, const double* v, const double* v2,
+                     const double* Mv, cudaStream_t st) {
+    const unsigned grid = grid_for(std::max<int64_t>(1, nunits * L.nf * L.W), 256, R.max_blocks);
+    if (dim == 3) integrate_kernel<3><<<grid, 256, 0, st>>>(R, L, nunits, nsubset, gidx, coef, dphi, flux, v, v2, Mv);
+    else integrate_kernel<2><<<grid, 256, 0, st>>>(R, L, nunits, nsubset, gidx, coef, dphi, flux, v, v2, Mv);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------
 // host layout (hierarchical rows, unpadded columns) <-> device layout (lattice rows, interleaved)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) permute_in_kernel(const LevelView L, const int32_t* __restrict__ h2l,

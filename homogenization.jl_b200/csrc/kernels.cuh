@@ -100,6 +100,10 @@ int launch_cut(int dim, int op, int kind, const LevelView& L, const CutView& C, 
 int launch_scalar_post(const Reducer& R, int post, int slot, cudaStream_t st);
 int launch_masked_copy_to_base(const LevelView& L1, int64_t nn, const int32_t* node_first, const uint8_t* contrib, const double* v,
                                double* u, cudaStream_t st);
+int launch_rhs_flux(int dim, const LevelView& L, int64_t nunits, const double* dphi, const double* flux, double* b, cudaStream_t st);
+int launch_integrate(int dim, const Reducer& R, const LevelView& L, int64_t nunits, int64_t nsubset, const int32_t* gidx,
+                     const double* coef, const double* dphi, const double* flux, const double* v, const double* v2,
+                     const double* Mv, cudaStream_t st);
 int launch_apply_constraint(int dim, const LevelView& L, int64_t nbelems, const int32_t* belems, const uint16_t* cmask,
                             double* x, cudaStream_t st);
 int launch_restrict(int dim, const LevelView& Lf, const LevelView& Lc, int64_t nunits, const double* rf, double* bc, cudaStream_t st);

@@ -149,9 +149,10 @@ void lattice_gradients(int dim, const I3* v, int g[4][3]) {
 
 // integer stencil of a refined reference mesh: acc[p][dir][c] (stiffness components, then mass)
 template <class Lat, class Pack>
-std::vector<int> integer_stencil(int dim, const IntMesh& mesh, int nf, Lat lat, Pack pack) {
+std::vector<int> integer_stencil(int dim, const IntMesh& mesh, int nf, Lat lat, Pack pack, std::vector<int>* gradsum = nullptr) {
     const int nv = dim + 1, ndir = dim == 3 ? NDIR3 : NDIR2, nc = dim == 3 ? NC3 : NC2;
     std::vector<int> acc((size_t)nf * ndir * nc, 0);
+    if (gradsum) gradsum->assign((size_t)nf * dim, 0);
     for (const auto& el : mesh.elems) {
         I3 v[4];
         for (int a = 0; a < nv; ++a) v[a] = lat(el[a]);
@@ -159,6 +160,8 @@ std::vector<int> integer_stencil(int dim, const IntMesh& mesh, int nf, Lat lat, 
         lattice_gradients(dim, v, g);
         for (int a = 0; a < nv; ++a) {
             int pa = pack(v[a]);
+            if (gradsum)
+                for (int k = 0; k < dim; ++k) (*gradsum)[(size_t)pa * dim + k] += g[a][k];
             for (int b = 0; b < nv; ++b) {
                 int d = dir_index(dim, v[b][0] - v[a][0], v[b][1] - v[a][1], v[b][2] - v[a][2]);
                 HMG_CHECK(d >= 0, "fine-element edge is not one of the stencil directions");
@@ -268,7 +271,19 @@ RefElement build_reference(int dim, int nlevels) {
 
         // (2) integer stencil: acc[p][dir][c]
         const int ndir = ref.ndir, nc = ref.nc;
-        const std::vector<int> acc = integer_stencil(dim, mesh, L.nf, lat, pack);
+        std::vector<int> gradsum;
+        const std::vector<int> acc = integer_stencil(dim, mesh, L.nf, lat, pack, &gradsum);
+        // int d phi_i / d x_j over the refined reference element (partial_derivatives_functionals,
+        // src/examples/homogenized_coefficients.jl:407-442): fine elements have volume 1/(d! m^d) and
+        // gradient m * (lattice gradient); zero at interior nodes
+        {
+            const double sg = 1.0 / ((dim == 3 ? 6.0 : 2.0) * std::pow((double)m, dim - 1));
+            L.dphi.resize((size_t)L.nf * dim);
+            for (size_t q = 0; q < L.dphi.size(); ++q) L.dphi[q] = gradsum[q] * sg;
+            for (int p = 0; p < L.nf; ++p)
+                if ((L.nodeinfo[p] >> 24) == 0)
+                    for (int k = 0; k < dim; ++k) HMG_CHECK(gradsum[(size_t)p * dim + k] == 0, "gradient functional of an interior node is not zero");
+        }
         // class invariance + table
         double fact = dim == 3 ? 6.0 : 2.0;
         double s_stiff = dim == 3 ? 1.0 / (fact * m) : 1.0 / fact;

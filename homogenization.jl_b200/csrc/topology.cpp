@@ -255,6 +255,36 @@ Partition build_partition(const Topology& T, const int32_t* owner_rank, int rank
     return P;
 }
 
+void element_flux_vectors(int dim, int64_t ne, const double* nodes, const int64_t* elems, const double* sigma,
+                          const double* xi, std::vector<double>& flux) {
+    const int nv = dim + 1;
+    flux.assign((size_t)ne * dim, 0.0);
+    for (int64_t e = 0; e < ne; ++e) {
+        const int64_t* el = elems + e * nv;
+        double J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        for (int c = 0; c < dim; ++c)
+            for (int r = 0; r < dim; ++r) J[r][c] = nodes[el[c + 1] * dim + r] - nodes[el[0] * dim + r];
+        double s[3] = {0, 0, 0}, y[3] = {0, 0, 0}, det;
+        for (int d = 0; d < dim; ++d) s[d] = sigma[e * dim + d] * xi[d];
+        // y = J^-1 s by Cramer's rule (adjugate / det)
+        if (dim == 2) {
+            det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+            y[0] = (J[1][1] * s[0] - J[0][1] * s[1]) / det;
+            y[1] = (-J[1][0] * s[0] + J[0][0] * s[1]) / det;
+        } else {
+            const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
+                         c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+            det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+            const double a[3][3] = {{c00, J[0][2] * J[2][1] - J[0][1] * J[2][2], J[0][1] * J[1][2] - J[0][2] * J[1][1]},
+                                    {c01, J[0][0] * J[2][2] - J[0][2] * J[2][0], J[0][2] * J[1][0] - J[0][0] * J[1][2]},
+                                    {c02, J[0][1] * J[2][0] - J[0][0] * J[2][1], J[0][0] * J[1][1] - J[0][1] * J[1][0]}};
+            for (int k = 0; k < 3; ++k) y[k] = (a[k][0] * s[0] + a[k][1] * s[1] + a[k][2] * s[2]) / det;
+        }
+        HMG_CHECK(det != 0.0 && std::isfinite(det), "degenerate base element");
+        for (int k = 0; k < dim; ++k) flux[(size_t)e * dim + k] = -std::fabs(det) * y[k];
+    }
+}
+
 void element_coefficients(int dim, int64_t ne, const double* nodes, const int64_t* elems,
                           const double* sigma, std::vector<double>& coef, int stride) {
     const int nv = dim + 1;
