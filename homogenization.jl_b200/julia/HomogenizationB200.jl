@@ -18,7 +18,7 @@ using Homogenization: Mesh, ImplicitFineGrid, LevelState, BaseLevel, L2PlusDivAG
                       ZeroDirichletConstraint, nelements, nnodes, refined_mesh, nlevels
 import Homogenization: broadcast_interfaces!, apply_constraint!, zero_out_all_but_one!,
                        local_residual!, restrict_to!, interpolate_and_sum_to!, smoothing_steps!,
-                       vcycle!
+                       vcycle!, rhs_aξ∇v!, integrate_first_term, integrate_terms, integrate_area, next_rhs!
 import LinearAlgebra: mul!
 using SparseArrays: SparseMatrixCSC
 using StaticArrays: SVector
@@ -44,6 +44,7 @@ LevelStates, resident on one GPU (hmg_create).  Freed by a finalizer (hmg_destro
 mutable struct DeviceGrid
     ctx::Ptr{Cvoid}
     implicit::ImplicitFineGrid
+    DeviceGrid(ctx::Ptr{Cvoid}, implicit::ImplicitFineGrid) = new(ctx, implicit)
     function DeviceGrid(implicit::ImplicitFineGrid{dim}, σs::Vector{SVector{dim,Float64}}, λ::Float64; device::Integer = 0) where {dim}
         base = implicit.base
         ctx = Ref{Ptr{Cvoid}}(C_NULL)
@@ -168,6 +169,83 @@ function vcycle!(implicit::ImplicitFineGrid, base::DeviceBaseLevel, ops::Vector{
     check(ccall((:hmg_set_lambda, libhmg), Cint, (Ptr{Cvoid}, Float64), base.grid.ctx, ops[k].λ))
     check(ccall((:hmg_vcycle, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}), base.grid.ctx, k, steps, C_NULL))
     nothing
+end
+
+# ---- the callers around the V-cycle (src/examples/homogenized_coefficients.jl), on the device ----
+# The element subsets of the driver are prefixes 1:n of the magnitude-ordered base mesh (:272).
+
+# rhs_aξ∇v!(b, ∂ϕ∂xᵢs, implicit, σs, ξ)   (:449-474)
+function rhs_aξ∇v!(b::DeviceMatrix, ∂ϕ∂xᵢs::Vector{SVector{dim,Float64}}, implicit::ImplicitFineGrid{dim},
+                   σs::Vector{SVector{dim,Float64}}, ξ::SVector{dim,Float64}) where {dim}
+    xi = collect(ξ)
+    GC.@preserve xi check(ccall((:hmg_rhs_axi_grad, libhmg), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), b.grid.ctx, xi, b.which))
+    nothing
+end
+
+# integrate_first_term(v₀, ∂ϕ∂xᵢs, implicit, subset, ops, σs, ξ)   (:592-632)
+function integrate_first_term(v₀::DeviceMatrix, ∂ϕ∂xᵢs::Vector{SVector{dim,Float64}}, implicit::ImplicitFineGrid{dim},
+                              subset::Base.OneTo, ops::L2PlusDivAGrad, σs::Vector{SVector{dim,Float64}},
+                              ξ::SVector{dim,Float64}) where {dim}
+    xi = collect(ξ)
+    out = Ref{Float64}(0.0)
+    GC.@preserve xi check(ccall((:hmg_integrate_first_term, libhmg), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Ref{Float64}),
+                                v₀.grid.ctx, v₀.which, xi, length(subset), out))
+    out[]
+end
+
+# integrate_terms(vₖ, vₖ₋₁, implicit, subset, ops)   (:634-667)
+function integrate_terms(vₖ::DeviceMatrix, vₖ₋₁::DeviceMatrix, implicit::ImplicitFineGrid, subset::Base.OneTo, ops::L2PlusDivAGrad)
+    out = Ref{Float64}(0.0)
+    check(ccall((:hmg_integrate_terms, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Ref{Float64}),
+                vₖ.grid.ctx, vₖ.which, vₖ₋₁.which, length(subset), out))
+    out[]
+end
+
+# integrate_area(ops, implicit, subset)   (:673-689) -- needs the grid, so it dispatches on a DeviceGrid
+function integrate_area(g::DeviceGrid, subset::Base.OneTo)
+    out = Ref{Float64}(0.0)
+    check(ccall((:hmg_integrate_area, libhmg), Cint, (Ptr{Cvoid}, Int64, Ref{Float64}), g.ctx, length(subset), out))
+    out[]
+end
+
+# next_rhs!(b, x, implicit, ops)   (:695-713)
+function next_rhs!(b::DeviceMatrix, x::DeviceMatrix, implicit::ImplicitFineGrid, ops::L2PlusDivAGrad)
+    check(ccall((:hmg_set_lambda, libhmg), Cint, (Ptr{Cvoid}, Float64), b.grid.ctx, ops.λ))
+    check(ccall((:hmg_next_rhs, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint), b.grid.ctx, b.which, x.which))
+    nothing
+end
+
+"""
+    PartitionedDeviceGrid(implicit, σs, λ, owner_rank, rank, nranks, nccl_id; device)
+
+One process per GPU (e.g. under MPI.jl): `owner_rank[e]` assigns every coarse element to a rank, `nccl_id` is the
+128-byte id produced by `nccl_unique_id()` on rank 0 and broadcast by the launcher.  The state matrices of the
+returned grid hold this rank's columns only (`local_elements(grid)`); only interface partial sums and scalars move.
+"""
+function PartitionedDeviceGrid(implicit::ImplicitFineGrid{dim}, σs::Vector{SVector{dim,Float64}}, λ::Float64,
+                               owner_rank::Vector{Int32}, rank::Integer, nranks::Integer, nccl_id::Vector{UInt8};
+                               device::Integer = rank) where {dim}
+    base = implicit.base
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    nodes = reinterpret(Float64, base.nodes); elems = reinterpret(Int64, base.elements); sig = reinterpret(Float64, σs)
+    GC.@preserve nodes elems sig owner_rank nccl_id begin
+        check(ccall((:hmg_create_partitioned, libhmg), Cint,
+            (Cint, Cint, Int64, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Float64, Cint, Cint, Cint, Ptr{Int32}, Ptr{UInt8}, Ref{Ptr{Cvoid}}),
+            dim, nlevels(implicit), nelements(base), nnodes(base), nodes, elems, sig, λ, device, rank, nranks, owner_rank, nccl_id, ctx))
+    end
+    g = DeviceGrid(ctx[], implicit)
+    finalizer(x -> (x.ctx == C_NULL || ccall((:hmg_destroy, libhmg), Cint, (Ptr{Cvoid},), x.ctx); x.ctx = C_NULL), g)
+    g
+end
+function nccl_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:hmg_nccl_unique_id, libhmg), Cint, (Ptr{UInt8},), id))
+    id
+end
+function local_elements(g::DeviceGrid)
+    out = Vector{Int64}(undef, ccall((:hmg_ne_local, libhmg), Int64, (Ptr{Cvoid},), g.ctx))
+    check(ccall((:hmg_local_elements, libhmg), Cint, (Ptr{Cvoid}, Ptr{Int64}), g.ctx, out))
+    out
 end
 
 end # module
