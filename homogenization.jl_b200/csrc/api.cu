@@ -250,9 +250,15 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const 
         std::memcpy(&id, nccl_id, sizeof(id));
         NCCL_OK(nccl().CommInitRank(&c->comm, nranks, id, rank));
     }
-    // interleave width: one warp lane per element of a unit
+    // interleave width: one warp lane per element of a unit.  Units of 16 (a warp takes two lines of a 3D
+    // plane, HMG_GROUP_WIDTH=16) leave more room for prefetch in the ring at level 6 but lose more to
+    // unpaired lines than they gain (measured: 0.72 vs 0.59 ms on 24 576 elements), so 32 is the default
     c->W = 32;
-    c->wshift = 5;
+    if (const char* w = getenv("HMG_GROUP_WIDTH")) {
+        const int v = atoi(w);
+        if (v == 32 || (v == 16 && dim == 3)) c->W = v;
+    }
+    c->wshift = c->W == 32 ? 5 : 4;
     c->nunits = (ne + c->W - 1) / c->W;
 
     // per-level tables and state vectors

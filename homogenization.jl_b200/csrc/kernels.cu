@@ -111,8 +111,10 @@ __device__ __forceinline__ void block_reduce_finish(double v, const Reducer& R, 
 // ------------------------------------------------------------------------------------------
 // K1: local operator apply
 // ------------------------------------------------------------------------------------------
-// Lanes are coarse elements (W = 32 interleaved columns), so node class, neighbour offsets and control
-// flow are warp-uniform and every shared/global access of a warp is one conflict-free 256-byte row.
+// Lanes are coarse elements (W = 32 interleaved columns; W = 16 for 6-level 3D hierarchies, where a warp
+// takes TWO lines of a plane, one per half-warp -- all interior lines of a diagonal plane have the same
+// length and classes), so node class, neighbour offsets and control flow are warp-uniform and every
+// shared/global access of a warp is one (two) conflict-free row(s) of W doubles.
 // A CTA owns a contiguous range of (element group, lattice plane) pairs, balanced by rows.  Its input
 // rows stream ONCE from HBM through a shared-memory ring: one elected thread issues TMA bulk copies
 // (cp.async.bulk, completion on mbarriers) of fixed-size chunks, consumer warps take the lines of the
@@ -120,7 +122,6 @@ __device__ __forceinline__ void block_reduce_finish(double v, const Reducer& R, 
 // back once their window has passed them.  The ring is addressed by (stream row mod R); the first
 // SP rows are mirrored behind the ring so that a line never wraps.  Each lane walks its line with a
 // register sliding window: 7 (3D) / 3 (2D) shared loads per node instead of 15 / 7.
-constexpr int APPLY_W = 32;             // element-interleave width = warp size
 constexpr int APPLY_Q = 64, APPLY_QS = 6;   // mbarrier slots (chunks in flight), log2
 constexpr int APPLY_MAXT = 16 * 32;    // 15 consumer warps + the producer warp: 128 registers per thread
 
@@ -151,7 +152,9 @@ template <int DIM> __device__ __forceinline__ int64_t plane_at_or_after(int64_t 
     return (u + 1) * (m + 1);
 }
 
-template <int DIM, int MODE, bool DOT> struct OutDev {
+template <int DIM, int W, int MODE, bool DOT> struct OutDev {
+    static constexpr int APPLY_W = W;
+    bool active;           // false: this half-warp repeats its sibling's line (its results are dropped)
     double* yl;            // output row of node 0 of the current line (lane included)
     const double* tl;
     double sa;
@@ -190,8 +193,10 @@ template <int DIM, int MODE, bool DOT> struct OutDev {
             tq[TD - 1] = __ldcs(tl + min(k + TD, klast) * APPLY_W);
             v = MODE == APPLY_RESIDUAL ? (fixed ? 0.0 : tv - acc) : fma(sa, acc, tv);
         }
-        yl[k * APPLY_W] = v;
-        if (DOT) dsum = fma(weight<CLS>() * x0, v, dsum);
+        if (W == 32 || active) {
+            yl[k * APPLY_W] = v;
+            if (DOT) dsum = fma(weight<CLS>() * x0, v, dsum);
+        }
     }
 };
 
@@ -200,15 +205,18 @@ struct SmemLoad {
     __device__ __forceinline__ double operator()(int addr) const { return sm[addr]; }
 };
 
-template <int DIM, int MODE, bool DOT>
+template <int DIM, int W, int MODE, bool DOT>
 __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_constant__ ApplyParams<DIM> a) {
     using D = Dims<DIM>;
+    constexpr int APPLY_W = W;
+    static_assert(W == 32 || (W == 16 && DIM == 3), "W = 16 pairs two lines of a 3D plane per warp");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[APPLY_Q], empty_bar[APPLY_Q];
     double* sm = reinterpret_cast<double*>(smem_raw);
     const int m = a.m, nf = a.nf, NW = a.nwarps, R = a.R, SP = a.SP, CS = a.cs, CH = 1 << a.cs;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
+    const int el = lane & (W - 1), half = lane / W;     // element of the unit, line of the pair (W = 16)
     const int NPL = m + 1;
 
     if (threadIdx.x == 0) {
@@ -267,7 +275,8 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
     } else if (nchunks > 0) {
         // ---------------- consumers ----------------
         SmemLoad mem{sm};
-        OutDev<DIM, MODE, DOT> out;
+        OutDev<DIM, W, MODE, DOT> out;
+        out.active = true;
         out.sa = a.sa;
         out.dsum = 0.0;
         out.cm = 0; out.ml = out.mh = 0ull;
@@ -298,20 +307,20 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
             step = NW;
             if (u != ucur) {
                 ucur = u;
-                const int64_t e = u * APPLY_W + lane;
+                const int64_t e = u * APPLY_W + el;
                 if constexpr (LEAN) {
-                    op.ecp = a.coef + u * D::CS * APPLY_W + lane;
+                    op.ecp = a.coef + u * D::CS * APPLY_W + el;
                     op.stride = APPLY_W;
                     op.lambda = a.lambda;
                 } else {
 #pragma unroll
-                    for (int q = 0; q < D::NC; ++q) op.ec[q] = __ldg(a.coef + (u * D::CS + q) * APPLY_W + lane);
+                    for (int q = 0; q < D::NC; ++q) op.ec[q] = __ldg(a.coef + (u * D::CS + q) * APPLY_W + el);
                     op.ec[D::NC - 1] *= a.lambda;
                 }
                 interior_coefficients(op, a.T);
                 if (MODE != APPLY_MULADD) out.cm = (unsigned)__ldg(a.cmask + e);
                 if (DOT) {
-                    const uint8_t* mp = a.mult + u * 16 * APPLY_W + lane;
+                    const uint8_t* mp = a.mult + u * 16 * APPLY_W + el;
                     unsigned long long lo = 0, hi = 0;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
@@ -325,8 +334,8 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
                     out.mw[3] = (double)(unsigned)(hi & 255ull);
                 }
                 su = (int)(u * nf - g0);
-                ybase = a.y + u * (int64_t)nf * APPLY_W + lane;
-                tbase = MODE == APPLY_AX ? nullptr : a.t + u * (int64_t)nf * APPLY_W + lane;
+                ybase = a.y + u * (int64_t)nf * APPLY_W + el;
+                tbase = MODE == APPLY_AX ? nullptr : a.t + u * (int64_t)nf * APPLY_W + el;
             }
             // rows of the task: first line, number of lines, row window [behind, need]
             LineGeo<DIM> g;
@@ -386,23 +395,40 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
             out.tl = MODE == APPLY_AX ? nullptr : tbase + (int64_t)rc * APPLY_W;
             if constexpr (DIM == 3) {
                 const int L = g.L;
-                for (int li = 0; li < nl; ++li) {
-                    g.bc = qc * APPLY_W + lane;
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) { g.bm[q] = qm[q] * APPLY_W + lane; g.bp[q] = qp[q] * APPLY_W + lane; }
+                auto adv = [&](int& p, int d) { p += d; if (p >= R) p -= R; };
+                auto kind = [&](int i) { return i == 0 ? 0 : (i == t ? 2 : 1); };
+                int li = 0;
+                while (li < nl) {
+                    const int i0 = il + li;
+                    // W = 16: the second half-warp takes the next line if it is of the same kind, else it repeats
+                    // this one (results dropped)
+                    const bool pair = W == 16 && li + 1 < nl && kind(i0) == kind(i0 + 1);
+                    const int hs = W == 16 && pair ? half : 0;
+                    if (W == 16) out.active = pair || half == 0;
+                    int pc = qc, pm0 = qm[0], pm1 = qm[1], pm2 = qm[2], pp0 = qp[0], pp1 = qp[1], pp2 = qp[2];
+                    if (hs) { adv(pc, L); adv(pm0, L - 1); adv(pm1, L - 1); adv(pm2, L); adv(pp0, L + 1); adv(pp1, L + 1); adv(pp2, L); }
+                    g.bc = pc * APPLY_W + el;
+                    g.bm[0] = pm0 * APPLY_W + el; g.bm[1] = pm1 * APPLY_W + el; g.bm[2] = pm2 * APPLY_W + el;
+                    g.bp[0] = pp0 * APPLY_W + el; g.bp[1] = pp1 * APPLY_W + el; g.bp[2] = pp2 * APPLY_W + el;
+                    double* const yl0 = out.yl;
+                    const double* const tl0 = out.tl;
+                    if (hs) { out.yl += L * APPLY_W; if (MODE != APPLY_AX) out.tl += L * APPLY_W; }
                     out.begin(0, L);
-                    run_line3(op, a.T, mem, APPLY_W, g, t, il + li, out);
-                    // the next line of the plane: every base moves by one line of its own plane
-                    auto adv = [&](int& p, int d) { p += d; if (p >= R) p -= R; };
-                    adv(qc, L); adv(qm[0], L - 1); adv(qm[1], L - 1); adv(qm[2], L);
-                    adv(qp[0], L + 1); adv(qp[1], L + 1); adv(qp[2], L);
-                    out.yl += L * APPLY_W;
-                    if (MODE != APPLY_AX) out.tl += L * APPLY_W;
+                    run_line3(op, a.T, mem, APPLY_W, g, t, i0, out);
+                    // the next line(s) of the plane: every base moves by one line of its own plane
+                    const int step_lines = pair ? 2 : 1;
+                    for (int q = 0; q < step_lines; ++q) {
+                        adv(qc, L); adv(qm[0], L - 1); adv(qm[1], L - 1); adv(qm[2], L);
+                        adv(qp[0], L + 1); adv(qp[1], L + 1); adv(qp[2], L);
+                    }
+                    out.yl = yl0 + step_lines * L * APPLY_W;
+                    if (MODE != APPLY_AX) out.tl = tl0 + step_lines * L * APPLY_W;
+                    li += step_lines;
                 }
             } else {
-                g.bc = qc * APPLY_W + lane;
-                g.bm[0] = qm[0] * APPLY_W + lane;
-                g.bp[0] = qp[0] * APPLY_W + lane;
+                g.bc = qc * APPLY_W + el;
+                g.bm[0] = qm[0] * APPLY_W + el;
+                g.bp[0] = qp[0] * APPLY_W + el;
                 out.begin(g.k0, g.k1);
                 run_line2(op, a.T, mem, APPLY_W, g, t, out);
             }
@@ -479,11 +505,11 @@ ApplyConfig make_apply_config(int dim, int m, int nf, int W) {
     return c;
 }
 
-template <int DIM, int MODE, bool DOT>
+template <int DIM, int W, int MODE, bool DOT>
 static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
     static size_t configured = 0;
     static int sms = 0;
-    auto kern = apply_kernel<DIM, MODE, DOT>;
+    auto kern = apply_kernel<DIM, W, MODE, DOT>;
     if (a.cfg.smem_bytes > configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.cfg.smem_bytes) != cudaSuccess) return 0;
         configured = a.cfg.smem_bytes;
@@ -519,16 +545,18 @@ static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
     return 1;
 }
 
-template <int DIM> static int launch_apply_d(const ApplyArgs& a, cudaStream_t st) {
-    if (a.mode == APPLY_AX) return a.dot_post >= 0 ? launch_apply_t<DIM, APPLY_AX, true>(a, st) : launch_apply_t<DIM, APPLY_AX, false>(a, st);
-    if (a.mode == APPLY_RESIDUAL) return launch_apply_t<DIM, APPLY_RESIDUAL, false>(a, st);
-    return launch_apply_t<DIM, APPLY_MULADD, false>(a, st);
+template <int DIM, int W> static int launch_apply_d(const ApplyArgs& a, cudaStream_t st) {
+    if (a.mode == APPLY_AX) return a.dot_post >= 0 ? launch_apply_t<DIM, W, APPLY_AX, true>(a, st) : launch_apply_t<DIM, W, APPLY_AX, false>(a, st);
+    if (a.mode == APPLY_RESIDUAL) return launch_apply_t<DIM, W, APPLY_RESIDUAL, false>(a, st);
+    return launch_apply_t<DIM, W, APPLY_MULADD, false>(a, st);
 }
 
 int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st) {
     if (a.nunits == 0) return 0;
-    if (a.L.W != APPLY_W || a.cfg.ring_rows <= 0) return -1;
-    return dim == 3 ? launch_apply_d<3>(a, st) : launch_apply_d<2>(a, st);
+    if (a.cfg.ring_rows <= 0) return -1;
+    if (a.L.W == 32) return dim == 3 ? launch_apply_d<3, 32>(a, st) : launch_apply_d<2, 32>(a, st);
+    if (a.L.W == 16 && dim == 3) return launch_apply_d<3, 16>(a, st);
+    return -1;
 }
 
 // ------------------------------------------------------------------------------------------
