@@ -342,18 +342,20 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    # The metric is quoted on BASELINE.json configs[1] (C2: 2D Tri64, refinements = 7, large base mesh);
-    # the same problem is sharded over the ranks for N > 1 (strong scaling).  The 3D Tet64 scaling
-    # configuration (C4) is measured in the same run and reported under "also".
-    name = "C2" if args.workload == "auto" else args.workload
+    # BASELINE.json: configs[1] (C2: 2D Tri64, refinements = 7, large base mesh, "on 1xB200") is the workload at
+    # N = 1; configs[3] (C4: 3D Tet64, refinements = 5, "coarse elements sharded over 2/4/8xB200") is the workload
+    # at N > 1 (strong scaling of the same mesh).  The other one is measured in the same run and reported under
+    # "also", and at N > 1 rank 0 additionally times the primary workload on its own GPU ("single_gpu").
+    name = ("C2" if world == 1 else "C4") if args.workload == "auto" else args.workload
     w = dict(WORKLOADS[name], key=name)
     if args.cells:
         w["c"] = args.cells
         w["name"] = w["name"].replace(f"c={WORKLOADS[name]['c']}", f"c={args.cells}")
     elif args.impl == "b200" and args.workload == "auto":
         # three pinned host matrices of the local share (x, b, result) must fit the host comfortably
-        need = 3 * 8 * nf_of(w["dim"], w["levels"]) * 2 * w["c"] ** 2 // max(1, world)
-        if need * 1.5 > host_memory_available():
+        nel = 2 * w["c"] ** 2 if w["dim"] == 2 else 6 * w["c"] ** 3
+        need = 3 * 8 * nf_of(w["dim"], w["levels"]) * nel // max(1, world)
+        if name == "C2" and need * 1.5 > host_memory_available():
             w["c"] = 128
             w["name"] = w["name"].replace("c=192", "c=128 (host memory too small for c=192)")
     dim, levels = w["dim"], w["levels"]
@@ -391,11 +393,21 @@ def main():
 
     main_r = measure(w, args, torch, hmg, dist, rank, world, device, steps, warmup, not args.no_e2e, True)
     also = None
+    single = None
     if args.workload == "auto" and not args.no_also:
-        w3 = dict(WORKLOADS["C4"], key="C4")
+        other = "C4" if name == "C2" else "C2"
+        w3 = dict(WORKLOADS[other], key=other)
         r3 = measure(w3, args, torch, hmg, dist, rank, world, device, min(steps, 5), 3, False, False)
-        also = {"C4": {k: r3[k] for k in ("value", "ms_per_step", "config", "ax", "vcycle_model", "roofline", "gpu_launches")}}
-        also["C4"]["unit"] = "GDOF/s"
+        also = {other: {k: r3[k] for k in ("value", "ms_per_step", "config", "ax", "vcycle_model", "roofline", "gpu_launches")}}
+        also[other]["unit"] = "GDOF/s"
+        if world > 1:
+            # the primary workload on ONE GPU, timed in this very job (rank 0 alone, the others wait): the
+            # denominator of the strong-scaling efficiency, free of run-to-run and box-to-box variation
+            if rank == 0:
+                r1 = measure(w, args, torch, hmg, None, 0, 1, device, min(steps, 3), 3, False, False)
+                single = {"workload": r1["config"]["workload"], "value": r1["value"], "unit": "GDOF/s",
+                          "ms_per_step": r1["ms_per_step"], "ax": r1["ax"]["value"]}
+            dist.barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -411,7 +423,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": main_r["config"], "ax": main_r["ax"], "vcycle_model": main_r["vcycle_model"],
             "roofline": main_r["roofline"], "clocks": main_r["clocks"], "e2e": main_r["e2e"],
-            "gpu_launches": main_r["gpu_launches"], "cpu_baseline": cpu, "also": also,
+            "gpu_launches": main_r["gpu_launches"], "cpu_baseline": cpu, "also": also, "single_gpu": single,
         }
         print(json.dumps(line))
     if dist is not None:
