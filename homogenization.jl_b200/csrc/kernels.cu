@@ -538,7 +538,8 @@ static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
     const int64_t planes = a.nunits * (a.L.m + 1);
     const int64_t rows_per_sm = a.nunits * a.L.nf / sms;
     static const int over_env = getenv("HMG_APPLY_OVERSUB") ? atoi(getenv("HMG_APPLY_OVERSUB")) : 0;
-    const int64_t over = over_env > 0 ? over_env : std::max<int64_t>(1, std::min<int64_t>(8, rows_per_sm / 8192));
+    // (measured: + 6 % in 2D; in 3D the extra halo planes and pipeline fills cost more than they gain)
+    const int64_t over = over_env > 0 ? over_env : (DIM == 2 ? std::max<int64_t>(1, std::min<int64_t>(8, rows_per_sm / 8192)) : 1);
     int64_t grid = std::min<int64_t>((int64_t)sms * a.cfg.ctas_per_sm * over, planes);
     if (DOT) grid = std::min<int64_t>(grid, a.red.max_blocks);
     kern<<<(unsigned)grid, (a.cfg.nwarps + 1) * 32, a.cfg.smem_bytes, st>>>(p);
