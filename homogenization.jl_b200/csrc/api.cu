@@ -422,17 +422,40 @@ void do_global_product(hmg_ctx* c, int l, const double* x, double* y, int dot_po
     if (dot_post >= 0) finish_reduction(c, dot_post, S_TMP);
     do_broadcast(c, l, y);                                       // interface sums
 }
+// r = broadcast(r) and rho = dot(r, r) over all stored entries without a pass over r: the residual apply
+// left the interior part in S_TMP; the interface kernels add (owners x sum^2) of every shared node
+void do_broadcast_rho(hmg_ctx* c, int l, double* r) {
+    const LevelView& V = c->level(l).view;
+    if (c->nranks == 1) {
+        const int n = launch_interface_sum_sq(c->dim, V, c->tview, r, c->red, POST_RHO_ADD, c->stream);
+        check_launch(c, n);
+        if (n == 0) check_launch(c, launch_scalar_post(c->red, POST_RHO, 0, c->stream));     // no shared cell at all
+        return;
+    }
+    check_launch(c, launch_interface_sum_sq(c->dim, V, c->tview, r, c->red, POST_ADD, c->stream));
+    const int64_t slots = c->cut_slots(l);
+    if (slots > 0) {
+        double* send = c->cut_send[l - 1];
+        for (int kind = 0; kind < 3; ++kind)
+            check_launch(c, launch_cut(c->dim, CUT_PACK, kind, V, c->cutv[kind], c->cut_base(l, kind), r, send, c->stream));
+        NCCL_OK(nccl().AllReduce(send, c->cut_recv, (size_t)slots, ncclDouble, ncclSum, c->comm, c->stream));
+        for (int kind = 0; kind < 3; ++kind)
+            check_launch(c, launch_cut_unpack_sq(c->dim, kind, V, c->cutv[kind], c->cut_base(l, kind), r, c->cut_recv, c->red,
+                                                 c->stream));
+    }
+    finish_reduction(c, POST_RHO, S_TMP);
+}
 void do_smoothing(hmg_ctx* c, int l, int steps) {
     const int64_t n = c->nstored(l);
     double *x = c->vecp(l, HMG_X), *r = c->vecp(l, HMG_R), *p = c->vecp(l, HMG_P), *Ap = c->vecp(l, HMG_AP);
-    // r = broadcast(constraint(b - A x)); p = r and rho = r.r in one pass
-    do_apply(c, l, APPLY_RESIDUAL, 1.0, x, r, c->vecp(l, HMG_B));
-    do_broadcast(c, l, r);
-    check_launch(c, launch_copy_dot(c->red, r, p, n, kernel_post(c, POST_RHO), c->stream));
-    finish_reduction(c, POST_RHO, S_TMP);
+    // r = broadcast(constraint(b - A x)), rho = r.r (src/multigrid.jl:50-54); the copy p = r is folded into the
+    // first update below, the first product reads r itself
+    do_apply(c, l, APPLY_RESIDUAL, 1.0, x, r, c->vecp(l, HMG_B), POST_STORE);
+    do_broadcast_rho(c, l, r);
+    if (steps == 0) CUDA_OK(cudaMemcpyAsync(p, r, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     for (int i = 0; i < steps; ++i) {
-        do_global_product(c, l, p, Ap, POST_PAP);                     // Ap = broadcast(constraint(A p)), alpha = rho / p.Ap
-        check_launch(c, launch_cg_update(c->red, x, p, r, Ap, n, kernel_post(c, POST_RSQR), c->stream));
+        do_global_product(c, l, i == 0 ? r : p, Ap, POST_PAP);        // Ap = broadcast(constraint(A p)), alpha = rho / p.Ap
+        check_launch(c, launch_cg_update(c->red, x, p, r, Ap, n, kernel_post(c, POST_RSQR), i == 0, c->stream));
         finish_reduction(c, POST_RSQR, S_TMP);
         // the reference also updates p after the last step, but that value is never used
         // (src/multigrid.jl:68; the next smoothing call starts from a fresh residual)
@@ -1056,7 +1079,7 @@ int hmg_time_op(hmg_ctx* c, int op, int level, int steps, int reps, float* ms_ou
             do_apply(c, level, APPLY_RESIDUAL, 1.0, c->vecp(level, HMG_X), c->vecp(level, HMG_R), c->vecp(level, HMG_B));
         } else if (op == 6) {
             check_launch(c, launch_cg_update(c->red, c->vecp(level, HMG_X), c->vecp(level, HMG_P), c->vecp(level, HMG_R),
-                                             c->vecp(level, HMG_AP), c->nstored(level), POST_RSQR, c->stream));
+                                             c->vecp(level, HMG_AP), c->nstored(level), POST_RSQR, false, c->stream));
         } else if (op == 7) {
             check_launch(c, launch_p_update(c->red, c->vecp(level, HMG_P), c->vecp(level, HMG_R), c->nstored(level), c->stream));
         } else if (op == 8) {

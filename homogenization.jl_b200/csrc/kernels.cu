@@ -67,6 +67,8 @@ __device__ __forceinline__ void scalar_post(double* S, int post, int slot, doubl
     else if (post == POST_RHO) S[S_RHO] = tot;
     else if (post == POST_PAP) { S[S_PAP] = tot; S[S_ALPHA] = S[S_RHO] / tot; }
     else if (post == POST_RSQR) { S[S_RSQR] = tot; S[S_BETA] = tot / S[S_RHO]; S[S_RHO] = tot; }
+    else if (post == POST_ADD) S[slot] += tot;
+    else if (post == POST_RHO_ADD) S[S_RHO] = S[S_TMP] + tot;
 }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -195,7 +197,10 @@ template <int DIM, int W, int MODE, bool DOT> struct OutDev {
         }
         if (W == 32 || active) {
             yl[k * APPLY_W] = v;
-            if (DOT) dsum = fma(weight<CLS>() * x0, v, dsum);
+            if (DOT) {
+                if (MODE == APPLY_AX) dsum = fma(weight<CLS>() * x0, v, dsum);
+                else if (CLS == 0) dsum = fma(v, v, dsum);      // interior part of dot(r, r); interfaces: K2
+            }
         }
     }
 };
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
                 }
                 interior_coefficients(op, a.T);
                 if (MODE != APPLY_MULADD) out.cm = (unsigned)__ldg(a.cmask + e);
-                if (DOT) {
+                if (DOT && MODE == APPLY_AX) {
                     const uint8_t* mp = a.mult + u * 16 * APPLY_W + el;
                     unsigned long long lo = 0, hi = 0;
 #pragma unroll
@@ -548,7 +553,7 @@ static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
 
 template <int DIM, int W> static int launch_apply_d(const ApplyArgs& a, cudaStream_t st) {
     if (a.mode == APPLY_AX) return a.dot_post >= 0 ? launch_apply_t<DIM, W, APPLY_AX, true>(a, st) : launch_apply_t<DIM, W, APPLY_AX, false>(a, st);
-    if (a.mode == APPLY_RESIDUAL) return launch_apply_t<DIM, W, APPLY_RESIDUAL, false>(a, st);
+    if (a.mode == APPLY_RESIDUAL) return a.dot_post >= 0 ? launch_apply_t<DIM, W, APPLY_RESIDUAL, true>(a, st) : launch_apply_t<DIM, W, APPLY_RESIDUAL, false>(a, st);
     return launch_apply_t<DIM, W, APPLY_MULADD, false>(a, st);
 }
 
@@ -568,63 +573,68 @@ int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st) {
 // (src/implicit_fine_grid.jl:219-244) and writes both.  Cells with more owners (3D edges, vertices)
 // are processed cell by cell: one thread per shared fine node.  OP 0: sum + broadcast; OP 1: zero
 // all but the first owner (src/implicit_fine_grid.jl:334-386).
-template <int DIM, int OP>
+// SQ: additionally reduce sum over the touched entries of value^2 ( = owners * sum^2 per shared node) and add it
+// to S_TMP -- the part of rho = dot(r, r) that lives on interfaces; the apply kernel reduces the interior part
+// (src/multigrid.jl:54 without a pass over r).  With SQ the grid is bounded and blocks loop over virtual blocks.
+template <int DIM, int OP, bool SQ>
 __global__ void __launch_bounds__(256) interface_kernel(const LevelView L, const TopoView T, int64_t npair_blocks,
-                                                        double* __restrict__ x) {
+                                                        int64_t nvirtual, double* __restrict__ x, const Reducer R, int post) {
     constexpr int NF = DIM == 3 ? 4 : 3;
     const int W = L.W, ws = L.wshift, nf = L.nf;
-    if ((int64_t)blockIdx.x < npair_blocks) {
-        const int npc = DIM == 3 ? L.npf : L.npe;
-        const uint16_t* tab = L.iface_idx;   // 3D: faces first; 2D: edges first
-        const int l = threadIdx.x & (W - 1), ks = threadIdx.x >> ws, nk = blockDim.x >> ws;
-        const int64_t u = blockIdx.x / NF;
-        const int f = (int)(blockIdx.x - u * NF);
-        const int64_t e = u * W + l;
-        if (e >= T.ne) return;
-        const int32_t pr = T.partner[e * 4 + f];
-        if (pr < 0 || (pr >> 3) < e) return;       // the lower owner drives the pair
-        const int64_t pe = pr >> 3;
-        const int pf = pr & 7;
-        double* A = x + u * (int64_t)nf * W + l;
-        double* B = x + (pe >> ws) * (int64_t)nf * W + (pe & (W - 1));
-        const uint16_t* ta = tab + f * npc;
-        const uint16_t* tb = tab + pf * npc;
-        // four nodes per step: all eight loads are in flight before the first store (the kernel is bound by
-        // memory latency, not by bytes)
-        constexpr int U = 4;
-        for (int k0 = ks; k0 < npc; k0 += nk * U) {
-            int64_t oa[U], ob[U];
-            double va[U], vb[U];
+    double sq = 0.0;
+    for (int64_t vb = blockIdx.x; vb < nvirtual; vb += gridDim.x) {
+        if (vb < npair_blocks) {
+            const int npc = DIM == 3 ? L.npf : L.npe;
+            const uint16_t* tab = L.iface_idx;   // 3D: faces first; 2D: edges first
+            const int l = threadIdx.x & (W - 1), ks = threadIdx.x >> ws, nk = blockDim.x >> ws;
+            const int64_t u = vb / NF;
+            const int f = (int)(vb - u * NF);
+            const int64_t e = u * W + l;
+            if (e >= T.ne) continue;
+            const int32_t pr = T.partner[e * 4 + f];
+            if (pr < 0 || (pr >> 3) < e) continue;       // the lower owner drives the pair
+            const int64_t pe = pr >> 3;
+            const int pf = pr & 7;
+            double* A = x + u * (int64_t)nf * W + l;
+            double* B = x + (pe >> ws) * (int64_t)nf * W + (pe & (W - 1));
+            const uint16_t* ta = tab + f * npc;
+            const uint16_t* tb = tab + pf * npc;
+            // four nodes per step: all eight loads are in flight before the first store
+            constexpr int U = 4;
+            for (int k0 = ks; k0 < npc; k0 += nk * U) {
+                int64_t oa[U], ob[U];
+                double va[U], vb_[U];
 #pragma unroll
-            for (int q = 0; q < U; ++q) {
-                const int k = min(k0 + q * nk, npc - 1);
-                oa[q] = (int64_t)__ldg(ta + k) * W;
-                ob[q] = (int64_t)__ldg(tb + k) * W;
-            }
-            if (OP == 0) {
-#pragma unroll
-                for (int q = 0; q < U; ++q) { va[q] = A[oa[q]]; vb[q] = B[ob[q]]; }
-            }
-#pragma unroll
-            for (int q = 0; q < U; ++q) {
-                if (k0 + q * nk >= npc) break;
+                for (int q = 0; q < U; ++q) {
+                    const int k = min(k0 + q * nk, npc - 1);
+                    oa[q] = (int64_t)__ldg(ta + k) * W;
+                    ob[q] = (int64_t)__ldg(tb + k) * W;
+                }
                 if (OP == 0) {
-                    const double sum = va[q] + vb[q];
-                    A[oa[q]] = sum;
-                    B[ob[q]] = sum;
-                } else {
-                    B[ob[q]] = 0.0;
+#pragma unroll
+                    for (int q = 0; q < U; ++q) { va[q] = A[oa[q]]; vb_[q] = B[ob[q]]; }
+                }
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    if (k0 + q * nk >= npc) break;
+                    if (OP == 0) {
+                        const double sum = va[q] + vb_[q];
+                        A[oa[q]] = sum;
+                        B[ob[q]] = sum;
+                        if (SQ) sq = fma(2.0 * sum, sum, sq);
+                    } else {
+                        B[ob[q]] = 0.0;
+                    }
                 }
             }
+            continue;
         }
-        return;
-    }
-    // multi-owner cells
-    const int nel = DIM == 3 ? 6 : 3, nfl = DIM == 3 ? 4 : 0;
-    const int64_t nedge_items = DIM == 3 ? T.nedges * L.npe : 0;
-    const int64_t total = nedge_items + T.nverts;
-    const int64_t nb = gridDim.x - npair_blocks;
-    for (int64_t t = ((int64_t)blockIdx.x - npair_blocks) * blockDim.x + threadIdx.x; t < total; t += nb * blockDim.x) {
+        // multi-owner cells: 256 (cell, node) items per virtual block
+        const int nel = DIM == 3 ? 6 : 3, nfl = DIM == 3 ? 4 : 0;
+        const int64_t nedge_items = DIM == 3 ? T.nedges * L.npe : 0;
+        const int64_t total = nedge_items + T.nverts;
+        const int64_t t = (vb - npair_blocks) * blockDim.x + threadIdx.x;
+        if (t >= total) continue;
         const int64_t* off;
         const int32_t* own;
         const uint16_t* tab;
@@ -651,13 +661,16 @@ __global__ void __launch_bounds__(256) interface_kernel(const LevelView L, const
             if (OP == 0) s += *ptr;
             else if (o > b) *ptr = 0.0;
         }
-        if (OP == 0)
+        if (OP == 0) {
             for (int64_t o = b; o < en; ++o) {
                 const int32_t id = own[o];
                 const int64_t el = id >> 3;
                 x[((el >> ws) * (int64_t)nf + __ldg(tab + (id & 7) * npc + k)) * W + (el & (W - 1))] = s;
             }
+            if (SQ) sq = fma((double)(en - b) * s, s, sq);
+        }
     }
+    if (SQ) block_reduce_finish(sq, R, post, S_TMP);
 }
 
 static unsigned grid_for(int64_t n, int block, int max_blocks = 148 * 16) {
@@ -667,33 +680,39 @@ static unsigned grid_for(int64_t n, int block, int max_blocks = 148 * 16) {
     return (unsigned)g;
 }
 
-template <int OP>
-static int launch_interface(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st) {
+// returns the number of launches (0: the level has no shared cell on this rank)
+template <int OP, bool SQ>
+static int launch_interface(int dim, const LevelView& L, const TopoView& T, double* x, const Reducer& R, int post, cudaStream_t st) {
     const int npc = dim == 3 ? L.npf : L.npe;
     const int64_t nunits = (T.ne + L.W - 1) / L.W;
     const int64_t npair_blocks = npc > 0 ? nunits * (dim == 3 ? 4 : 3) : 0;
     const int64_t multi = (dim == 3 ? T.nedges * L.npe : 0) + T.nverts;
-    const int64_t nmulti_blocks = multi > 0 ? grid_for(multi, 256) : 0;
-    if (npair_blocks + nmulti_blocks == 0) return 0;
-    const unsigned grid = (unsigned)(npair_blocks + nmulti_blocks);
-    if (dim == 3) interface_kernel<3, OP><<<grid, 256, 0, st>>>(L, T, npair_blocks, x);
-    else interface_kernel<2, OP><<<grid, 256, 0, st>>>(L, T, npair_blocks, x);
+    const int64_t nmulti_blocks = (multi + 255) / 256;
+    const int64_t nvirtual = npair_blocks + nmulti_blocks;
+    if (nvirtual == 0) return 0;
+    const unsigned grid = (unsigned)(SQ ? std::min<int64_t>(nvirtual, R.max_blocks) : nvirtual);
+    if (dim == 3) interface_kernel<3, OP, SQ><<<grid, 256, 0, st>>>(L, T, npair_blocks, nvirtual, x, R, post);
+    else interface_kernel<2, OP, SQ><<<grid, 256, 0, st>>>(L, T, npair_blocks, nvirtual, x, R, post);
     return 1;
 }
 int launch_interface_sum(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st) {
-    return launch_interface<0>(dim, L, T, x, st);
+    return launch_interface<0, false>(dim, L, T, x, Reducer{}, 0, st);
+}
+int launch_interface_sum_sq(int dim, const LevelView& L, const TopoView& T, double* x, const Reducer& R, int post, cudaStream_t st) {
+    return launch_interface<0, true>(dim, L, T, x, R, post, st);
 }
 int launch_zero_all_but_one(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st) {
-    return launch_interface<1>(dim, L, T, x, st);
+    return launch_interface<1, false>(dim, L, T, x, Reducer{}, 0, st);
 }
 
 // Cut cells (owners on several ranks): pack the partial sum over the local owners into the level's
 // packed buffer / write the all-reduced total back to the local owners / zero all but the globally
 // first owner.  One thread per (cell, paired node).
-template <int OP>
+template <int OP, bool SQ>
 __global__ void __launch_bounds__(256) cut_kernel(const LevelView L, const CutView C, int npc, const uint16_t* __restrict__ tab,
-                                                  int64_t buf_base, double* __restrict__ x, double* __restrict__ buf) {
+                                                  int64_t buf_base, double* __restrict__ x, double* __restrict__ buf, const Reducer R) {
     const int64_t total = C.ncells * npc;
+    double sq = 0.0;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t cell = t / npc;
         const int k = (int)(t - cell * npc);
@@ -709,7 +728,9 @@ __global__ void __launch_bounds__(256) cut_kernel(const LevelView L, const CutVi
             else if (!(o == b && C.first_local[cell])) *ptr = 0.0;
         }
         if (OP == CUT_PACK) buf[s] = acc;
+        if (SQ) sq = fma((double)(en - b) * acc, acc, sq);     // every local copy of the node holds the total
     }
+    if (SQ) block_reduce_finish(sq, R, POST_ADD, S_TMP);
 }
 int launch_cut(int dim, int op, int kind, const LevelView& L, const CutView& C, int64_t buf_base, double* x, double* buf,
                cudaStream_t st) {
@@ -718,9 +739,19 @@ int launch_cut(int dim, int op, int kind, const LevelView& L, const CutView& C, 
     const uint16_t* tab = L.iface_idx + (kind == 0 ? 0 : (kind == 1 ? nfl * L.npf : nfl * L.npf + nel * L.npe));
     if (C.ncells * npc == 0) return 0;
     const unsigned grid = grid_for(C.ncells * npc, 256);
-    if (op == CUT_PACK) cut_kernel<CUT_PACK><<<grid, 256, 0, st>>>(L, C, npc, tab, buf_base, x, buf);
-    else if (op == CUT_UNPACK) cut_kernel<CUT_UNPACK><<<grid, 256, 0, st>>>(L, C, npc, tab, buf_base, x, buf);
-    else cut_kernel<CUT_ZERO_BUT_FIRST><<<grid, 256, 0, st>>>(L, C, npc, tab, buf_base, x, buf);
+    if (op == CUT_PACK) cut_kernel<CUT_PACK, false><<<grid, 256, 0, st>>>(L, C, npc, tab, buf_base, x, buf, Reducer{});
+    else if (op == CUT_UNPACK) cut_kernel<CUT_UNPACK, false><<<grid, 256, 0, st>>>(L, C, npc, tab, buf_base, x, buf, Reducer{});
+    else cut_kernel<CUT_ZERO_BUT_FIRST, false><<<grid, 256, 0, st>>>(L, C, npc, tab, buf_base, x, buf, Reducer{});
+    return 1;
+}
+// unpack + add (local copies) * total^2 of every cut node to S_TMP
+int launch_cut_unpack_sq(int dim, int kind, const LevelView& L, const CutView& C, int64_t buf_base, double* x, double* buf,
+                         const Reducer& R, cudaStream_t st) {
+    const int nfl = dim == 3 ? 4 : 0, nel = dim == 3 ? 6 : 3;
+    const int npc = kind == 0 ? L.npf : (kind == 1 ? L.npe : 1);
+    const uint16_t* tab = L.iface_idx + (kind == 0 ? 0 : (kind == 1 ? nfl * L.npf : nfl * L.npf + nel * L.npe));
+    if (C.ncells * npc == 0) return 0;
+    cut_kernel<CUT_UNPACK, true><<<grid_for(C.ncells * npc, 256, R.max_blocks), 256, 0, st>>>(L, C, npc, tab, buf_base, x, buf, R);
     return 1;
 }
 
@@ -837,18 +868,23 @@ __global__ void __launch_bounds__(256) copy_dot_kernel(const Reducer R, const do
 }
 
 // x += alpha p ; r -= alpha Ap ; rsqr = dot(r, r) -> beta, rho   (src/multigrid.jl:64-68)
-__global__ void __launch_bounds__(256) cg_update_kernel(const Reducer R, double* __restrict__ x, const double* __restrict__ p,
+// FIRST: the first step of a smoothing call, where the search direction IS the residual: p is written
+// (p = r_old) instead of read, which replaces the p = r copy of src/multigrid.jl:53
+template <bool FIRST>
+__global__ void __launch_bounds__(256) cg_update_kernel(const Reducer R, double* __restrict__ x, double* __restrict__ p,
                                                         double* __restrict__ r, const double* __restrict__ Ap, int64_t n, int post) {
     const double alpha = R.scalars[S_ALPHA];
     double s = 0.0;
     const int64_t n2 = n >> 1;
     double2* x2 = reinterpret_cast<double2*>(x);
     double2* r2 = reinterpret_cast<double2*>(r);
-    const double2* p2 = reinterpret_cast<const double2*>(p);
+    double2* p2 = reinterpret_cast<double2*>(p);
     const double2* q2 = reinterpret_cast<const double2*>(Ap);
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n2; t += (int64_t)gridDim.x * blockDim.x) {
         double2 xv = x2[t], rv = r2[t];
-        const double2 pv = p2[t], qv = q2[t];
+        const double2 qv = q2[t];
+        double2 pv;
+        if (FIRST) { pv = rv; p2[t] = rv; } else pv = p2[t];
         xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
         rv.x = fma(-alpha, qv.x, rv.x); rv.y = fma(-alpha, qv.y, rv.y);
         x2[t] = xv; r2[t] = rv;
@@ -890,8 +926,9 @@ int launch_copy_dot(const Reducer& R, const double* r, double* p, int64_t n, int
     copy_dot_kernel<<<grid_for(n / 2 + 1, 256, R.max_blocks), 256, 0, st>>>(R, r, p, n, post);
     return 1;
 }
-int launch_cg_update(const Reducer& R, double* x, const double* p, double* r, const double* Ap, int64_t n, int post, cudaStream_t st) {
-    cg_update_kernel<<<grid_for(n / 2 + 1, 256, R.max_blocks), 256, 0, st>>>(R, x, p, r, Ap, n, post);
+int launch_cg_update(const Reducer& R, double* x, double* p, double* r, const double* Ap, int64_t n, int post, bool first, cudaStream_t st) {
+    if (first) cg_update_kernel<true><<<grid_for(n / 2 + 1, 256, R.max_blocks), 256, 0, st>>>(R, x, p, r, Ap, n, post);
+    else cg_update_kernel<false><<<grid_for(n / 2 + 1, 256, R.max_blocks), 256, 0, st>>>(R, x, p, r, Ap, n, post);
     return 1;
 }
 int launch_p_update(const Reducer& R, double* p, const double* r, int64_t n, cudaStream_t st) {

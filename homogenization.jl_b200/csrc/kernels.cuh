@@ -36,7 +36,7 @@ struct TopoView {
 
 // scalar slots on the device (no host round trip inside a V-cycle)
 enum Scalar { S_RHO = 0, S_PAP = 1, S_ALPHA = 2, S_RSQR = 3, S_BETA = 4, S_TMP = 5, S_NRM = 6, S_COUNT = 16 };
-enum PostOp { POST_STORE = 0, POST_RHO = 1, POST_PAP = 2, POST_RSQR = 3 };
+enum PostOp { POST_STORE = 0, POST_RHO = 1, POST_PAP = 2, POST_RSQR = 3, POST_ADD = 4, POST_RHO_ADD = 5 };
 
 struct Reducer {
     double* partials;     // [max_blocks]
@@ -92,6 +92,9 @@ struct ApplyArgs {
 int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st);
 ApplyConfig make_apply_config(int dim, int m, int nf, int W);
 int launch_interface_sum(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
+int launch_interface_sum_sq(int dim, const LevelView& L, const TopoView& T, double* x, const Reducer& R, int post, cudaStream_t st);
+int launch_cut_unpack_sq(int dim, int kind, const LevelView& L, const CutView& C, int64_t buf_base, double* x, double* buf,
+                         const Reducer& R, cudaStream_t st);
 int launch_zero_all_but_one(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
 // kind 0 faces / 1 edges / 2 vertices; buf_base = first slot of the kind in the level's packed buffer
 int launch_cut(int dim, int op, int kind, const LevelView& L, const CutView& C, int64_t buf_base, double* x, double* buf,
@@ -110,7 +113,7 @@ int launch_restrict(int dim, const LevelView& Lf, const LevelView& Lc, int64_t n
 int launch_interp_add(int dim, const LevelView& Lf, const LevelView& Lc, int64_t nunits, double* xf, const double* xc, cudaStream_t st);
 int launch_dot(const Reducer& R, const double* a, const double* b, int64_t n, int post, int slot, cudaStream_t st);
 int launch_copy_dot(const Reducer& R, const double* r, double* p, int64_t n, int post, cudaStream_t st);
-int launch_cg_update(const Reducer& R, double* x, const double* p, double* r, const double* Ap, int64_t n, int post, cudaStream_t st);
+int launch_cg_update(const Reducer& R, double* x, double* p, double* r, const double* Ap, int64_t n, int post, bool first, cudaStream_t st);
 int launch_p_update(const Reducer& R, double* p, const double* r, int64_t n, cudaStream_t st);
 int launch_axpy(double alpha, const double* x, double* y, int64_t n, cudaStream_t st);
 int launch_fill(double* x, double v, int64_t n, cudaStream_t st);
