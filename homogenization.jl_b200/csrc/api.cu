@@ -81,6 +81,8 @@ const NcclApi& nccl() {
 struct LevelDev {
     LevelView view{};
     ApplyConfig cfg{};
+    ApplyConfig cfg_fused{};      // launch shape of the fused p-update + product (ring_rows <= 0: does not fit)
+    double* p2 = nullptr;         // the other search-direction buffer of the fused p-update (lazy)
     std::vector<double> tab;      // StencilTab of the level (travels in the kernel parameter block)
     int32_t* hier2lat = nullptr;
     double* vec[HMG_NVEC] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -282,6 +284,8 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const 
         L.hier2lat = c->dupload(R.hier2lat);
         L.cfg = make_apply_config(dim, R.m, R.nf, c->W);
         HMG_CHECK(L.cfg.ring_rows > 0, "a level of this hierarchy does not fit the shared-memory ring of the apply kernel");
+        L.cfg_fused = make_apply_config(dim, R.m, R.nf, c->W, true);
+        if (c->W != 32 || (getenv("HMG_FUSE_P") && atoi(getenv("HMG_FUSE_P")) == 0)) L.cfg_fused.ring_rows = -1;
         L.tab = R.gi;
         L.tab.insert(L.tab.end(), R.gc.begin(), R.gc.end());
         L.tab.insert(L.tab.end(), R.ge.begin(), R.ge.end());
@@ -366,6 +370,7 @@ void do_apply(hmg_ctx* c, int l, int mode, double alpha, const double* x, double
     ApplyArgs a;
     a.L = L.view;
     a.cfg = L.cfg;
+    a.cfg_fused = L.cfg_fused;
     a.nunits = c->nunits;
     a.tab = L.tab.data();
     a.coef = c->elem_coef;
@@ -445,6 +450,26 @@ void do_broadcast_rho(hmg_ctx* c, int l, double* r) {
     }
     finish_reduction(c, POST_RHO, S_TMP);
 }
+// p' = r + beta p and Ap = broadcast(constraint(A p')) with p' applied straight out of shared memory: the new
+// direction goes to the level's second p buffer (other CTAs still read the old one), then the buffers swap
+void do_fused_direction_product(hmg_ctx* c, int l) {
+    LevelDev& L = c->level(l);
+    if (!L.p2) L.p2 = c->dalloc<double>((size_t)c->nstored(l));
+    ApplyArgs a;
+    a.L = L.view; a.cfg = L.cfg; a.cfg_fused = L.cfg_fused;
+    a.nunits = c->nunits; a.tab = L.tab.data();
+    a.coef = c->elem_coef; a.cmask = c->cmask; a.mult = c->mult;
+    a.x = c->vecp(l, HMG_P); a.r2 = c->vecp(l, HMG_R); a.pout = L.p2;
+    a.y = c->vecp(l, HMG_AP); a.b = nullptr;
+    a.alpha = 1.0; a.lambda = c->lambda; a.mode = APPLY_AX;
+    a.dot_post = kernel_post(c, POST_PAP); a.red = c->red;
+    const int n = launch_apply(c->dim, a, c->stream);
+    HMG_CHECK(n >= 0, "apply kernel refused the fused launch configuration");
+    check_launch(c, n);
+    std::swap(L.vec[HMG_P], L.p2);
+    finish_reduction(c, POST_PAP, S_TMP);
+    do_broadcast(c, l, c->vecp(l, HMG_AP));
+}
 void do_smoothing(hmg_ctx* c, int l, int steps) {
     const int64_t n = c->nstored(l);
     double *x = c->vecp(l, HMG_X), *r = c->vecp(l, HMG_R), *p = c->vecp(l, HMG_P), *Ap = c->vecp(l, HMG_AP);
@@ -453,13 +478,20 @@ void do_smoothing(hmg_ctx* c, int l, int steps) {
     do_apply(c, l, APPLY_RESIDUAL, 1.0, x, r, c->vecp(l, HMG_B), POST_STORE);
     do_broadcast_rho(c, l, r);
     if (steps == 0) CUDA_OK(cudaMemcpyAsync(p, r, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    const bool fuse = c->level(l).cfg_fused.ring_rows > 0;
     for (int i = 0; i < steps; ++i) {
-        do_global_product(c, l, i == 0 ? r : p, Ap, POST_PAP);        // Ap = broadcast(constraint(A p)), alpha = rho / p.Ap
+        // Ap = broadcast(constraint(A p)), alpha = rho / p.Ap; after the first step the direction update
+        // p = r + beta p (src/multigrid.jl:68) happens inside the product
+        if (i == 0) do_global_product(c, l, r, Ap, POST_PAP);
+        else if (fuse) { do_fused_direction_product(c, l); p = c->vecp(l, HMG_P); }
+        else {
+            check_launch(c, launch_p_update(c->red, p, r, n, c->stream));
+            do_global_product(c, l, p, Ap, POST_PAP);
+        }
         check_launch(c, launch_cg_update(c->red, x, p, r, Ap, n, kernel_post(c, POST_RSQR), i == 0, c->stream));
         finish_reduction(c, POST_RSQR, S_TMP);
         // the reference also updates p after the last step, but that value is never used
-        // (src/multigrid.jl:68; the next smoothing call starts from a fresh residual)
-        if (i + 1 < steps) check_launch(c, launch_p_update(c->red, p, r, n, c->stream));
+        // (the next smoothing call starts from a fresh residual)
     }
 }
 void do_coarse_solve(hmg_ctx* c) {
@@ -1090,6 +1122,9 @@ int hmg_time_op(hmg_ctx* c, int op, int level, int steps, int reps, float* ms_ou
         } else if (op == 10) {
             check_launch(c, launch_interp_add(c->dim, c->level(level).view, c->level(level - 1).view, c->nunits,
                                               c->vecp(level, HMG_X), c->vecp(level - 1, HMG_X), c->stream));
+        } else if (op == 12) {
+            HMG_CHECK(c->level(level).cfg_fused.ring_rows > 0, "the fused p-update does not fit this level");
+            do_fused_direction_product(c, level);
         } else if (op == 11) {
             do_apply(c, level, APPLY_AX, 1.0, c->vecp(level, HMG_P), c->vecp(level, HMG_AP), nullptr, POST_STORE);
         } else {

@@ -288,7 +288,8 @@ HMG_HD LineRows2 line_rows2(int m, int i, int k0, int k1) {
     const int kn = k1 - 1 < L - 2 ? k1 - 1 : L - 2;            // last node of the next line that is read
     r.need = i < m ? (kn >= 0 ? r.rm[0] + kn : r.c + k1 - 1) : r.c;
     if (r.need < r.c + (k1 < L ? k1 : L - 1)) r.need = r.c + (k1 < L ? k1 : L - 1);
-    r.behind = i > 0 ? r.rp[0] + k0 : r.c;      // monotone in task order (line 0 stays resident until line 1 starts)
+    // oldest row read: node k0 - 1 of the previous line; monotone in task order (line 0 stays resident until line 1 starts)
+    r.behind = i > 0 ? r.rp[0] + (k0 > 0 ? k0 - 1 : 0) : r.c;
     return r;
 }
 

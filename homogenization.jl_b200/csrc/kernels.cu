@@ -125,6 +125,7 @@ __device__ __forceinline__ void block_reduce_finish(double v, const Reducer& R, 
 // SP rows are mirrored behind the ring so that a line never wraps.  Each lane walks its line with a
 // register sliding window: 7 (3D) / 3 (2D) shared loads per node instead of 15 / 7.
 constexpr int APPLY_Q = 64, APPLY_QS = 6;   // mbarrier slots (chunks in flight), log2
+constexpr int APPLY_STAGES = 16;             // staging slots of the fused p-update variant: 4 per converter warp
 constexpr int APPLY_MAXT = 16 * 32;    // 15 consumer warps + the producer warp: 128 registers per thread
 
 template <int DIM> struct ApplyParams {
@@ -140,6 +141,10 @@ template <int DIM> struct ApplyParams {
     int m, nf, nwarps, R, SP, cs, seg_shift, run;
     int dot_post;
     Reducer red;
+    // FUSEP: x = old p, r2 = r, pout = the other p buffer, staging of 2^sr_shift rows x nstage slots
+    const double* r2;
+    double* pout;
+    int sr_shift, nstage, nconv;
 };
 
 template <int DIM> __device__ __forceinline__ int plane_off(int m, int t) { return DIM == 3 ? lat_off3(m, t) : lat_off2(m, t); }
@@ -210,13 +215,17 @@ struct SmemLoad {
     __device__ __forceinline__ double operator()(int addr) const { return sm[addr]; }
 };
 
-template <int DIM, int W, int MODE, bool DOT>
+// FUSEP (with MODE = AX): the input is not a stored vector but the new search direction p' = r + beta p of
+// src/multigrid.jl:68.  The producer warp bulk-copies chunks of r and p into a small staging area, converts them
+// into the ring (p' is what the stencil reads) and stores p' to the OTHER p buffer (neighbouring CTAs still read
+// the old p for their halo planes), so p' never makes a round trip through HBM before it is applied.
+template <int DIM, int W, int MODE, bool DOT, bool FUSEP>
 __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_constant__ ApplyParams<DIM> a) {
     using D = Dims<DIM>;
     constexpr int APPLY_W = W;
     static_assert(W == 32 || (W == 16 && DIM == 3), "W = 16 pairs two lines of a 3D plane per warp");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[APPLY_Q], empty_bar[APPLY_Q];
+    __shared__ __align__(8) uint64_t full_bar[APPLY_Q], empty_bar[APPLY_Q], stage_bar[APPLY_STAGES];
     double* sm = reinterpret_cast<double*>(smem_raw);
     const int m = a.m, nf = a.nf, NW = a.nwarps, R = a.R, SP = a.SP, CS = a.cs, CH = 1 << a.cs;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
@@ -225,7 +234,9 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
     const int NPL = m + 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < APPLY_Q; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NW); }
+        // FUSEP: a ring chunk is complete after all of its staging sub-chunks were converted
+        for (int s = 0; s < APPLY_Q; ++s) { mbar_init(&full_bar[s], FUSEP ? (1u << (a.cs - a.sr_shift)) : 1u); mbar_init(&empty_bar[s], NW); }
+        for (int s = 0; s < APPLY_STAGES; ++s) mbar_init(&stage_bar[s], 1);
         fence_mbar_init();
     }
     fence_proxy_async();
@@ -244,7 +255,86 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
     const int nchunks = (stotal + CH - 1) >> CS;
     double dsum = 0.0;
 
-    if (warp == NW) {
+    if (FUSEP && warp >= NW) {
+        // ---------------- producers + converters: warp NW + c takes the staging chunks j = c (mod NCV) --------
+        // Each converter warp owns 4 staging slots, issues its own bulk copies (r and p of a chunk of 16 rows
+        // complete on one mbarrier), converts the chunk into the ring and arrives on the ring chunk's barrier.
+        const int cw = warp - NW, NCV = a.nconv;
+        constexpr int SR = 16, SRS = 4, SLOTS = 4;
+        const int nsub = (stotal + SR - 1) >> SRS;
+        if (nchunks > 0 && cw < NCV) {
+            const uint32_t RB = APPLY_W * 8;
+            double* stage = sm + (size_t)(R + SP) * APPLY_W + (size_t)cw * SLOTS * 2 * SR * APPLY_W;
+            uint64_t* sbar = stage_bar + cw * SLOTS;
+            const double* rsrc = a.r2 + g0 * APPLY_W;
+            const double* psrc = a.x + g0 * APPLY_W;
+            double* pdst = a.pout + g0 * APPLY_W + lane;
+            const double beta = a.red.scalars[S_BETA];
+            // rows of the stream this CTA owns (the halo planes belong to its neighbours, who store them)
+            const int own0 = (int)(u0 * nf + plane_off<DIM>(m, t0) - g0);
+            const int own1 = (int)(t1 == 0 ? u1 * nf - g0 : u1 * nf + plane_off<DIM>(m, t1) - g0);
+            auto issue = [&](int j, int slot) {
+                const int s0 = j << SRS, n = min(SR, stotal - s0);
+                double* dst = stage + (size_t)slot * 2 * SR * APPLY_W;
+                mbar_expect_tx(&sbar[slot], 2u * (uint32_t)n * RB);
+                bulk_g2s(dst, rsrc + (int64_t)s0 * APPLY_W, (uint32_t)n * RB, &sbar[slot]);
+                bulk_g2s(dst + SR * APPLY_W, psrc + (int64_t)s0 * APPLY_W, (uint32_t)n * RB, &sbar[slot]);
+            };
+            if (lane == 0)
+                for (int q = 0; q < SLOTS; ++q)
+                    if (cw + q * NCV < nsub) issue(cw + q * NCV, q);
+            int confirmed = 0, it = 0;
+            int phys = (cw << SRS) % R;                       // ring row of the chunk's first row
+            const int pstep = (NCV << SRS) % R;
+            for (int j = cw; j < nsub; j += NCV, ++it) {
+                const int s0 = j << SRS, n = min(SR, stotal - s0), slot = it & (SLOTS - 1);
+                mbar_wait(&sbar[slot], (unsigned)(it >> 2) & 1u);
+                const int old = s0 + n - 1 - R;
+                if (old >= 0) {
+                    const int c_old = old >> CS;
+                    while (confirmed <= c_old) {
+                        mbar_wait(&empty_bar[confirmed & (APPLY_Q - 1)], (confirmed >> APPLY_QS) & 1u);
+                        ++confirmed;
+                    }
+                }
+                const double* sr = stage + (size_t)slot * 2 * SR * APPLY_W + lane;
+                const double* sp = sr + SR * APPLY_W;
+                if (n == SR && phys >= SP && phys + SR <= R && s0 >= own0 && s0 + SR <= own1) {
+                    // common case: a whole slot, no ring wrap, no mirror rows, every row owned -- fully unrolled
+                    double* dr = sm + phys * APPLY_W + lane;
+                    double* dg = pdst + (int64_t)s0 * APPLY_W;
+                    double v[SR];
+#pragma unroll
+                    for (int q = 0; q < SR; ++q) v[q] = fma(beta, sp[q * APPLY_W], sr[q * APPLY_W]);
+#pragma unroll
+                    for (int q = 0; q < SR; ++q) { dr[q * APPLY_W] = v[q]; dg[q * APPLY_W] = v[q]; }
+                } else {
+                    for (int q = 0; q < n; ++q) {
+                        const double v = fma(beta, sp[q * APPLY_W], sr[q * APPLY_W]);
+                        int ph = phys + q;
+                        if (ph >= R) ph -= R;
+                        sm[ph * APPLY_W + lane] = v;
+                        if (ph < SP) sm[(R + ph) * APPLY_W + lane] = v;
+                        const int srow = s0 + q;
+                        if (srow >= own0 && srow < own1) pdst[(int64_t)srow * APPLY_W] = v;
+                    }
+                }
+                phys += pstep;
+                if (phys >= R) phys -= R;
+                __syncwarp();
+                if (lane == 0) {
+                    fence_proxy_async();                       // the slot's generic reads are done before TMA rewrites it
+                    if (j + SLOTS * NCV < nsub) issue(j + SLOTS * NCV, slot);
+                    uint64_t* bar = &full_bar[(s0 >> CS) & (APPLY_Q - 1)];
+                    mbar_arrive(bar);
+                    if (j == nsub - 1) {                       // the last ring chunk may hold fewer sub-chunks
+                        const int have = ((stotal - ((s0 >> CS) << CS)) + SR - 1) >> SRS;
+                        for (int q = have; q < (1 << (CS - SRS)); ++q) mbar_arrive(bar);
+                    }
+                }
+            }
+        }
+    } else if (warp == NW) {
         // ---------------- producer ----------------
         if (lane == 0 && nchunks > 0) {
             const uint32_t RB = APPLY_W * 8;
@@ -393,9 +483,12 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
                 if (p >= R) p -= R;
                 return p;
             };
-            int qc = ring(rc), qm[Sweep<DIM>::NP], qp[Sweep<DIM>::NP];
+            int qc = 0, qm[Sweep<DIM>::NP], qp[Sweep<DIM>::NP];
+            if constexpr (DIM == 3) {
+                qc = ring(rc);
 #pragma unroll
-            for (int q = 0; q < Sweep<DIM>::NP; ++q) { qm[q] = ring(rm[q]); qp[q] = ring(rp[q]); }
+                for (int q = 0; q < Sweep<DIM>::NP; ++q) { qm[q] = ring(rm[q]); qp[q] = ring(rp[q]); }
+            }
             out.yl = ybase + (int64_t)rc * APPLY_W;
             out.tl = MODE == APPLY_AX ? nullptr : tbase + (int64_t)rc * APPLY_W;
             if constexpr (DIM == 3) {
@@ -431,9 +524,12 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
                     li += step_lines;
                 }
             } else {
-                g.bc = qc * APPLY_W + el;
-                g.bm[0] = qm[0] * APPLY_W + el;
-                g.bp[0] = qp[0] * APPLY_W + el;
+                // ring rows are taken at node kb = k0 - 1 of each line (the first node the segment reads), so that
+                // a segment never runs more than SEG + 2 rows past its base: the mirror behind the ring stays small
+                const int kb = g.k0 > 0 ? g.k0 - 1 : 0;
+                g.bc = (ring(rc + kb) - kb) * APPLY_W + el;
+                g.bm[0] = (ring(rm[0] + kb) - kb) * APPLY_W + el;
+                g.bp[0] = (ring(rp[0] + kb) - kb) * APPLY_W + el;
                 out.begin(g.k0, g.k1);
                 run_line2(op, a.T, mem, APPLY_W, g, t, out);
             }
@@ -454,7 +550,7 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
 }
 
 // ring size and launch shape of one level
-ApplyConfig make_apply_config(int dim, int m, int nf, int W) {
+ApplyConfig make_apply_config(int dim, int m, int nf, int W, bool fused) {
     ApplyConfig c{};
     auto envi = [](const char* name, int dflt) {
         const char* v = getenv(name);
@@ -463,9 +559,14 @@ ApplyConfig make_apply_config(int dim, int m, int nf, int W) {
     c.nwarps = std::max(1, std::min(15, envi("HMG_APPLY_WARPS", 15)));
     c.ctas_per_sm = 1;
     c.seg = dim == 2 ? std::max(2, std::min(8, envi("HMG_APPLY_SEG_SHIFT", 5))) : 30;
-    c.spill_rows = m + 3;
+    c.spill_rows = dim == 2 ? (1 << c.seg) + 3 : m + 3;       // rows a task may run past the base of a line
     const int rowb = W * 8;
-    const int max_rows = std::min((227 * 1024 - 2048) / rowb - c.spill_rows, envi("HMG_APPLY_RING_ROWS", 1 << 20));
+    // fused p-update: staging slots of 16 rows of r and p each; enough of them to keep ~48 KB in flight
+    c.stage_shift = 4;
+    const int nconv = std::max(1, std::min(4, envi("HMG_APPLY_CONVERTERS", 2)));     // converter warps, 4 slots each
+    c.nstage = fused ? 4 * nconv : 0;
+    const int stage_bytes = c.nstage * 2 * (1 << c.stage_shift) * rowb;
+    const int max_rows = std::min((227 * 1024 - 2048 - stage_bytes) / rowb - c.spill_rows, envi("HMG_APPLY_RING_ROWS", 1 << 20));
     // the largest row window of a task, for `run` lines per task (3D)
     auto window = [&](int run) {
         int w = 1;
@@ -505,19 +606,21 @@ ApplyConfig make_apply_config(int dim, int m, int nf, int W) {
     const int min_rows = window(c.run) + 2 * CH;
     int R = std::min(max_rows, (APPLY_Q - 2) * CH);
     c.ring_rows = R >= min_rows ? R : -1;        // -1: the level does not fit (refused by the launcher)
-    c.smem_bytes = (size_t)(std::max(R, 1) + c.spill_rows) * rowb;
+    c.smem_bytes = (size_t)(std::max(R, 1) + c.spill_rows) * rowb + stage_bytes;
+    if (fused) c.nwarps = std::min(c.nwarps, 16 - nconv);
     (void)nf;
     return c;
 }
 
-template <int DIM, int W, int MODE, bool DOT>
+template <int DIM, int W, int MODE, bool DOT, bool FUSEP = false>
 static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
     static size_t configured = 0;
     static int sms = 0;
-    auto kern = apply_kernel<DIM, W, MODE, DOT>;
-    if (a.cfg.smem_bytes > configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.cfg.smem_bytes) != cudaSuccess) return 0;
-        configured = a.cfg.smem_bytes;
+    auto kern = apply_kernel<DIM, W, MODE, DOT, FUSEP>;
+    const ApplyConfig& cfg = FUSEP ? a.cfg_fused : a.cfg;
+    if (cfg.smem_bytes > configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes) != cudaSuccess) return 0;
+        configured = cfg.smem_bytes;
     }
     if (sms == 0) {
         int dev = 0;
@@ -533,9 +636,10 @@ static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
     p.sa = MODE == APPLY_MULADD ? a.alpha : 1.0;
     p.lambda = a.lambda;
     p.m = a.L.m; p.nf = a.L.nf;
-    p.nwarps = a.cfg.nwarps; p.R = a.cfg.ring_rows; p.SP = a.cfg.spill_rows; p.cs = a.cfg.chunk_shift;
-    p.seg_shift = a.cfg.seg;
-    p.run = a.cfg.run;
+    p.nwarps = cfg.nwarps; p.R = cfg.ring_rows; p.SP = cfg.spill_rows; p.cs = cfg.chunk_shift;
+    p.seg_shift = cfg.seg;
+    p.run = cfg.run;
+    p.r2 = a.r2; p.pout = a.pout; p.sr_shift = cfg.stage_shift; p.nstage = cfg.nstage; p.nconv = cfg.nstage / 4;
     p.dot_post = a.dot_post;
     p.red = a.red;
     // more CTAs than SMs when the problem is large: the hardware hands the next CTA to whichever SM finishes
@@ -545,13 +649,17 @@ static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
     static const int over_env = getenv("HMG_APPLY_OVERSUB") ? atoi(getenv("HMG_APPLY_OVERSUB")) : 0;
     // (measured: + 6 % in 2D; in 3D the extra halo planes and pipeline fills cost more than they gain)
     const int64_t over = over_env > 0 ? over_env : (DIM == 2 ? std::max<int64_t>(1, std::min<int64_t>(8, rows_per_sm / 8192)) : 1);
-    int64_t grid = std::min<int64_t>((int64_t)sms * a.cfg.ctas_per_sm * over, planes);
+    int64_t grid = std::min<int64_t>((int64_t)sms * cfg.ctas_per_sm * over, planes);
     if (DOT) grid = std::min<int64_t>(grid, a.red.max_blocks);
-    kern<<<(unsigned)grid, (a.cfg.nwarps + 1) * 32, a.cfg.smem_bytes, st>>>(p);
+    kern<<<(unsigned)grid, (cfg.nwarps + (FUSEP ? cfg.nstage / 4 : 1)) * 32, cfg.smem_bytes, st>>>(p);
     return 1;
 }
 
 template <int DIM, int W> static int launch_apply_d(const ApplyArgs& a, cudaStream_t st) {
+    if (a.mode == APPLY_AX && a.r2 != nullptr) {
+        if (W != 32 || a.dot_post < 0 || a.cfg_fused.ring_rows <= 0) return -1;
+        return launch_apply_t<DIM, 32, APPLY_AX, true, true>(a, st);
+    }
     if (a.mode == APPLY_AX) return a.dot_post >= 0 ? launch_apply_t<DIM, W, APPLY_AX, true>(a, st) : launch_apply_t<DIM, W, APPLY_AX, false>(a, st);
     if (a.mode == APPLY_RESIDUAL) return a.dot_post >= 0 ? launch_apply_t<DIM, W, APPLY_RESIDUAL, true>(a, st) : launch_apply_t<DIM, W, APPLY_RESIDUAL, false>(a, st);
     return launch_apply_t<DIM, W, APPLY_MULADD, false>(a, st);

@@ -65,6 +65,7 @@ struct ApplyConfig {
     int chunk_shift;   // log2(rows per TMA chunk)
     int seg;           // 2D: log2(nodes per task) (a line is split into segments); 3D: unused
     int run;           // 3D: consecutive lines of a plane per task
+    int stage_shift, nstage;   // fused p-update: log2(rows per staging slot), staging slots (0: not fused)
     int ctas_per_sm;
     size_t smem_bytes;
 };
@@ -72,6 +73,9 @@ struct ApplyConfig {
 struct ApplyArgs {
     LevelView L;
     ApplyConfig cfg;
+    ApplyConfig cfg_fused;     // launch shape of the fused p-update variant (ring_rows <= 0: not available)
+    const double* r2 = nullptr;   // fused p-update: input is r2 + beta * x (x = old p), p' goes to pout
+    double* pout = nullptr;
     int64_t nunits;
     const double* tab;         // host pointer: StencilTab<DIM> of the level (copied into the parameter block)
     const double* coef;        // [nunits][CS][W]  |J| P (upper triangle) and |J|, element-interleaved
@@ -90,7 +94,7 @@ struct ApplyArgs {
 
 // launchers (all asynchronous on `st`); return the number of kernels launched
 int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st);
-ApplyConfig make_apply_config(int dim, int m, int nf, int W);
+ApplyConfig make_apply_config(int dim, int m, int nf, int W, bool fused = false);
 int launch_interface_sum(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
 int launch_interface_sum_sq(int dim, const LevelView& L, const TopoView& T, double* x, const Reducer& R, int post, cudaStream_t st);
 int launch_cut_unpack_sq(int dim, int kind, const LevelView& L, const CutView& C, int64_t buf_base, double* x, double* buf,
