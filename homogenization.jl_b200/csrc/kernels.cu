@@ -144,7 +144,7 @@ template <int DIM> struct ApplyParams {
     // FUSEP: x = old p, r2 = r, pout = the other p buffer, staging of 2^sr_shift rows x nstage slots
     const double* r2;
     double* pout;
-    int sr_shift, nstage, nconv;
+    int sr_shift, nstage, nconv, slot_shift;
 };
 
 template <int DIM> __device__ __forceinline__ int plane_off(int m, int t) { return DIM == 3 ? lat_off3(m, t) : lat_off2(m, t); }
@@ -260,7 +260,8 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
         // Each converter warp owns 4 staging slots, issues its own bulk copies (r and p of a chunk of 16 rows
         // complete on one mbarrier), converts the chunk into the ring and arrives on the ring chunk's barrier.
         const int cw = warp - NW, NCV = a.nconv;
-        constexpr int SR = 16, SRS = 4, SLOTS = 4;
+        constexpr int SR = 16, SRS = 4;
+        const int SLS = a.slot_shift, SLOTS = 1 << SLS;      // staging slots per converter warp
         const int nsub = (stotal + SR - 1) >> SRS;
         if (nchunks > 0 && cw < NCV) {
             const uint32_t RB = APPLY_W * 8;
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
             const int pstep = (NCV << SRS) % R;
             for (int j = cw; j < nsub; j += NCV, ++it) {
                 const int s0 = j << SRS, n = min(SR, stotal - s0), slot = it & (SLOTS - 1);
-                mbar_wait(&sbar[slot], (unsigned)(it >> 2) & 1u);
+                mbar_wait(&sbar[slot], (unsigned)(it >> SLS) & 1u);
                 const int old = s0 + n - 1 - R;
                 if (old >= 0) {
                     const int c_old = old >> CS;
@@ -550,7 +551,21 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
 }
 
 // ring size and launch shape of one level
+static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool fused, int slot_shift);
 ApplyConfig make_apply_config(int dim, int m, int nf, int W, bool fused) {
+    if (!fused) return make_apply_config_slots(dim, m, nf, W, false, 2);
+    // fused p-update: prefer 4 staging slots per converter warp, fall back to 2 where the ring is tight (3D level 6)
+    const char* v = getenv("HMG_APPLY_SLOT_SHIFT");
+    for (int ss : {2, 1}) {
+        if (v && atoi(v) != ss) continue;
+        const ApplyConfig c = make_apply_config_slots(dim, m, nf, W, true, ss);
+        if (c.ring_rows > 0) return c;
+    }
+    ApplyConfig none{};
+    none.ring_rows = -1;
+    return none;
+}
+static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool fused, int slot_shift) {
     ApplyConfig c{};
     auto envi = [](const char* name, int dflt) {
         const char* v = getenv(name);
@@ -563,8 +578,10 @@ ApplyConfig make_apply_config(int dim, int m, int nf, int W, bool fused) {
     const int rowb = W * 8;
     // fused p-update: staging slots of 16 rows of r and p each; enough of them to keep ~48 KB in flight
     c.stage_shift = 4;
-    const int nconv = std::max(1, std::min(4, envi("HMG_APPLY_CONVERTERS", 2)));     // converter warps, 4 slots each
-    c.nstage = fused ? 4 * nconv : 0;
+    // fused p-update: converter warps with 2^slot_shift staging slots of 16 rows of r and p each
+    c.nconv = fused ? std::max(1, std::min(4, envi("HMG_APPLY_CONVERTERS", 2))) : 0;
+    c.slot_shift = slot_shift;
+    c.nstage = c.nconv << c.slot_shift;
     const int stage_bytes = c.nstage * 2 * (1 << c.stage_shift) * rowb;
     const int max_rows = std::min((227 * 1024 - 2048 - stage_bytes) / rowb - c.spill_rows, envi("HMG_APPLY_RING_ROWS", 1 << 20));
     // the largest row window of a task, for `run` lines per task (3D)
@@ -607,7 +624,7 @@ ApplyConfig make_apply_config(int dim, int m, int nf, int W, bool fused) {
     int R = std::min(max_rows, (APPLY_Q - 2) * CH);
     c.ring_rows = R >= min_rows ? R : -1;        // -1: the level does not fit (refused by the launcher)
     c.smem_bytes = (size_t)(std::max(R, 1) + c.spill_rows) * rowb + stage_bytes;
-    if (fused) c.nwarps = std::min(c.nwarps, 16 - nconv);
+    if (fused) c.nwarps = std::min(c.nwarps, 16 - c.nconv);
     (void)nf;
     return c;
 }
@@ -639,7 +656,7 @@ static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
     p.nwarps = cfg.nwarps; p.R = cfg.ring_rows; p.SP = cfg.spill_rows; p.cs = cfg.chunk_shift;
     p.seg_shift = cfg.seg;
     p.run = cfg.run;
-    p.r2 = a.r2; p.pout = a.pout; p.sr_shift = cfg.stage_shift; p.nstage = cfg.nstage; p.nconv = cfg.nstage / 4;
+    p.r2 = a.r2; p.pout = a.pout; p.sr_shift = cfg.stage_shift; p.nstage = cfg.nstage; p.nconv = cfg.nconv; p.slot_shift = cfg.slot_shift;
     p.dot_post = a.dot_post;
     p.red = a.red;
     // more CTAs than SMs when the problem is large: the hardware hands the next CTA to whichever SM finishes
@@ -651,7 +668,7 @@ static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
     const int64_t over = over_env > 0 ? over_env : (DIM == 2 ? std::max<int64_t>(1, std::min<int64_t>(8, rows_per_sm / 8192)) : 1);
     int64_t grid = std::min<int64_t>((int64_t)sms * cfg.ctas_per_sm * over, planes);
     if (DOT) grid = std::min<int64_t>(grid, a.red.max_blocks);
-    kern<<<(unsigned)grid, (cfg.nwarps + (FUSEP ? cfg.nstage / 4 : 1)) * 32, cfg.smem_bytes, st>>>(p);
+    kern<<<(unsigned)grid, (cfg.nwarps + (FUSEP ? cfg.nconv : 1)) * 32, cfg.smem_bytes, st>>>(p);
     return 1;
 }
 

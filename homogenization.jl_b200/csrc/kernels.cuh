@@ -66,6 +66,7 @@ struct ApplyConfig {
     int seg;           // 2D: log2(nodes per task) (a line is split into segments); 3D: unused
     int run;           // 3D: consecutive lines of a plane per task
     int stage_shift, nstage;   // fused p-update: log2(rows per staging slot), staging slots (0: not fused)
+    int nconv, slot_shift;     // ... converter warps, log2(staging slots per converter warp)
     int ctas_per_sm;
     size_t smem_bytes;
 };
