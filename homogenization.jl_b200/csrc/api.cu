@@ -82,6 +82,7 @@ struct LevelDev {
     LevelView view{};
     ApplyConfig cfg{};
     ApplyConfig cfg_fused{};      // launch shape of the fused p-update + product (ring_rows <= 0: does not fit)
+    ApplyConfig cfg_rhs{};        // launch shape of the residual / mul! variants
     double* p2 = nullptr;         // the other search-direction buffer of the fused p-update (lazy)
     std::vector<double> tab;      // StencilTab of the level (travels in the kernel parameter block)
     int32_t* hier2lat = nullptr;
@@ -284,6 +285,8 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const 
         L.hier2lat = c->dupload(R.hier2lat);
         L.cfg = make_apply_config(dim, R.m, R.nf, c->W);
         HMG_CHECK(L.cfg.ring_rows > 0, "a level of this hierarchy does not fit the shared-memory ring of the apply kernel");
+        L.cfg_rhs = make_apply_config(dim, R.m, R.nf, c->W, false, true);
+        if (L.cfg_rhs.ring_rows <= 0) L.cfg_rhs = L.cfg;
         L.cfg_fused = make_apply_config(dim, R.m, R.nf, c->W, true);
         if (c->W != 32 || (getenv("HMG_FUSE_P") && atoi(getenv("HMG_FUSE_P")) == 0)) L.cfg_fused.ring_rows = -1;
         L.tab = R.gi;
@@ -371,6 +374,7 @@ void do_apply(hmg_ctx* c, int l, int mode, double alpha, const double* x, double
     a.L = L.view;
     a.cfg = L.cfg;
     a.cfg_fused = L.cfg_fused;
+    a.cfg_rhs = L.cfg_rhs;
     a.nunits = c->nunits;
     a.tab = L.tab.data();
     a.coef = c->elem_coef;
@@ -456,7 +460,7 @@ void do_fused_direction_product(hmg_ctx* c, int l) {
     LevelDev& L = c->level(l);
     if (!L.p2) L.p2 = c->dalloc<double>((size_t)c->nstored(l));
     ApplyArgs a;
-    a.L = L.view; a.cfg = L.cfg; a.cfg_fused = L.cfg_fused;
+    a.L = L.view; a.cfg = L.cfg; a.cfg_fused = L.cfg_fused; a.cfg_rhs = L.cfg_rhs;
     a.nunits = c->nunits; a.tab = L.tab.data();
     a.coef = c->elem_coef; a.cmask = c->cmask; a.mult = c->mult;
     a.x = c->vecp(l, HMG_P); a.r2 = c->vecp(l, HMG_R); a.pout = L.p2;
@@ -1005,7 +1009,7 @@ void mass_apply(hmg_ctx* c, const double* coef, double lambda, const double* x, 
     LevelDev& L = c->level(l);
     check_launch(c, launch_fill(y, 0.0, c->nstored(l), c->stream));
     ApplyArgs a;
-    a.L = L.view; a.cfg = L.cfg; a.nunits = c->nunits; a.tab = L.tab.data();
+    a.L = L.view; a.cfg = L.cfg; a.cfg_rhs = L.cfg_rhs; a.nunits = c->nunits; a.tab = L.tab.data();
     a.coef = coef; a.cmask = c->cmask; a.mult = c->mult;
     a.x = x; a.y = y; a.b = nullptr;
     a.alpha = 1.0; a.lambda = lambda; a.mode = APPLY_MULADD; a.dot_post = -1; a.red = c->red;

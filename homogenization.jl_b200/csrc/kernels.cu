@@ -551,9 +551,9 @@ __global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_const
 }
 
 // ring size and launch shape of one level
-static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool fused, int slot_shift);
-ApplyConfig make_apply_config(int dim, int m, int nf, int W, bool fused) {
-    if (!fused) return make_apply_config_slots(dim, m, nf, W, false, 2);
+static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool fused, int slot_shift, bool streaming_rhs = false);
+ApplyConfig make_apply_config(int dim, int m, int nf, int W, bool fused, bool streaming_rhs) {
+    if (!fused) return make_apply_config_slots(dim, m, nf, W, false, 2, streaming_rhs);
     // fused p-update: prefer 4 staging slots per converter warp, fall back to 2 where the ring is tight (3D level 6)
     const char* v = getenv("HMG_APPLY_SLOT_SHIFT");
     for (int ss : {2, 1}) {
@@ -565,7 +565,7 @@ ApplyConfig make_apply_config(int dim, int m, int nf, int W, bool fused) {
     none.ring_rows = -1;
     return none;
 }
-static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool fused, int slot_shift) {
+static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool fused, int slot_shift, bool streaming_rhs) {
     ApplyConfig c{};
     auto envi = [](const char* name, int dflt) {
         const char* v = getenv(name);
@@ -605,18 +605,29 @@ static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool f
     };
     // prefer long runs (per-task overhead) and large chunks (every warp observes every chunk), as long as
     // the ring keeps `slack` rows of prefetch beyond the window: bytes in flight hide the HBM latency
-    const int slack = 160;
+    // The variants that also stream b / y straight from L2 (residual, mul!) prefer large chunks -- the producer's
+    // L2 prefetch runs one chunk ahead -- and short runs (measured on B200).
+    const int slack = streaming_rhs ? 96 : 160;
     const int run_env = envi("HMG_APPLY_RUN", 0), cs_env = envi("HMG_APPLY_CHUNK_SHIFT", 0);
     c.run = 1; c.chunk_shift = 5;
     bool found = false;
-    for (int run : {4, 2, 1}) {
-        if (dim == 2 && run != 1) continue;
-        if (run_env && run != run_env) continue;
+    auto fits = [&](int run, int cs) {
+        if (dim == 2 && run != 1) return false;
+        if ((run_env && run != run_env) || (cs_env && cs != cs_env)) return false;
+        return window(run) + 2 * (1 << cs) + slack <= max_rows;
+    };
+    if (streaming_rhs) {
         for (int cs : {7, 6, 5}) {
-            if (cs_env && cs != cs_env) continue;
-            if (window(run) + 2 * (1 << cs) + slack <= max_rows) { c.run = run; c.chunk_shift = cs; found = true; break; }
+            for (int run : {2, 1})
+                if (fits(run, cs)) { c.run = run; c.chunk_shift = cs; found = true; break; }
+            if (found) break;
         }
-        if (found) break;
+    } else {
+        for (int run : {4, 2, 1}) {
+            for (int cs : {7, 6, 5})
+                if (fits(run, cs)) { c.run = run; c.chunk_shift = cs; found = true; break; }
+            if (found) break;
+        }
     }
     if (!found) { c.run = run_env ? run_env : 1; c.chunk_shift = cs_env ? cs_env : 5; }
     const int CH = 1 << c.chunk_shift;
@@ -634,7 +645,7 @@ static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
     static size_t configured = 0;
     static int sms = 0;
     auto kern = apply_kernel<DIM, W, MODE, DOT, FUSEP>;
-    const ApplyConfig& cfg = FUSEP ? a.cfg_fused : a.cfg;
+    const ApplyConfig& cfg = FUSEP ? a.cfg_fused : (MODE == APPLY_AX ? a.cfg : a.cfg_rhs);
     if (cfg.smem_bytes > configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes) != cudaSuccess) return 0;
         configured = cfg.smem_bytes;

@@ -75,6 +75,7 @@ struct ApplyArgs {
     LevelView L;
     ApplyConfig cfg;
     ApplyConfig cfg_fused;     // launch shape of the fused p-update variant (ring_rows <= 0: not available)
+    ApplyConfig cfg_rhs;       // launch shape of the residual / mul! variants
     const double* r2 = nullptr;   // fused p-update: input is r2 + beta * x (x = old p), p' goes to pout
     double* pout = nullptr;
     int64_t nunits;
@@ -95,7 +96,7 @@ struct ApplyArgs {
 
 // launchers (all asynchronous on `st`); return the number of kernels launched
 int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st);
-ApplyConfig make_apply_config(int dim, int m, int nf, int W, bool fused = false);
+ApplyConfig make_apply_config(int dim, int m, int nf, int W, bool fused = false, bool streaming_rhs = false);
 int launch_interface_sum(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
 int launch_interface_sum_sq(int dim, const LevelView& L, const TopoView& T, double* x, const Reducer& R, int post, cudaStream_t st);
 int launch_cut_unpack_sq(int dim, int kind, const LevelView& L, const CutView& C, int64_t buf_base, double* x, double* buf,
