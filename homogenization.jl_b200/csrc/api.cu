@@ -1,5 +1,6 @@
 // C ABI of libhmg_b200 (see include/hmg.h): context, state vectors, orchestration of the V-cycle.
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <algorithm>
 #include <map>
@@ -289,6 +290,11 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const 
         if (L.cfg_rhs.ring_rows <= 0) L.cfg_rhs = L.cfg;
         L.cfg_fused = make_apply_config(dim, R.m, R.nf, c->W, true);
         if (c->W != 32 || (getenv("HMG_FUSE_P") && atoi(getenv("HMG_FUSE_P")) == 0)) L.cfg_fused.ring_rows = -1;
+        if (getenv("HMG_DEBUG_CFG"))
+            for (const ApplyConfig* q : {&L.cfg, &L.cfg_rhs, &L.cfg_fused})
+                fprintf(stderr, "hmg: level %d (m=%d) %s: warps %d ring %d spill %d chunk %d run %d seg %d conv %d slots %d smem %zu\n", l, R.m,
+                        q == &L.cfg ? "product " : (q == &L.cfg_rhs ? "residual" : "fused   "), q->nwarps, q->ring_rows, q->spill_rows,
+                        1 << q->chunk_shift, q->run, q->seg, q->nconv, q->nconv ? 1 << q->slot_shift : 0, q->smem_bytes);
         L.tab = R.gi;
         L.tab.insert(L.tab.end(), R.gc.begin(), R.gc.end());
         L.tab.insert(L.tab.end(), R.ge.begin(), R.ge.end());

@@ -607,14 +607,15 @@ static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool f
     // the ring keeps `slack` rows of prefetch beyond the window: bytes in flight hide the HBM latency
     // The variants that also stream b / y straight from L2 (residual, mul!) prefer large chunks -- the producer's
     // L2 prefetch runs one chunk ahead -- and short runs (measured on B200).
-    const int slack = streaming_rhs ? 96 : 160;
+    const int slack = streaming_rhs ? 48 : 160;
     const int run_env = envi("HMG_APPLY_RUN", 0), cs_env = envi("HMG_APPLY_CHUNK_SHIFT", 0);
     c.run = 1; c.chunk_shift = 5;
     bool found = false;
     auto fits = [&](int run, int cs) {
         if (dim == 2 && run != 1) return false;
         if ((run_env && run != run_env) || (cs_env && cs != cs_env)) return false;
-        return window(run) + 2 * (1 << cs) + slack <= max_rows;
+        // (with a tight ring, runs of two lines cost the residual variant 30 % at 3D level 6)
+        return window(run) + 2 * (1 << cs) + slack + (streaming_rhs && run > 1 ? 200 : 0) <= max_rows;
     };
     if (streaming_rhs) {
         for (int cs : {7, 6, 5}) {
@@ -633,6 +634,8 @@ static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool f
     const int CH = 1 << c.chunk_shift;
     const int min_rows = window(c.run) + 2 * CH;
     int R = std::min(max_rows, (APPLY_Q - 2) * CH);
+    // the variants that read b / y straight through L1 leave the rest of the SM's memory to the cache
+    if (streaming_rhs && !getenv("HMG_APPLY_RING_ROWS")) R = std::min(R, min_rows + 200);
     c.ring_rows = R >= min_rows ? R : -1;        // -1: the level does not fit (refused by the launcher)
     c.smem_bytes = (size_t)(std::max(R, 1) + c.spill_rows) * rowb + stage_bytes;
     if (fused) c.nwarps = std::min(c.nwarps, 16 - c.nconv);
