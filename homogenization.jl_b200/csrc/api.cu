@@ -402,11 +402,10 @@ void do_cut_exchange(hmg_ctx* c, int l, double* x) {
     if (c->nranks == 1 || slots == 0) return;
     const LevelView& V = c->level(l).view;
     double* send = c->cut_send[l - 1];
-    for (int kind = 0; kind < 3; ++kind)
-        check_launch(c, launch_cut(c->dim, CUT_PACK, kind, V, c->cutv[kind], c->cut_base(l, kind), x, send, c->stream));
+    const int64_t base[3] = {c->cut_base(l, 0), c->cut_base(l, 1), c->cut_base(l, 2)};
+    check_launch(c, launch_cut(c->dim, CUT_PACK, V, c->cutv, base, x, send, false, c->red, c->stream));
     NCCL_OK(nccl().AllReduce(send, c->cut_recv, (size_t)slots, ncclDouble, ncclSum, c->comm, c->stream));
-    for (int kind = 0; kind < 3; ++kind)
-        check_launch(c, launch_cut(c->dim, CUT_UNPACK, kind, V, c->cutv[kind], c->cut_base(l, kind), x, c->cut_recv, c->stream));
+    check_launch(c, launch_cut(c->dim, CUT_UNPACK, V, c->cutv, base, x, c->cut_recv, false, c->red, c->stream));
 }
 void do_broadcast(hmg_ctx* c, int l, double* x) {
     check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->stream));
@@ -414,9 +413,10 @@ void do_broadcast(hmg_ctx* c, int l, double* x) {
 }
 void do_zero_all_but_one(hmg_ctx* c, int l, double* x) {
     check_launch(c, launch_zero_all_but_one(c->dim, c->level(l).view, c->tview, x, c->stream));
-    if (c->nranks > 1)
-        for (int kind = 0; kind < 3; ++kind)
-            check_launch(c, launch_cut(c->dim, CUT_ZERO_BUT_FIRST, kind, c->level(l).view, c->cutv[kind], 0, x, nullptr, c->stream));
+    if (c->nranks > 1) {
+        const int64_t base[3] = {0, 0, 0};
+        check_launch(c, launch_cut(c->dim, CUT_ZERO_BUT_FIRST, c->level(l).view, c->cutv, base, x, nullptr, false, c->red, c->stream));
+    }
 }
 // post-op of a reduction kernel: on one GPU the kernel's last block derives the CG scalars itself; with
 // several ranks the kernel stores the local sum in S_TMP, the sums are all-reduced and a one-thread
@@ -451,12 +451,10 @@ void do_broadcast_rho(hmg_ctx* c, int l, double* r) {
     const int64_t slots = c->cut_slots(l);
     if (slots > 0) {
         double* send = c->cut_send[l - 1];
-        for (int kind = 0; kind < 3; ++kind)
-            check_launch(c, launch_cut(c->dim, CUT_PACK, kind, V, c->cutv[kind], c->cut_base(l, kind), r, send, c->stream));
+        const int64_t base[3] = {c->cut_base(l, 0), c->cut_base(l, 1), c->cut_base(l, 2)};
+        check_launch(c, launch_cut(c->dim, CUT_PACK, V, c->cutv, base, r, send, false, c->red, c->stream));
         NCCL_OK(nccl().AllReduce(send, c->cut_recv, (size_t)slots, ncclDouble, ncclSum, c->comm, c->stream));
-        for (int kind = 0; kind < 3; ++kind)
-            check_launch(c, launch_cut_unpack_sq(c->dim, kind, V, c->cutv[kind], c->cut_base(l, kind), r, c->cut_recv, c->red,
-                                                 c->stream));
+        check_launch(c, launch_cut(c->dim, CUT_UNPACK, V, c->cutv, base, r, c->cut_recv, true, c->red, c->stream));
     }
     finish_reduction(c, POST_RHO, S_TMP);
 }

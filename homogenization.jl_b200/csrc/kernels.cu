@@ -846,22 +846,32 @@ int launch_zero_all_but_one(int dim, const LevelView& L, const TopoView& T, doub
 
 // Cut cells (owners on several ranks): pack the partial sum over the local owners into the level's
 // packed buffer / write the all-reduced total back to the local owners / zero all but the globally
-// first owner.  One thread per (cell, paired node).
+// first owner.  One thread per (cell, paired node); faces, edges and vertices in ONE launch.
+struct CutAll {
+    CutView kind[3];
+    int npc[3];               // paired nodes per cell
+    int64_t base[3];          // first slot of the kind in the packed buffer
+    const uint16_t* tab[3];   // packed node index of the t-th paired node of every local cell
+    int64_t items[4];         // prefix sums of ncells * npc
+};
 template <int OP, bool SQ>
-__global__ void __launch_bounds__(256) cut_kernel(const LevelView L, const CutView C, int npc, const uint16_t* __restrict__ tab,
-                                                  int64_t buf_base, double* __restrict__ x, double* __restrict__ buf, const Reducer R) {
-    const int64_t total = C.ncells * npc;
+__global__ void __launch_bounds__(256) cut_kernel(const LevelView L, const CutAll A, double* __restrict__ x, double* __restrict__ buf,
+                                                  const Reducer R) {
     double sq = 0.0;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t cell = t / npc;
-        const int k = (int)(t - cell * npc);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < A.items[3]; t += (int64_t)gridDim.x * blockDim.x) {
+        const int kd = t < A.items[1] ? 0 : (t < A.items[2] ? 1 : 2);
+        const CutView& C = A.kind[kd];
+        const int npc = A.npc[kd];
+        const int64_t q = t - A.items[kd];
+        const int64_t cell = q / npc;
+        const int k = (int)(q - cell * npc);
         const int64_t b = C.off[cell], en = C.off[cell + 1];
-        const int64_t s = buf_base + C.slot[cell] * npc + k;
+        const int64_t s = A.base[kd] + C.slot[cell] * npc + k;
         double acc = OP == CUT_UNPACK ? buf[s] : 0.0;
         for (int64_t o = b; o < en; ++o) {
             const int32_t id = C.own[o];
             const int64_t el = id >> 3;
-            double* ptr = x + ((el >> L.wshift) * (int64_t)L.nf + __ldg(tab + (id & 7) * npc + k)) * L.W + (el & (L.W - 1));
+            double* ptr = x + ((el >> L.wshift) * (int64_t)L.nf + __ldg(A.tab[kd] + (id & 7) * npc + k)) * L.W + (el & (L.W - 1));
             if (OP == CUT_PACK) acc += *ptr;
             else if (OP == CUT_UNPACK) *ptr = acc;
             else if (!(o == b && C.first_local[cell])) *ptr = 0.0;
@@ -871,26 +881,26 @@ __global__ void __launch_bounds__(256) cut_kernel(const LevelView L, const CutVi
     }
     if (SQ) block_reduce_finish(sq, R, POST_ADD, S_TMP);
 }
-int launch_cut(int dim, int op, int kind, const LevelView& L, const CutView& C, int64_t buf_base, double* x, double* buf,
-               cudaStream_t st) {
+// op: CUT_PACK / CUT_UNPACK / CUT_ZERO_BUT_FIRST; sq (with CUT_UNPACK): add (local copies) * total^2 to S_TMP
+int launch_cut(int dim, int op, const LevelView& L, const CutView* C, const int64_t* base, double* x, double* buf, bool sq,
+               const Reducer& R, cudaStream_t st) {
     const int nfl = dim == 3 ? 4 : 0, nel = dim == 3 ? 6 : 3;
-    const int npc = kind == 0 ? L.npf : (kind == 1 ? L.npe : 1);
-    const uint16_t* tab = L.iface_idx + (kind == 0 ? 0 : (kind == 1 ? nfl * L.npf : nfl * L.npf + nel * L.npe));
-    if (C.ncells * npc == 0) return 0;
-    const unsigned grid = grid_for(C.ncells * npc, 256);
-    if (op == CUT_PACK) cut_kernel<CUT_PACK, false><<<grid, 256, 0, st>>>(L, C, npc, tab, buf_base, x, buf, Reducer{});
-    else if (op == CUT_UNPACK) cut_kernel<CUT_UNPACK, false><<<grid, 256, 0, st>>>(L, C, npc, tab, buf_base, x, buf, Reducer{});
-    else cut_kernel<CUT_ZERO_BUT_FIRST, false><<<grid, 256, 0, st>>>(L, C, npc, tab, buf_base, x, buf, Reducer{});
-    return 1;
-}
-// unpack + add (local copies) * total^2 of every cut node to S_TMP
-int launch_cut_unpack_sq(int dim, int kind, const LevelView& L, const CutView& C, int64_t buf_base, double* x, double* buf,
-                         const Reducer& R, cudaStream_t st) {
-    const int nfl = dim == 3 ? 4 : 0, nel = dim == 3 ? 6 : 3;
-    const int npc = kind == 0 ? L.npf : (kind == 1 ? L.npe : 1);
-    const uint16_t* tab = L.iface_idx + (kind == 0 ? 0 : (kind == 1 ? nfl * L.npf : nfl * L.npf + nel * L.npe));
-    if (C.ncells * npc == 0) return 0;
-    cut_kernel<CUT_UNPACK, true><<<grid_for(C.ncells * npc, 256, R.max_blocks), 256, 0, st>>>(L, C, npc, tab, buf_base, x, buf, R);
+    CutAll A;
+    A.items[0] = 0;
+    for (int kd = 0; kd < 3; ++kd) {
+        A.kind[kd] = C[kd];
+        A.npc[kd] = kd == 0 ? L.npf : (kd == 1 ? L.npe : 1);
+        A.base[kd] = base[kd];
+        A.tab[kd] = L.iface_idx + (kd == 0 ? 0 : (kd == 1 ? nfl * L.npf : nfl * L.npf + nel * L.npe));
+        A.items[kd + 1] = A.items[kd] + C[kd].ncells * A.npc[kd];
+        if (A.npc[kd] == 0) A.npc[kd] = 1;      // never divided by: the kind has no item
+    }
+    if (A.items[3] == 0 && !sq) return 0;
+    const unsigned grid = grid_for(std::max<int64_t>(A.items[3], 1), 256, sq ? R.max_blocks : 148 * 16);
+    if (op == CUT_PACK) cut_kernel<CUT_PACK, false><<<grid, 256, 0, st>>>(L, A, x, buf, R);
+    else if (op == CUT_UNPACK && sq) cut_kernel<CUT_UNPACK, true><<<grid, 256, 0, st>>>(L, A, x, buf, R);
+    else if (op == CUT_UNPACK) cut_kernel<CUT_UNPACK, false><<<grid, 256, 0, st>>>(L, A, x, buf, R);
+    else cut_kernel<CUT_ZERO_BUT_FIRST, false><<<grid, 256, 0, st>>>(L, A, x, buf, R);
     return 1;
 }
 

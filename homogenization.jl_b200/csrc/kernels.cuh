@@ -99,12 +99,11 @@ int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st);
 ApplyConfig make_apply_config(int dim, int m, int nf, int W, bool fused = false, bool streaming_rhs = false);
 int launch_interface_sum(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
 int launch_interface_sum_sq(int dim, const LevelView& L, const TopoView& T, double* x, const Reducer& R, int post, cudaStream_t st);
-int launch_cut_unpack_sq(int dim, int kind, const LevelView& L, const CutView& C, int64_t buf_base, double* x, double* buf,
-                         const Reducer& R, cudaStream_t st);
 int launch_zero_all_but_one(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
-// kind 0 faces / 1 edges / 2 vertices; buf_base = first slot of the kind in the level's packed buffer
-int launch_cut(int dim, int op, int kind, const LevelView& L, const CutView& C, int64_t buf_base, double* x, double* buf,
-               cudaStream_t st);
+// all three kinds (faces / edges / vertices) in one launch; base[kind] = first slot of the kind in the level's
+// packed buffer; sq (with CUT_UNPACK): add (local copies) * total^2 of every cut node to S_TMP
+int launch_cut(int dim, int op, const LevelView& L, const CutView* C, const int64_t* base, double* x, double* buf, bool sq,
+               const Reducer& R, cudaStream_t st);
 // derived CG scalars after a cross-rank all-reduce of the raw dot product in S_TMP
 int launch_scalar_post(const Reducer& R, int post, int slot, cudaStream_t st);
 int launch_masked_copy_to_base(const LevelView& L1, int64_t nn, const int32_t* node_first, const uint8_t* contrib, const double* v,
