@@ -71,6 +71,7 @@ HOST_PROTOTYPES = {
     "hmg_host_boundary": (_i32, [_i32, _i64, _i64, _p, _p, _p]),
     "hmg_host_class_of": (_i32, [_i32, _i32, _i32]),
     "hmg_host_partition_elements": (_i32, [_i32, _i64, _i64, _p, _p, _i32, _i32, C.POINTER(_i64), _p, _p, _p, _p, _p]),
+    "hmg_host_partition_peers": (_i32, [_i32, _i64, _i64, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "hmg_host_partition_cells": (_i32, [_i32, _i64, _i64, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "hmg_host_element_coefficients": (_i32, [_i32, _i64, _i64, _p, _p, _p, _p, _i32]),
     "hmg_host_apply_sweep": (_i32, [_i32, _i32, _i32, _i32, _p, _p, _p, _p]),

@@ -52,6 +52,10 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 const NcclApi& nccl() {
@@ -74,6 +78,10 @@ const NcclApi& nccl() {
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
     api.Reduce = reinterpret_cast<decltype(api.Reduce)>(sym("ncclReduce"));
     api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
     loaded = true;
     return api;
@@ -114,6 +122,13 @@ struct hmg_ctx {
     int64_t cut_nglobal[3] = {0, 0, 0};
     std::vector<double*> cut_send;       // per level: packed partial sums, slots of foreign cells stay zero
     double* cut_recv = nullptr;
+    // neighbour exchange (default): one message per rank that shares a cut cell, laid out per level as
+    // [shared faces x npf][shared edges x npe][shared vertices]
+    bool cut_p2p = true;
+    std::vector<int> neighbors;
+    std::vector<std::vector<int64_t>> msg_off, msg_len;   // [level][neighbour]
+    std::vector<int64_t*> kbase;         // per level, device: [nranks * 3] first entry of a kind's section
+    double *p2p_send = nullptr, *p2p_recv = nullptr;
     uint8_t* node_contrib = nullptr;
     // driver functionals (finest level)
     double* dphi = nullptr;              // [nf][dim]
@@ -341,6 +356,37 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const 
         }
         c->cut_recv = c->dalloc<double>((size_t)max_slots);
         c->node_contrib = c->dupload(P.node_contrib);
+        for (int kind = 0; kind < 3; ++kind) {
+            const CutCells& C = P.cut[kind];
+            c->cutv[kind].peer_off = c->dupload(C.peer_off);
+            c->cutv[kind].peer_rank = c->dupload(C.peer_rank);
+            c->cutv[kind].peer_idx = c->dupload(C.peer_idx);
+            c->cutv[kind].my_pos = c->dupload(C.my_pos);
+        }
+        if (const char* v = getenv("HMG_CUT_ALLREDUCE")) c->cut_p2p = atoi(v) == 0;
+        for (int q = 0; q < nranks; ++q)
+            if (q != rank && P.shared_with[(size_t)q * 3] + P.shared_with[(size_t)q * 3 + 1] + P.shared_with[(size_t)q * 3 + 2] > 0)
+                c->neighbors.push_back(q);
+        c->msg_off.resize(nlevels); c->msg_len.resize(nlevels); c->kbase.resize(nlevels);
+        int64_t max_msg = 1;
+        for (int l = 1; l <= nlevels; ++l) {
+            const LevelView& V = c->lv[l - 1].view;
+            std::vector<int64_t> kb((size_t)nranks * 3, 0);
+            int64_t at = 0;
+            for (int q : c->neighbors) {
+                c->msg_off[l - 1].push_back(at);
+                const int64_t nper[3] = {V.npf, V.npe, 1};
+                for (int kind = 0; kind < 3; ++kind) {
+                    kb[(size_t)q * 3 + kind] = at;
+                    at += P.shared_with[(size_t)q * 3 + kind] * nper[kind];
+                }
+                c->msg_len[l - 1].push_back(at - c->msg_off[l - 1].back());
+            }
+            c->kbase[l - 1] = c->dupload(kb);
+            max_msg = std::max(max_msg, at);
+        }
+        c->p2p_send = c->dalloc<double>((size_t)max_msg);
+        c->p2p_recv = c->dalloc<double>((size_t)max_msg);
     }
     {
         std::vector<uint16_t> cm((size_t)c->nunits * c->W, 0);
@@ -395,17 +441,37 @@ void do_apply(hmg_ctx* c, int l, int mode, double alpha, const double* x, double
     HMG_CHECK(n >= 0, "apply kernel refused the launch configuration");
     check_launch(c, n);
 }
-// cut cells: pack the partial sums of the local owners, all-reduce the packed buffer over the ranks
-// (only interface partial sums move, NCCL over NVLink), write the totals back
-void do_cut_exchange(hmg_ctx* c, int l, double* x) {
-    const int64_t slots = c->cut_slots(l);
-    if (c->nranks == 1 || slots == 0) return;
+// cut cells: only interface partial sums move (NCCL over NVLink).  Default: every rank sends the partial sum of a
+// cut node to the ranks that share it (grouped ncclSend / ncclRecv with its <= 7 neighbours in a block partition)
+// and adds the partial sums in ascending rank order.  HMG_CUT_ALLREDUCE=1: one all-reduce of a packed buffer that
+// covers the cut cells of all ranks (simpler, 7x the traffic on 8 ranks).  sq: also add owners x total^2 to S_TMP.
+void do_cut_exchange_impl(hmg_ctx* c, int l, double* x, bool sq) {
     const LevelView& V = c->level(l).view;
+    if (c->cut_p2p) {
+        const std::vector<int64_t>& off = c->msg_off[l - 1];
+        const std::vector<int64_t>& len = c->msg_len[l - 1];
+        check_launch(c, launch_cut_p2p(c->dim, CUT_PACK, V, c->cutv, c->kbase[l - 1], x, c->p2p_send, false, c->red, c->stream));
+        NCCL_OK(nccl().GroupStart());
+        for (size_t q = 0; q < c->neighbors.size(); ++q) {
+            if (len[q] == 0) continue;
+            NCCL_OK(nccl().Send(c->p2p_send + off[q], (size_t)len[q], ncclDouble, c->neighbors[q], c->comm, c->stream));
+            NCCL_OK(nccl().Recv(c->p2p_recv + off[q], (size_t)len[q], ncclDouble, c->neighbors[q], c->comm, c->stream));
+        }
+        NCCL_OK(nccl().GroupEnd());
+        check_launch(c, launch_cut_p2p(c->dim, CUT_UNPACK, V, c->cutv, c->kbase[l - 1], x, c->p2p_recv, sq, c->red, c->stream));
+        return;
+    }
+    const int64_t slots = c->cut_slots(l);
     double* send = c->cut_send[l - 1];
     const int64_t base[3] = {c->cut_base(l, 0), c->cut_base(l, 1), c->cut_base(l, 2)};
     check_launch(c, launch_cut(c->dim, CUT_PACK, V, c->cutv, base, x, send, false, c->red, c->stream));
     NCCL_OK(nccl().AllReduce(send, c->cut_recv, (size_t)slots, ncclDouble, ncclSum, c->comm, c->stream));
-    check_launch(c, launch_cut(c->dim, CUT_UNPACK, V, c->cutv, base, x, c->cut_recv, false, c->red, c->stream));
+    check_launch(c, launch_cut(c->dim, CUT_UNPACK, V, c->cutv, base, x, c->cut_recv, sq, c->red, c->stream));
+}
+void do_cut_exchange(hmg_ctx* c, int l, double* x) {
+    const int64_t slots = c->cut_slots(l);
+    if (c->nranks == 1 || slots == 0) return;
+    do_cut_exchange_impl(c, l, x, false);
 }
 void do_broadcast(hmg_ctx* c, int l, double* x) {
     check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->stream));
@@ -449,13 +515,7 @@ void do_broadcast_rho(hmg_ctx* c, int l, double* r) {
     }
     check_launch(c, launch_interface_sum_sq(c->dim, V, c->tview, r, c->red, POST_ADD, c->stream));
     const int64_t slots = c->cut_slots(l);
-    if (slots > 0) {
-        double* send = c->cut_send[l - 1];
-        const int64_t base[3] = {c->cut_base(l, 0), c->cut_base(l, 1), c->cut_base(l, 2)};
-        check_launch(c, launch_cut(c->dim, CUT_PACK, V, c->cutv, base, r, send, false, c->red, c->stream));
-        NCCL_OK(nccl().AllReduce(send, c->cut_recv, (size_t)slots, ncclDouble, ncclSum, c->comm, c->stream));
-        check_launch(c, launch_cut(c->dim, CUT_UNPACK, V, c->cutv, base, r, c->cut_recv, true, c->red, c->stream));
-    }
+    if (slots > 0) do_cut_exchange_impl(c, l, r, true);
     finish_reduction(c, POST_RHO, S_TMP);
 }
 // p' = r + beta p and Ap = broadcast(constraint(A p')) with p' applied straight out of shared memory: the new

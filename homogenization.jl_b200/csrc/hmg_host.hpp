@@ -116,6 +116,12 @@ struct CutCells {                      // the cut cells of one kind this rank ta
     std::vector<int64_t> offset;       // CSR over the LOCAL owners of the cell
     std::vector<int32_t> owner;        // local element * 8 + local id, ascending global element
     std::vector<uint8_t> first_local;  // 1 if the globally first owner of the cell is owner[offset[c]]
+    // neighbour exchange: the OTHER ranks that share the cell, ascending, with the ordinal of the cell among
+    // the cut cells of this kind the two ranks share (both enumerate the global cells in the same order)
+    std::vector<int64_t> peer_off;     // CSR over the peers of the cell
+    std::vector<int32_t> peer_rank;
+    std::vector<int32_t> peer_idx;
+    std::vector<int32_t> my_pos;       // number of peers with a smaller rank (position of the own partial sum)
     int64_t ncells() const { return (int64_t)slot.size(); }
 };
 struct Partition {
@@ -124,6 +130,7 @@ struct Partition {
     std::vector<int32_t> global_to_local;   // global element -> local element, -1 if remote
     CellMap faces, edges, verts;            // interface cells with all owners on this rank (local ids)
     CutCells cut[3];                        // 0 faces (3D), 1 edges, 2 vertices
+    std::vector<int64_t> shared_with;       // [nranks][3] cut cells of every kind shared with each other rank
     std::vector<uint16_t> cmask;            // per local element
     std::vector<uint8_t> mult;              // [ne_local][16] owners (on all ranks) of the cell behind every node class
     std::vector<int32_t> node_first;        // per base node: first LOCAL owner (local element*8+local id), -1 if none

@@ -301,6 +301,26 @@ int hmg_host_partition_cells(int dim, int64_t ne, int64_t nn, const int64_t* ele
     HOST_END
 }
 
+// neighbour exchange of the cut cells of one kind: per participating cell (same order as hmg_host_partition_cells
+// with cut == 1) the other ranks that share it, ascending, the ordinal of the cell in the message exchanged with
+// each of them, and the position of the own partial sum in the rank-ordered total; shared_with[nranks * 3] =
+// cut cells of every kind shared with every rank.  sizes[2] = cells, peer entries.  Arrays may be NULL.
+int hmg_host_partition_peers(int dim, int64_t ne, int64_t nn, const int64_t* elems1, const int32_t* owner_rank, int rank,
+                             int nranks, int kind, int64_t* sizes, int64_t* peer_off, int32_t* peer_rank, int32_t* peer_idx,
+                             int32_t* my_pos, int64_t* shared_with) {
+    HOST_BEGIN
+    HMG_CHECK(kind >= 0 && kind < 3, "kind must be 0, 1 or 2");
+    const Partition P = host_partition(dim, ne, nn, elems1, owner_rank, rank, nranks);
+    const CutCells& C = P.cut[kind];
+    if (sizes) { sizes[0] = C.ncells(); sizes[1] = (int64_t)C.peer_rank.size(); }
+    if (peer_off) std::copy(C.peer_off.begin(), C.peer_off.end(), peer_off);
+    if (peer_rank) std::copy(C.peer_rank.begin(), C.peer_rank.end(), peer_rank);
+    if (peer_idx) std::copy(C.peer_idx.begin(), C.peer_idx.end(), peer_idx);
+    if (my_pos) std::copy(C.my_pos.begin(), C.my_pos.end(), my_pos);
+    if (shared_with) std::copy(P.shared_with.begin(), P.shared_with.end(), shared_with);
+    HOST_END
+}
+
 // class bitmask of a local face / edge / vertex
 int hmg_host_class_of(int dim, int kind, int lid) {
     return kind == 0 ? class_of_face(lid) : kind == 1 ? class_of_edge(dim, lid) : class_of_vertex(dim, lid);

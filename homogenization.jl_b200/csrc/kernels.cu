@@ -904,6 +904,66 @@ int launch_cut(int dim, int op, const LevelView& L, const CutView* C, const int6
     return 1;
 }
 
+template <int OP, bool SQ>
+__global__ void __launch_bounds__(256) cut_p2p_kernel(const LevelView L, const CutAll A, const int64_t* __restrict__ kbase,
+                                                      double* __restrict__ x, double* __restrict__ msg, const Reducer R) {
+    double sq = 0.0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < A.items[3]; t += (int64_t)gridDim.x * blockDim.x) {
+        const int kd = t < A.items[1] ? 0 : (t < A.items[2] ? 1 : 2);
+        const CutView& C = A.kind[kd];
+        const int npc = A.npc[kd];
+        const int64_t q = t - A.items[kd];
+        const int64_t cell = q / npc;
+        const int k = (int)(q - cell * npc);
+        const int64_t b = C.off[cell], en = C.off[cell + 1];
+        double part = 0.0;
+        for (int64_t o = b; o < en; ++o) {
+            const int32_t id = C.own[o];
+            const int64_t el = id >> 3;
+            part += x[((el >> L.wshift) * (int64_t)L.nf + __ldg(A.tab[kd] + (id & 7) * npc + k)) * L.W + (el & (L.W - 1))];
+        }
+        const int64_t pb = C.peer_off[cell], pe = C.peer_off[cell + 1];
+        if (OP == CUT_PACK) {
+            for (int64_t j = pb; j < pe; ++j) msg[kbase[C.peer_rank[j] * 3 + kd] + (int64_t)C.peer_idx[j] * npc + k] = part;
+            continue;
+        }
+        const int mine = C.my_pos[cell];
+        double tot = 0.0;
+        for (int64_t j = pb; j < pe; ++j) {
+            if ((int)(j - pb) == mine) tot += part;
+            tot += msg[kbase[C.peer_rank[j] * 3 + kd] + (int64_t)C.peer_idx[j] * npc + k];
+        }
+        if ((int)(pe - pb) == mine) tot += part;
+        for (int64_t o = b; o < en; ++o) {
+            const int32_t id = C.own[o];
+            const int64_t el = id >> 3;
+            x[((el >> L.wshift) * (int64_t)L.nf + __ldg(A.tab[kd] + (id & 7) * npc + k)) * L.W + (el & (L.W - 1))] = tot;
+        }
+        if (SQ) sq = fma((double)(en - b) * tot, tot, sq);
+    }
+    if (SQ) block_reduce_finish(sq, R, POST_ADD, S_TMP);
+}
+int launch_cut_p2p(int dim, int op, const LevelView& L, const CutView* C, const int64_t* kbase, double* x, double* msg, bool sq,
+                   const Reducer& R, cudaStream_t st) {
+    const int nfl = dim == 3 ? 4 : 0, nel = dim == 3 ? 6 : 3;
+    CutAll A;
+    A.items[0] = 0;
+    for (int kd = 0; kd < 3; ++kd) {
+        A.kind[kd] = C[kd];
+        A.npc[kd] = kd == 0 ? L.npf : (kd == 1 ? L.npe : 1);
+        A.base[kd] = 0;
+        A.tab[kd] = L.iface_idx + (kd == 0 ? 0 : (kd == 1 ? nfl * L.npf : nfl * L.npf + nel * L.npe));
+        A.items[kd + 1] = A.items[kd] + C[kd].ncells * A.npc[kd];
+        if (A.npc[kd] == 0) A.npc[kd] = 1;
+    }
+    if (A.items[3] == 0 && !sq) return 0;
+    const unsigned grid = grid_for(std::max<int64_t>(A.items[3], 1), 256, sq ? R.max_blocks : 148 * 16);
+    if (op == CUT_PACK) cut_p2p_kernel<CUT_PACK, false><<<grid, 256, 0, st>>>(L, A, kbase, x, msg, R);
+    else if (sq) cut_p2p_kernel<CUT_UNPACK, true><<<grid, 256, 0, st>>>(L, A, kbase, x, msg, R);
+    else cut_p2p_kernel<CUT_UNPACK, false><<<grid, 256, 0, st>>>(L, A, kbase, x, msg, R);
+    return 1;
+}
+
 // apply_constraint!: zero every stored node whose class is on the domain boundary; only elements
 // that touch the domain boundary are visited (belems)
 __global__ void __launch_bounds__(256) constraint_kernel(const LevelView L, int64_t nbelems, const int32_t* __restrict__ belems,

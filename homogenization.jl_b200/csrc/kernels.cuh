@@ -52,6 +52,11 @@ struct CutView {
     const int64_t* off;         // CSR over the local owners
     const int32_t* own;         // local element * 8 + local id
     const uint8_t* first_local; // the globally first owner is own[off[c]]
+    // neighbour exchange: the other ranks sharing the cell (ascending) and the cell's ordinal in the message
+    const int64_t* peer_off;
+    const int32_t* peer_rank;
+    const int32_t* peer_idx;
+    const int32_t* my_pos;      // peers with a smaller rank: where the own partial sum enters the ordered total
 };
 enum CutOp { CUT_PACK = 0, CUT_UNPACK = 1, CUT_ZERO_BUT_FIRST = 2 };
 
@@ -104,6 +109,11 @@ int launch_zero_all_but_one(int dim, const LevelView& L, const TopoView& T, doub
 // packed buffer; sq (with CUT_UNPACK): add (local copies) * total^2 of every cut node to S_TMP
 int launch_cut(int dim, int op, const LevelView& L, const CutView* C, const int64_t* base, double* x, double* buf, bool sq,
                const Reducer& R, cudaStream_t st);
+// neighbour exchange of the cut cells: CUT_PACK writes the partial sum of every cut node into the message of every
+// rank that shares it, CUT_UNPACK adds the partial sums of all sharing ranks in ascending rank order (every rank gets
+// the same bits).  kbase[rank * 3 + kind] = first entry of the kind's section in the message to / from `rank`.
+int launch_cut_p2p(int dim, int op, const LevelView& L, const CutView* C, const int64_t* kbase, double* x, double* msg, bool sq,
+                   const Reducer& R, cudaStream_t st);
 // derived CG scalars after a cross-rank all-reduce of the raw dot product in S_TMP
 int launch_scalar_post(const Reducer& R, int post, int slot, cudaStream_t st);
 int launch_masked_copy_to_base(const LevelView& L1, int64_t nn, const int32_t* node_first, const uint8_t* contrib, const double* v,

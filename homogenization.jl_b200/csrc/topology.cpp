@@ -188,12 +188,15 @@ Partition build_partition(const Topology& T, const int32_t* owner_rank, int rank
     auto rank_of = [&](int32_t id) { return owner_rank ? owner_rank[id >> 3] : 0; };
     const CellMap* maps[3] = {&T.faces, &T.edges, &T.verts};
     CellMap* locals[3] = {&P.faces, &P.edges, &P.verts};
+    P.shared_with.assign((size_t)nranks * 3, 0);
+    std::vector<int> cell_ranks;
     for (int kind = 0; kind < 3; ++kind) {
         const CellMap& m = *maps[kind];
         CellMap& loc = *locals[kind];
         CutCells& cut = P.cut[kind];
         loc.offset.assign(1, 0);
         cut.offset.assign(1, 0);
+        cut.peer_off.assign(1, 0);
         for (int64_t c = 0; c < m.ncells(); ++c) {
             const int64_t b = m.offset[c], en = m.offset[c + 1];
             int nlocal = 0;
@@ -218,6 +221,20 @@ Partition build_partition(const Topology& T, const int32_t* owner_rank, int rank
                 if (rank_of(m.owner[o]) == rank)
                     cut.owner.push_back(P.global_to_local[m.owner[o] >> 3] * 8 + (m.owner[o] & 7));
             cut.offset.push_back((int64_t)cut.owner.size());
+            // the other ranks that share the cell
+            cell_ranks.clear();
+            for (int64_t o = b; o < en; ++o) cell_ranks.push_back(rank_of(m.owner[o]));
+            std::sort(cell_ranks.begin(), cell_ranks.end());
+            cell_ranks.erase(std::unique(cell_ranks.begin(), cell_ranks.end()), cell_ranks.end());
+            int below = 0;
+            for (int q : cell_ranks) {
+                if (q == rank) continue;
+                if (q < rank) ++below;
+                cut.peer_rank.push_back(q);
+                cut.peer_idx.push_back((int32_t)P.shared_with[(size_t)q * 3 + kind]++);
+            }
+            cut.my_pos.push_back(below);
+            cut.peer_off.push_back((int64_t)cut.peer_rank.size());
         }
     }
     // Dirichlet classes and owner counts of the local elements (from the GLOBAL topology)

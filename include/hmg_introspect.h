@@ -51,6 +51,15 @@ int hmg_host_partition_cells(int dim, int64_t ne, int64_t nn, const int64_t* ele
 int hmg_host_element_coefficients(int dim, int64_t ne, int64_t nn, const double* nodes, const int64_t* elems1,
                                   const double* sigma, double* coef, int stride);
 
+/* neighbour exchange of the cut cells of one kind: per participating cell (same order as hmg_host_partition_cells
+ * with cut == 1) the other ranks that share it, ascending (CSR peer_off / peer_rank), the ordinal of the cell in the
+ * message exchanged with each of them (peer_idx) and the position of the own partial sum in the rank-ordered total
+ * (my_pos); shared_with[nranks * 3] = cut cells of every kind shared with every rank (the message sizes).
+ * sizes[2] = cells, peer entries.  Arrays may be NULL. */
+int hmg_host_partition_peers(int dim, int64_t ne, int64_t nn, const int64_t* elems1, const int32_t* owner_rank, int rank,
+                             int nranks, int kind, int64_t* sizes, int64_t* peer_off, int32_t* peer_rank, int32_t* peer_idx,
+                             int32_t* my_pos, int64_t* shared_with);
+
 /* runs the apply kernel's task enumeration and line sweeps (csrc/apply_core.cuh, the templates the
  * device kernel instantiates) for one element on the host: y = A x in lattice order, coef = |J| P (upper
  * triangle), lambda |J|; 2D lines are split into segments of 2^seg_shift nodes; info[4] = tasks, largest

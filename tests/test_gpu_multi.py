@@ -109,3 +109,19 @@ def test_two_gpus_match_the_oracle_on_the_whole_mesh(case):
     mp.spawn(_worker, args=(2, bytes(raw), case, results), nprocs=2, join=True)
     got = dict(results.get() for _ in range(2))
     assert got[0] == got[1]          # every rank sees the same residual history
+
+
+@pytest.mark.parametrize("case", [(3, 4, 4), (2, 6, 5)], ids=["tet-c4-L4", "tri-c6-L5"])
+def test_four_gpus_match_the_oracle_on_the_whole_mesh(case):
+    """2 x 2 blocks: cut edges and vertices are shared by up to four ranks (several peers per cut cell)."""
+    if _ngpus() < 4:
+        pytest.skip("needs four GPUs")
+    import torch
+    import torch.multiprocessing as mp
+    raw = (C.c_ubyte * 128)()
+    hmg._lib.check(hmg.load().hmg_nccl_unique_id(raw))
+    ctx = mp.get_context("spawn")
+    results = ctx.SimpleQueue()
+    mp.spawn(_worker, args=(4, bytes(raw), case, results), nprocs=4, join=True)
+    got = dict(results.get() for _ in range(4))
+    assert got[0] == got[1] == got[2] == got[3]

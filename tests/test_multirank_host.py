@@ -52,6 +52,16 @@ def partition_of(lib, mesh, owner, rank, nranks):
             L.check_host(lib.hmg_host_partition_cells(dim, ne, nn, vp(el1), vp(own), rank, nranks, kind, cut, vp(sizes), vp(off),
                                                       vp(el), vp(lid), vp(slot) if cut else None, vp(first) if cut else None))
             out[(cut, kind)] = dict(off=off, el=el, lid=lid, slot=slot, first=first, nglobal=int(sizes[2]))
+    out["shared_with"] = np.zeros((nranks, 3), np.int64)
+    for kind in range(3):
+        sizes = np.zeros(2, np.int64)
+        L.check_host(lib.hmg_host_partition_peers(dim, ne, nn, vp(el1), vp(own), rank, nranks, kind, vp(sizes), None, None, None,
+                                                  None, None))
+        nc, npe = int(sizes[0]), int(sizes[1])
+        poff, prank, pidx, mypos = np.zeros(nc + 1, np.int64), np.zeros(npe, np.int32), np.zeros(npe, np.int32), np.zeros(nc, np.int32)
+        L.check_host(lib.hmg_host_partition_peers(dim, ne, nn, vp(el1), vp(own), rank, nranks, kind, vp(sizes), vp(poff), vp(prank),
+                                                  vp(pidx), vp(mypos), vp(out["shared_with"])))
+        out[(1, kind)].update(poff=poff, prank=prank, pidx=pidx, mypos=mypos)
     return out
 
 
@@ -125,6 +135,65 @@ def _worker(rank, world, port, case):
                         xl[rows[(k, int(m["lid"][o]))], m["el"][o]] = recv[b:b + npc[k]]
             assert np.allclose(xl, expect[:, l2g], rtol=1e-14, atol=0), (rank, level)
 
+            # the same through the neighbour exchange: one message per rank that shares a cut cell, laid out as
+            # [shared faces x npf][shared edges x npe][shared vertices]; totals added in ascending rank order
+            xp = np.asfortranarray(x[:, l2g])
+            for k in nkinds:                                  # local cells first, as above
+                m = P[(0, k)]
+                for cell in range(len(m["off"]) - 1):
+                    own = range(m["off"][cell], m["off"][cell + 1])
+                    s = np.zeros(npc[k])
+                    for o in own:
+                        s = s + xp[rows[(k, int(m["lid"][o]))], m["el"][o]]
+                    for o in own:
+                        xp[rows[(k, int(m["lid"][o]))], m["el"][o]] = s
+            shared = [torch.zeros((world, 3), dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(shared, torch.from_numpy(P["shared_with"].copy()))
+            shared = [t.numpy() for t in shared]
+            for q in range(world):                            # both sides count the same shared cells
+                assert np.array_equal(shared[q][rank], P["shared_with"][q])
+
+            def layout(table):                                # kbase[(q, kind)] of the rank that owns `table`
+                kb, at = {}, 0
+                for q in range(world):
+                    for k in (0, 1, 2):
+                        kb[(q, k)] = at
+                        at += int(table[q, k]) * npc.get(k, 0)
+                return kb, at
+            kb, mine = layout(P["shared_with"])
+            longest = max(layout(t)[1] for t in shared)
+            msg = np.zeros(max(longest, 1))
+            part = {}
+            for k in nkinds:
+                m = P[(1, k)]
+                for cell in range(len(m["off"]) - 1):
+                    s = np.zeros(npc[k])
+                    for o in range(m["off"][cell], m["off"][cell + 1]):
+                        s = s + xp[rows[(k, int(m["lid"][o]))], m["el"][o]]
+                    part[(k, cell)] = s
+                    for j in range(m["poff"][cell], m["poff"][cell + 1]):
+                        b = kb[(int(m["prank"][j]), k)] + int(m["pidx"][j]) * npc[k]
+                        msg[b:b + npc[k]] = s
+            got = [torch.zeros(len(msg), dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(got, torch.from_numpy(msg))
+            for k in nkinds:
+                m = P[(1, k)]
+                for cell in range(len(m["off"]) - 1):
+                    tot = np.zeros(npc[k])
+                    peers = list(range(m["poff"][cell], m["poff"][cell + 1]))
+                    assert list(m["prank"][peers]) == sorted(m["prank"][peers])
+                    for n_, j in enumerate(peers):
+                        if n_ == m["mypos"][cell]:
+                            tot = tot + part[(k, cell)]
+                        q = int(m["prank"][j])
+                        b = layout(shared[q])[0][(rank, k)] + int(m["pidx"][j]) * npc[k]     # q's message for me
+                        tot = tot + got[q].numpy()[b:b + npc[k]]
+                    if len(peers) == m["mypos"][cell]:
+                        tot = tot + part[(k, cell)]
+                    for o in range(m["off"][cell], m["off"][cell + 1]):
+                        xp[rows[(k, int(m["lid"][o]))], m["el"][o]] = tot
+            assert np.allclose(xp, expect[:, l2g], rtol=1e-14, atol=0), (rank, level)
+
             # owner-count weights: sum_ranks sum_entries mult * p * Ap_local == dot(p, broadcast(Ap)) on the whole mesh
             p_glob = broadcast_interfaces(np.asfortranarray(rng.random((nf, mesh.nelements))), oimp, level)
             Ap_loc = np.asfortranarray(rng.random((nf, mesh.nelements)))
@@ -169,6 +238,12 @@ def _worker(rank, world, port, case):
 def test_two_ranks_reproduce_the_global_interface_sums(case):
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port(), case), nprocs=2, join=True)
+
+
+def test_four_ranks_share_edges_and_vertices():
+    """2 x 2 blocks: the cut cells along the middle are shared by up to four ranks (several peers per cell)."""
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(4, _free_port(), (3, 2, 3)), nprocs=4, join=True)
 
 
 def test_single_rank_partition_is_the_whole_mesh():
