@@ -4,7 +4,7 @@ CUDA_LIB  ?= /usr/local/cuda/lib64
 PKG       := homogenization.jl_b200
 CSRC      := $(PKG)/csrc
 LIB       := $(PKG)/libhmg_b200.so
-NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
+NVFLAGS   := $(HMG_EXTRA) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
              -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude -diag-suppress 20014
 SRCS      := $(CSRC)/api.cu $(CSRC)/kernels.cu $(CSRC)/reference.cpp $(CSRC)/topology.cpp $(CSRC)/introspect.cpp
 HDRS      := include/hmg.h $(CSRC)/hmg_host.hpp $(CSRC)/kernels.cuh $(CSRC)/lattice.hpp $(CSRC)/apply_core.cuh

@@ -127,6 +127,9 @@ __device__ __forceinline__ void block_reduce_finish(double v, const Reducer& R, 
 constexpr int APPLY_Q = 64, APPLY_QS = 6;   // mbarrier slots (chunks in flight), log2
 constexpr int APPLY_STAGES = 16;             // staging slots of the fused p-update variant: 4 per converter warp
 constexpr int APPLY_MAXT = 16 * 32;    // 15 consumer warps + the producer warp: 128 registers per thread
+#ifndef HMG_MAXT3
+#define HMG_MAXT3 512
+#endif
 
 template <int DIM> struct ApplyParams {
     StencilTab<DIM> T;
@@ -220,7 +223,7 @@ struct SmemLoad {
 // into the ring (p' is what the stencil reads) and stores p' to the OTHER p buffer (neighbouring CTAs still read
 // the old p for their halo planes), so p' never makes a round trip through HBM before it is applied.
 template <int DIM, int W, int MODE, bool DOT, bool FUSEP>
-__global__ void __launch_bounds__(APPLY_MAXT, 1) apply_kernel(const __grid_constant__ ApplyParams<DIM> a) {
+__global__ void __launch_bounds__(DIM == 3 ? HMG_MAXT3 : APPLY_MAXT, 1) apply_kernel(const __grid_constant__ ApplyParams<DIM> a) {
     using D = Dims<DIM>;
     constexpr int APPLY_W = W;
     static_assert(W == 32 || (W == 16 && DIM == 3), "W = 16 pairs two lines of a 3D plane per warp");
@@ -571,7 +574,8 @@ static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool f
         const char* v = getenv(name);
         return v ? atoi(v) : dflt;
     };
-    c.nwarps = std::max(1, std::min(15, envi("HMG_APPLY_WARPS", 15)));
+    const int maxw = (dim == 3 ? HMG_MAXT3 : APPLY_MAXT) / 32;      // warps of a CTA (consumers + producer / converters)
+    c.nwarps = std::max(1, std::min(maxw - 1, envi("HMG_APPLY_WARPS", maxw - 1)));
     c.ctas_per_sm = 1;
     c.seg = dim == 2 ? std::max(2, std::min(8, envi("HMG_APPLY_SEG_SHIFT", 5))) : 30;
     c.spill_rows = dim == 2 ? (1 << c.seg) + 3 : m + 3;       // rows a task may run past the base of a line
@@ -638,7 +642,7 @@ static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool f
     if (streaming_rhs && !getenv("HMG_APPLY_RING_ROWS")) R = std::min(R, min_rows + 200);
     c.ring_rows = R >= min_rows ? R : -1;        // -1: the level does not fit (refused by the launcher)
     c.smem_bytes = (size_t)(std::max(R, 1) + c.spill_rows) * rowb + stage_bytes;
-    if (fused) c.nwarps = std::min(c.nwarps, 16 - c.nconv);
+    if (fused) c.nwarps = std::min(c.nwarps, maxw - c.nconv);
     (void)nf;
     return c;
 }
