@@ -18,10 +18,18 @@ CASES = [(2, 5, 5), (2, 3, 7), (3, 3, 4), (3, 2, 5), (2, 4, 1), (3, 2, 2)]
 IDS = ["tri-c5-L5", "tri-c3-L7", "tet-c3-L4", "tet-c2-L5", "tri-c4-L1", "tet-c2-L2"]
 
 
+# BASELINE.json configs[4]: random piecewise coefficient field; and the magnitude-ordered mesh of the driver
+# (elements of a cell are no longer consecutive)
+CASES += [(2, 4, 5, "random"), (3, 2, 4, "random"), (3, 3, 3, "ordered")]
+IDS += ["tri-c4-L5-random", "tet-c2-L4-random", "tet-c3-L3-ordered"]
+
+
 @pytest.fixture(params=CASES, ids=IDS)
 def pair(request):
-    dim, c, levels = request.param
-    p = Pair(dim, c, levels, lam=0.7)
+    dim, c, levels = request.param[:3]
+    kind = request.param[3] if len(request.param) > 3 else "checkerboard"
+    p = Pair(dim, c, levels, lam=0.7, field="random" if kind == "random" else "checkerboard", seed=2 if kind == "random" else 1,
+             ordered=kind == "ordered")
     yield p
     p.close()
 
