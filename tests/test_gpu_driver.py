@@ -67,3 +67,26 @@ def test_homogenized_coefficient_matches_oracle(n, dim, refinements, tol):
             assert abs(rg - ro) <= 1e-10 * ro
             assert abs(s_g - s_o) <= 1e-8 * abs(s_o)
     assert abs(sg - so) <= 1e-8 * abs(so)
+
+
+@pytest.mark.parametrize("name", ["homogenization_tri_n1_r3", "homogenization_tet_n0_r2", "homogenization_C1_tri_n3_r4"])
+def test_homogenized_coefficient_matches_golden(name):
+    """The device driver against the oracle's committed golden histories (tests/golden/, no oracle run here);
+    `homogenization_C1_tri_n3_r4` is BASELINE.json configs[0], the README example
+    checkerboard_homogenization(3, Tri64, refinements=4, tolerance=1e-3)."""
+    import json
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden as mg
+    gold = json.load(open(os.path.join(here, "golden", name + ".json")))
+    n, dim, refinements, tol, seed = mg.CASES[name]
+    cells, x0, _ = mg.inputs(n, dim, refinements, seed)
+    sg, hg = hmg.driver.checkerboard_homogenization(n, dim, refinements=refinements, tolerance=tol, sigma_cells=cells, x0=x0)
+    assert [len(s) for s in hg] == [len(s) for s in gold["history"]]
+    for a, b in zip(hg, gold["history"]):
+        for (rg, s_g, _), (ro, s_o, _) in zip(a, b):
+            assert abs(rg - ro) <= 1e-10 * ro
+            assert abs(s_g - s_o) <= 1e-8 * abs(s_o)
+    assert abs(sg - gold["sigma"]) <= 1e-8 * abs(gold["sigma"])
