@@ -153,6 +153,7 @@ struct hmg_ctx {
     int64_t* interior_idx = nullptr;
     double* Ainv = nullptr;
     double *ubase = nullptr, *bint = nullptr, *xint = nullptr;
+    double* symv_work = nullptr;         // per-tile partial sums of the half-traffic coarse mat-vec
     // staging
     double* staging = nullptr;
     size_t staging_bytes = 0;
@@ -576,7 +577,8 @@ void do_coarse_solve(hmg_ctx* c) {
     }
     if (c->rank == 0) {
         check_launch(c, launch_gather(c->interior_idx, c->n_interior, c->ubase, c->bint, c->stream));
-        check_launch(c, launch_symv_full(c->Ainv, c->n_interior, c->bint, c->xint, c->stream));
+        if (c->symv_work) check_launch(c, launch_symv_half(c->Ainv, c->n_interior, c->bint, c->xint, c->symv_work, c->stream));
+        else check_launch(c, launch_symv_full(c->Ainv, c->n_interior, c->bint, c->xint, c->stream));
         check_launch(c, launch_fill(c->ubase, 0.0, c->nn, c->stream));
         check_launch(c, launch_scatter(c->interior_idx, c->n_interior, c->xint, c->ubase, c->stream));
     }
@@ -616,12 +618,16 @@ void set_coarse_dense(hmg_ctx* c, int64_t n, const std::vector<int64_t>& colptr,
     if (c->interior_idx) { c->dfree(c->interior_idx); c->interior_idx = nullptr; }
     if (c->bint) { c->dfree(c->bint); c->bint = nullptr; }
     if (c->xint) { c->dfree(c->xint); c->xint = nullptr; }
+    if (c->symv_work) { c->dfree(c->symv_work); c->symv_work = nullptr; }
     c->n_interior = n;
     if (c->rank != 0) return;            // the coarsest-grid solve stays on rank 0
     c->interior_idx = c->dupload(interior0);
     c->bint = c->dalloc<double>(n);
     c->xint = c->dalloc<double>(n);
     c->Ainv = c->dalloc<double>((size_t)n * n);
+    const int64_t half_min = getenv("HMG_SYMV_HALF_MIN") ? atoll(getenv("HMG_SYMV_HALF_MIN")) : 2048;
+    if (n >= half_min)      // small problems: the one-kernel full mat-vec is faster
+        c->symv_work = c->dalloc<double>((size_t)2 * ((n + 127) / 128) * n);
     CUDA_OK(cudaStreamSynchronize(c->stream));
     // scatter the CSC entries column by column through a bounded host buffer
     {

@@ -127,6 +127,9 @@ __device__ __forceinline__ void block_reduce_finish(double v, const Reducer& R, 
 constexpr int APPLY_Q = 64, APPLY_QS = 6;   // mbarrier slots (chunks in flight), log2
 constexpr int APPLY_STAGES = 16;             // staging slots of the fused p-update variant: 4 per converter warp
 constexpr int APPLY_MAXT = 16 * 32;    // 15 consumer warps + the producer warp: 128 registers per thread
+#ifndef HMG_TD2
+#define HMG_TD2 4
+#endif
 #ifndef HMG_MAXT3
 #define HMG_MAXT3 512
 #endif
@@ -183,7 +186,7 @@ template <int DIM, int W, int MODE, bool DOT> struct OutDev {
     // b / y of the next TD nodes travel in registers (they come from L2, where the producer's bulk prefetch
     // put them): the load of node k + TD is issued before node k is finished, which keeps
     // warps x TD x 256 bytes in flight per SM
-    static constexpr int TD = DIM == 2 ? 4 : 3;
+    static constexpr int TD = DIM == 2 ? HMG_TD2 : 3;
     double tq[TD];
     int klast;
     __device__ __forceinline__ void begin(int k0, int k1) {
@@ -1372,6 +1375,77 @@ __global__ void __launch_bounds__(256) symv_kernel(const double* __restrict__ A,
         s = warp_sum(s);
         if (lane == 0) y[c] = s;
     }
+}
+// y = A x reading only the lower-triangular 128 x 128 tiles of the (fully stored) symmetric matrix: a tile (I, J),
+// I >= J, contributes T x_J to the rows of tile I and T' x_I to the rows of tile J.  Both land in per-tile slots
+// (PR[J][rows of I], PC[I][rows of J]) that a second kernel adds in a fixed order: half the traffic of symv_kernel,
+// deterministic, no atomics.
+constexpr int SYMV_TS = 128;
+__global__ void __launch_bounds__(256) symv_tiles_kernel(const double* __restrict__ A, int64_t n, int nt, const double* __restrict__ x,
+                                                         double* __restrict__ PR, double* __restrict__ PC) {
+    __shared__ double us[8][SYMV_TS];
+    // triangular decode: block b -> (I, J) with I >= J, b = I (I + 1) / 2 + J
+    const int64_t b = blockIdx.x;
+    int I = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+    while ((int64_t)(I + 1) * (I + 2) / 2 <= b) ++I;
+    while ((int64_t)I * (I + 1) / 2 > b) --I;
+    const int J = (int)(b - (int64_t)I * (I + 1) / 2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)I * SYMV_TS, c0 = (int64_t)J * SYMV_TS;
+    double xi[4], u[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t r = r0 + lane + 32 * k;
+        xi[k] = r < n ? x[r] : 0.0;
+    }
+    for (int cc = warp; cc < SYMV_TS; cc += 8) {
+        const int64_t c = c0 + cc;
+        if (c >= n) break;
+        const double xj = x[c];
+        const double* col = A + c * n + r0;
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int rr = lane + 32 * k;
+            const double t = r0 + rr < n ? col[rr] : 0.0;
+            u[k] = fma(t, xj, u[k]);
+            v = fma(t, xi[k], v);
+        }
+        if (I != J) {
+            v = warp_sum(v);
+            if (lane == 0) PC[(int64_t)I * n + c] = v;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) us[warp][lane + 32 * k] = u[k];
+    __syncthreads();
+    if (threadIdx.x < SYMV_TS) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += us[w][threadIdx.x];
+        const int64_t r = r0 + threadIdx.x;
+        if (r < n) PR[(int64_t)J * n + r] = sum;
+    }
+}
+__global__ void __launch_bounds__(256) symv_combine_kernel(int64_t n, int nt, const double* __restrict__ PR,
+                                                           const double* __restrict__ PC, double* __restrict__ y) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int T = (int)(i / SYMV_TS);
+        double s = 0.0;
+        for (int J = 0; J <= T; ++J) s += PR[(int64_t)J * n + i];
+        for (int I = T + 1; I < nt; ++I) s += PC[(int64_t)I * n + i];
+        y[i] = s;
+    }
+}
+// work: 2 * nt * n doubles (PR then PC), nt = ceil(n / 128)
+int launch_symv_half(const double* A, int64_t n, const double* x, double* y, double* work, cudaStream_t st) {
+    if (n == 0) return 0;
+    const int nt = (int)((n + SYMV_TS - 1) / SYMV_TS);
+    double* PR = work;
+    double* PC = work + (int64_t)nt * n;
+    symv_tiles_kernel<<<(unsigned)((int64_t)nt * (nt + 1) / 2), 256, 0, st>>>(A, n, nt, x, PR, PC);
+    symv_combine_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, nt, PR, PC, y);
+    return 2;
 }
 int launch_symv_full(const double* A, int64_t n, const double* x, double* y, cudaStream_t st) {
     if (n == 0) return 0;

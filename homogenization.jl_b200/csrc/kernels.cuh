@@ -145,5 +145,6 @@ int launch_gather(const int64_t* idx, int64_t n, const double* src, double* dst,
 int launch_scatter(const int64_t* idx, int64_t n, const double* src, double* dst, cudaStream_t st);
 int launch_symmetrize_lower(double* A, int64_t n, cudaStream_t st);
 int launch_symv_full(const double* A, int64_t n, const double* x, double* y, cudaStream_t st);
+int launch_symv_half(const double* A, int64_t n, const double* x, double* y, double* work, cudaStream_t st);
 
 }  // namespace hmg

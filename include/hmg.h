@@ -97,7 +97,9 @@ int hmg_local_residual(hmg_ctx* ctx, int level);
 int hmg_restrict(hmg_ctx* ctx, int level_fine);
 /* interpolate_and_sum_to!(levels[k].x, P, levels[k-1].x) (src/interpolation.jl:52-62) */
 int hmg_interpolate_add(hmg_ctx* ctx, int level_fine);
-/* smoothing_steps!(steps, implicit, ops, curr, k) (src/multigrid.jl:46-71) */
+/* smoothing_steps!(steps, implicit, ops, curr, k) (src/multigrid.jl:46-71).  x and r end up as in the reference;
+ * p and Ap are scratch (the reference's last, dead update of p is skipped; the copy p = r is folded into the first
+ * CG update; the p buffer may be swapped with an internal one by the fused direction update). */
 int hmg_smoothing_steps(hmg_ctx* ctx, int level, int steps);
 
 /* BaseLevel (src/multigrid.jl:30-41): the caller's factorisation F = cholesky(A[interior,
@@ -141,7 +143,9 @@ int hmg_synchronize(hmg_ctx* ctx);
  * 2 = hmg_mul(top, 1.0, P, AP), 3 = local apply AP = constraint(A P), 4 = interface sum of AP,
  * 5 = local residual, 6 / 7 / 8 = the fused CG vector kernels (x,r update; p update; p = r with
  * rho), 9 = restriction level -> level-1, 10 = interpolation level-1 -> level, 11 = local apply with
- * the fused owner-weighted dot.  The operation is launched `reps` times back to back. */
+ * the fused owner-weighted dot, 12 = the fused direction update + product of a CG step (p' = R + beta P
+ * formed inside the apply kernel, AP = broadcast(constraint(A p'))).  The operation is launched `reps`
+ * times back to back. */
 int hmg_time_op(hmg_ctx* ctx, int op, int level, int steps, int reps, float* ms_out);
 /* number of kernel launches issued on the context's stream since creation */
 int64_t hmg_launch_count(const hmg_ctx* ctx);

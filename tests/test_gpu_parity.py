@@ -209,3 +209,18 @@ def test_batched_vcycles_equal_single_calls(pair):
     st.x.set(x0); st.b.set(b0)
     batched = hmg.vcycles(pair.g, bl, L, 3, 3)
     assert np.array_equal(np.array(single), batched)      # deterministic reductions
+
+
+@pytest.mark.parametrize("half_min", ["1", "1000000"], ids=["half-traffic-tiles", "full-matvec"])
+def test_coarse_solve_variants_match_oracle(monkeypatch, half_min):
+    """The coarsest-grid solve x = A^-1 b on GPU 0 (src/multigrid.jl:75-93): both mat-vec kernels (the tiled
+    half-traffic one is the default from 2048 interior nodes on) against the oracle's sparse direct solve, on a base
+    mesh with 19^2 = 361 interior nodes (3 x 3 tiles)."""
+    monkeypatch.setenv("HMG_SYMV_HALF_MIN", half_min)
+    p = Pair(2, 20, 3, lam=0.7)
+    try:
+        ho, hg, xo, xg = _vcycle_history(p, 3, True)
+        assert np.all(np.abs(hg - ho) <= 1e-10 * ho), (ho, hg)
+        assert relerr(xg, xo) <= 1e-10
+    finally:
+        p.close()
