@@ -155,8 +155,10 @@ struct hmg_ctx {
     double *ubase = nullptr, *bint = nullptr, *xint = nullptr;
     double* symv_work = nullptr;         // per-tile partial sums of the half-traffic coarse mat-vec
     // staging
-    double* staging = nullptr;
+    double* staging[2] = {nullptr, nullptr};       // double-buffered: the copy of chunk i+1 overlaps the permutation of chunk i
     size_t staging_bytes = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_permuted[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
 
@@ -604,10 +606,25 @@ double read_scalar(hmg_ctx* c, int slot) {
     return v;
 }
 void ensure_staging(hmg_ctx* c, size_t bytes) {
+    if (!c->copy_stream) {
+        CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int q = 0; q < 2; ++q) {
+            CUDA_OK(cudaEventCreateWithFlags(&c->ev_copied[q], cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&c->ev_permuted[q], cudaEventDisableTiming));
+        }
+    }
     if (c->staging_bytes >= bytes) return;
-    if (c->staging) c->dfree(c->staging);
-    c->staging = c->dalloc<double>(bytes / sizeof(double), false);
+    for (int q = 0; q < 2; ++q) {
+        if (c->staging[q]) c->dfree(c->staging[q]);
+        c->staging[q] = c->dalloc<double>(bytes / sizeof(double), false);
+    }
     c->staging_bytes = bytes;
+}
+// columns per staged chunk: ~128 MB, whole units
+int64_t staging_chunk(hmg_ctx* c, int nf) {
+    int64_t chunk = std::max<int64_t>(1, (int64_t)(128 << 20) / ((int64_t)nf * 8));
+    chunk = std::max<int64_t>(c->W, chunk / c->W * c->W);
+    return std::min<int64_t>(chunk, (c->ne + c->W - 1) / c->W * c->W);
 }
 
 void set_coarse_dense(hmg_ctx* c, int64_t n, const std::vector<int64_t>& colptr, const std::vector<int64_t>& rowval,
@@ -721,6 +738,11 @@ int hmg_destroy(hmg_ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->comm) nccl().CommDestroy(c->comm);
     for (void* p : c->allocs) cudaFree(p);
+    for (int q = 0; q < 2; ++q) {
+        if (c->ev_copied[q]) cudaEventDestroy(c->ev_copied[q]);
+        if (c->ev_permuted[q]) cudaEventDestroy(c->ev_permuted[q]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -768,13 +790,21 @@ int hmg_upload(hmg_ctx* c, int level, int which, const double* host, int64_t ld_
     const int nf = L.view.nf;
     HMG_CHECK(host != nullptr && ld_host >= nf, "bad host matrix");
     double* dst = c->vecp(level, which);
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(c->ne, (int64_t)(256 << 20) / (nf * 8)));
+    const int64_t chunk = staging_chunk(c, nf);
     ensure_staging(c, (size_t)chunk * nf * 8);
-    for (int64_t c0 = 0; c0 < c->ne; c0 += chunk) {
+    // copy stream: host -> staging[i & 1]; main stream: staging -> device layout.  Events order the two.
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    int i = 0;
+    for (int64_t c0 = 0; c0 < c->ne; c0 += chunk, ++i) {
         const int64_t nc = std::min(chunk, c->ne - c0);
-        CUDA_OK(cudaMemcpy2DAsync(c->staging, (size_t)nf * 8, host + c0 * ld_host, (size_t)ld_host * 8, (size_t)nf * 8,
-                                  (size_t)nc, cudaMemcpyHostToDevice, c->stream));
-        check_launch(c, launch_permute_in(L.view, L.hier2lat, c->staging, nf, dst, c0, nc, c->stream));
+        const int q = i & 1;
+        if (i >= 2) CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_permuted[q], 0));
+        CUDA_OK(cudaMemcpy2DAsync(c->staging[q], (size_t)nf * 8, host + c0 * ld_host, (size_t)ld_host * 8, (size_t)nf * 8,
+                                  (size_t)nc, cudaMemcpyHostToDevice, c->copy_stream));
+        CUDA_OK(cudaEventRecord(c->ev_copied[q], c->copy_stream));
+        CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copied[q], 0));
+        check_launch(c, launch_permute_in(L.view, L.hier2lat, c->staging[q], nf, dst, c0, nc, c->stream));
+        CUDA_OK(cudaEventRecord(c->ev_permuted[q], c->stream));
     }
     CUDA_OK(cudaStreamSynchronize(c->stream));
     HMG_API_END
@@ -788,15 +818,23 @@ int hmg_download(hmg_ctx* c, int level, int which, double* host, int64_t ld_host
     const int nf = L.view.nf;
     HMG_CHECK(host != nullptr && ld_host >= nf, "bad host matrix");
     const double* src = c->vecp(level, which);
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(c->ne, (int64_t)(256 << 20) / (nf * 8)));
+    const int64_t chunk = staging_chunk(c, nf);
     ensure_staging(c, (size_t)chunk * nf * 8);
-    for (int64_t c0 = 0; c0 < c->ne; c0 += chunk) {
+    // main stream: device layout -> staging[i & 1]; copy stream: staging -> host
+    int i = 0;
+    for (int64_t c0 = 0; c0 < c->ne; c0 += chunk, ++i) {
         const int64_t nc = std::min(chunk, c->ne - c0);
-        check_launch(c, launch_permute_out(L.view, L.hier2lat, src, c->staging, nf, c0, nc, c->stream));
-        CUDA_OK(cudaMemcpy2DAsync(host + c0 * ld_host, (size_t)ld_host * 8, c->staging, (size_t)nf * 8, (size_t)nf * 8,
-                                  (size_t)nc, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_OK(cudaStreamSynchronize(c->stream));
+        const int q = i & 1;
+        if (i >= 2) CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copied[q], 0));
+        check_launch(c, launch_permute_out(L.view, L.hier2lat, src, c->staging[q], nf, c0, nc, c->stream));
+        CUDA_OK(cudaEventRecord(c->ev_permuted[q], c->stream));
+        CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_permuted[q], 0));
+        CUDA_OK(cudaMemcpy2DAsync(host + c0 * ld_host, (size_t)ld_host * 8, c->staging[q], (size_t)nf * 8, (size_t)nf * 8,
+                                  (size_t)nc, cudaMemcpyDeviceToHost, c->copy_stream));
+        CUDA_OK(cudaEventRecord(c->ev_copied[q], c->copy_stream));
     }
+    CUDA_OK(cudaStreamSynchronize(c->copy_stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
     HMG_API_END
 }
 

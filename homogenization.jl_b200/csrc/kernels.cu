@@ -1272,16 +1272,70 @@ __global__ void __launch_bounds__(256) permute_out_kernel(const LevelView L, con
         staged[c * lds + h] = src[((e >> L.wshift) * (int64_t)L.nf + h2l[h]) * L.W + (e & (L.W - 1))];
     }
 }
+// W = 32, e0 a multiple of 32: 32 x 32 tiles through shared memory, so that both sides move whole 256-byte lines
+// (the host side is contiguous along a column, the device side along the 32 columns of a unit)
+template <bool IN>
+__global__ void __launch_bounds__(256) permute_tile_kernel(int nf, const int32_t* __restrict__ h2l, double* __restrict__ staged,
+                                                           int64_t lds, double* __restrict__ dev, int64_t e0, int64_t ncols) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t ntr = (nf + 31) / 32;
+    const int64_t ntiles = ((ncols + 31) / 32) * ntr;
+    for (int64_t b = blockIdx.x; b < ntiles; b += gridDim.x) {
+        const int64_t ub = b / ntr;                       // unit of the chunk
+        const int h0 = (int)(b - ub * ntr) * 32;
+        const int64_t cb = ub * 32;                       // first column of the unit inside the chunk
+        double* unit = dev + ((e0 + cb) >> 5) * (int64_t)nf * 32;
+        if (IN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t c = cb + ty + 8 * j;
+                const int h = h0 + tx;
+                tile[ty + 8 * j][tx] = (c < ncols && h < nf) ? staged[c * lds + h] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int h = h0 + ty + 8 * j;
+                if (h < nf) unit[(int64_t)__ldg(h2l + h) * 32 + tx] = tile[tx][ty + 8 * j];     // padding columns: zero
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int h = h0 + ty + 8 * j;
+                tile[tx][ty + 8 * j] = h < nf ? unit[(int64_t)__ldg(h2l + h) * 32 + tx] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t c = cb + ty + 8 * j;
+                const int h = h0 + tx;
+                if (c < ncols && h < nf) staged[c * lds + h] = tile[ty + 8 * j][tx];
+            }
+        }
+        __syncthreads();
+    }
+}
 int launch_permute_in(const LevelView& L, const int32_t* h2l, const double* staged, int64_t lds, double* dst, int64_t e0,
                       int64_t ncols, cudaStream_t st) {
     if (ncols == 0) return 0;
-    permute_in_kernel<<<grid_for(ncols * L.nf, 256), 256, 0, st>>>(L, h2l, staged, lds, dst, e0, ncols);
+    if (L.W == 32 && (e0 & 31) == 0) {
+        const int64_t ntiles = ((ncols + 31) / 32) * ((L.nf + 31) / 32);
+        permute_tile_kernel<true><<<grid_for(ntiles, 1, 148 * 16), 256, 0, st>>>(L.nf, h2l, const_cast<double*>(staged), lds, dst, e0, ncols);
+    } else {
+        permute_in_kernel<<<grid_for(ncols * L.nf, 256), 256, 0, st>>>(L, h2l, staged, lds, dst, e0, ncols);
+    }
     return 1;
 }
 int launch_permute_out(const LevelView& L, const int32_t* h2l, const double* src, double* staged, int64_t lds, int64_t e0,
                        int64_t ncols, cudaStream_t st) {
     if (ncols == 0) return 0;
-    permute_out_kernel<<<grid_for(ncols * L.nf, 256), 256, 0, st>>>(L, h2l, src, staged, lds, e0, ncols);
+    if (L.W == 32 && (e0 & 31) == 0) {
+        const int64_t ntiles = ((ncols + 31) / 32) * ((L.nf + 31) / 32);
+        permute_tile_kernel<false><<<grid_for(ntiles, 1, 148 * 16), 256, 0, st>>>(L.nf, h2l, staged, lds, const_cast<double*>(src), e0, ncols);
+    } else {
+        permute_out_kernel<<<grid_for(ncols * L.nf, 256), 256, 0, st>>>(L, h2l, src, staged, lds, e0, ncols);
+    }
     return 1;
 }
 
