@@ -100,6 +100,8 @@ struct LevelDev {
 
 }  // namespace
 
+namespace { void nccl_destroy(ncclComm_t comm) { nccl().CommDestroy(comm); } }
+
 struct hmg_ctx {
     int dim = 0, nlevels = 0, device = 0;
     int rank = 0, nranks = 1;
@@ -162,6 +164,22 @@ struct hmg_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
 
+    ~hmg_ctx() {
+        // also runs when hmg_create fails half-way: nothing of the context outlives it
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        if (copy_stream) cudaStreamSynchronize(copy_stream);
+        if (comm) nccl_destroy(comm);
+        for (void* p : allocs) cudaFree(p);
+        for (int q = 0; q < 2; ++q) {
+            if (ev_copied[q]) cudaEventDestroy(ev_copied[q]);
+            if (ev_permuted[q]) cudaEventDestroy(ev_permuted[q]);
+        }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
     template <class T> T* dalloc(size_t n, bool zero = true) {
         void* p = nullptr;
         if (n == 0) n = 1;
@@ -734,18 +752,6 @@ int hmg_nccl_unique_id(void* out128) {
 int hmg_destroy(hmg_ctx* c) {
     HMG_API_BEGIN
     if (!c) return 0;
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    if (c->comm) nccl().CommDestroy(c->comm);
-    for (void* p : c->allocs) cudaFree(p);
-    for (int q = 0; q < 2; ++q) {
-        if (c->ev_copied[q]) cudaEventDestroy(c->ev_copied[q]);
-        if (c->ev_permuted[q]) cudaEventDestroy(c->ev_permuted[q]);
-    }
-    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     HMG_API_END
 }

@@ -652,19 +652,21 @@ static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool f
 
 template <int DIM, int W, int MODE, bool DOT, bool FUSEP = false>
 static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
-    static size_t configured = 0;
-    static int sms = 0;
+    // per device: the opt-in shared-memory size is a per-device function attribute
+    static size_t configured_dev[64] = {0};
+    static int sms_dev[64] = {0};
     auto kern = apply_kernel<DIM, W, MODE, DOT, FUSEP>;
     const ApplyConfig& cfg = FUSEP ? a.cfg_fused : (MODE == APPLY_AX ? a.cfg : a.cfg_rhs);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return -1;
+    size_t& configured = configured_dev[dev];
+    int& sms = sms_dev[dev];
     if (cfg.smem_bytes > configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes) != cudaSuccess) return 0;
         configured = cfg.smem_bytes;
     }
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    if (sms == 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     ApplyParams<DIM> p;
     memcpy(&p.T, a.tab, sizeof(p.T));
     p.x = a.x; p.y = a.y;
