@@ -19,7 +19,7 @@ function main(dim::Int, c::Int, refinements::Int; steps = 3)
     Random.seed!(1)
     base = hypercube(dim == 2 ? Tri64 : Tet64, c, origin = ntuple(_ -> -c / 2, dim))
     σ_cells = generate_conductivity(base, c)
-    cond = conductivity_per_element(base, σ_cells, ntuple(_ -> c / 2 + 1.0, dim))
+    cond = conductivity_per_element(base, σ_cells, SVector{dim,Float64}(ntuple(_ -> c / 2 + 1.0, dim)))
     grids = refinements + 1
     implicit = ImplicitFineGrid(base, grids)
     constraint = ZeroDirichletConstraint(list_boundary_nodes_edges_faces(base)...)
