@@ -224,3 +224,42 @@ def test_coarse_solve_variants_match_oracle(monkeypatch, half_min):
         assert relerr(xg, xo) <= 1e-10
     finally:
         p.close()
+
+
+def _irregular_mesh(dim):
+    """A base mesh that is not a lattice of unit cells: vertices jittered (every element has its own Jacobian),
+    elements in a shuffled order (units of 32 mix orientations, neighbours are far apart in the column order)."""
+    from oracle.mesh import hypercube, sort_element_nodes
+    rng = np.random.default_rng(11)
+    m = hypercube(dim, 3 if dim == 3 else 5)
+    nodes = m.nodes.copy()
+    lo, hi = nodes.min(axis=0), nodes.max(axis=0)
+    inner = np.all((nodes > lo) & (nodes < hi), axis=1)
+    nodes[inner] += 0.15 * (rng.random((int(inner.sum()), dim)) - 0.5)
+    elements = sort_element_nodes(m.elements)[rng.permutation(m.nelements)]
+    return hmg.Mesh(nodes, elements), rng.uniform(1.0, 9.0, size=(m.nelements, dim))
+
+
+@pytest.mark.parametrize("dim,levels", [(2, 5), (3, 4)], ids=["tri-jittered-L5", "tet-jittered-L4"])
+def test_irregular_base_mesh_matches_oracle(dim, levels):
+    """Nothing in the device path assumes the checkerboard lattice: A*x and the V-cycle on a jittered, shuffled
+    base mesh with a random anisotropic coefficient per element."""
+    mesh, sigma = _irregular_mesh(dim)
+    p = Pair(dim, 0, levels, lam=0.9, mesh=mesh, sigma=sigma)
+    try:
+        L = levels
+        v = p.rand(L)
+        oi.broadcast_interfaces(v, p.oimp, L)
+        oi.apply_constraint(v, L, p.constraint, p.oimp)
+        st = p.g.state(L)
+        st.p.set(v)
+        hmg.apply_global(p.g, st.p, st.Ap)
+        Ap = oo.mul(1.0, p.obase, p.oops[L - 1], v, np.zeros_like(v))
+        oi.apply_constraint(Ap, L, p.constraint, p.oimp)
+        oi.broadcast_interfaces(Ap, p.oimp, L)
+        assert relerr(st.Ap.get(), Ap) <= 1e-12
+        ho, hg, xo, xg = _vcycle_history(p, 4, True)
+        assert np.all(np.abs(hg - ho) <= 1e-10 * ho), (ho, hg)
+        assert relerr(xg, xo) <= 1e-10
+    finally:
+        p.close()
