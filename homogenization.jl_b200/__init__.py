@@ -13,4 +13,5 @@ from ._lib import HmgError, LIB_PATH, PROTOTYPES, load        # noqa: F401
 from .api import *                                            # noqa: F401,F403
 from .api import Mesh, DeviceMatrix, LevelState, ImplicitFineGrid, BaseLevel  # noqa: F401
 from . import inputs                                          # noqa: F401
+from . import vtk                                             # noqa: F401
 from . import driver                                          # noqa: F401

@@ -29,6 +29,8 @@ PROTOTYPES = {
     "hmg_set_sigma": (_i32, [_p, _p]),
     "hmg_upload": (_i32, [_p, _i32, _i32, _p, _i64]),
     "hmg_download": (_i32, [_p, _i32, _i32, _p, _i64]),
+    "hmg_download_rows": (_i32, [_p, _i32, _i32, _i64, _p, _i64]),
+    "hmg_copy_columns_from": (_i32, [_p, _i32, _i32, _p, _i32]),
     "hmg_fill": (_i32, [_p, _i32, _i32, _f64]),
     "hmg_copy": (_i32, [_p, _i32, _i32, _i32]),
     "hmg_axpy": (_i32, [_p, _i32, _f64, _i32, _i32]),
@@ -53,6 +55,7 @@ PROTOTYPES = {
     "hmg_integrate_terms": (_i32, [_p, _i32, _i32, _i64, _pd]),
     "hmg_integrate_area": (_i32, [_p, _i64, _pd]),
     "hmg_next_rhs": (_i32, [_p, _i32, _i32]),
+    "hmg_refined_mesh": (_i32, [_p, _i32, _p, _p, C.POINTER(_i64)]),
     "hmg_synchronize": (_i32, [_p]),
     "hmg_time_op": (_i32, [_p, _i32, _i32, _i32, _i32, C.POINTER(C.c_float)]),
     "hmg_launch_count": (_i64, [_p]),
@@ -64,6 +67,7 @@ PROTOTYPES = {
 HOST_PROTOTYPES = {
     "hmg_host_last_error": (C.c_char_p, []),
     "hmg_host_reference": (_i32, [_i32, _i32, _i32, _p, _p, _p, _pd]),
+    "hmg_host_refined_mesh": (_i32, [_i32, _i32, _i32, _p, _p, C.POINTER(_i64)]),
     "hmg_host_local_matrix": (_i32, [_i32, _i32, _i32, _p, _p]),
     "hmg_host_transfer_matrix": (_i32, [_i32, _i32, _i32, _p]),
     "hmg_host_interface_rows": (_i32, [_i32, _i32, _i32, _i32, _i32, _p, C.POINTER(_i64)]),

@@ -67,6 +67,28 @@ class DeviceMatrix:
                                              out.ctypes.data_as(C.c_void_p), out.shape[0]))
         return out
 
+    def get_rows(self, nrows):
+        """Array(device[1:nrows, :]): the first ``nrows`` hierarchical rows of every column -- with
+        nrows = Nf(k) the values on the nodes of the coarser level k, the slice export_unknown takes
+        (src/examples/homogenized_coefficients.jl:84).  Only nrows x Ne_local doubles are transferred."""
+        nrows = int(nrows)
+        if not 0 <= nrows <= self.shape[0]:
+            raise ValueError(f"nrows must be in 0..{self.shape[0]}")
+        out = np.empty((nrows, self.shape[1]), dtype=np.float64, order="F")
+        check(self.implicit.lib.hmg_download_rows(self.implicit.ctx, self.level, self.which, nrows,
+                                                  out.ctypes.data_as(C.c_void_p), max(nrows, 1)))
+        return out
+
+    def copy_columns_from(self, other):
+        """self = other[:, OneTo(Ne_local(self))] on the device, across contexts: shrink_level_state
+        (src/examples/homogenized_coefficients.jl:54-60) without a host round trip.  ``self`` lives in a
+        context created on an element prefix of ``other``'s base mesh."""
+        if other.level != self.level:
+            raise ValueError("copy_columns_from: levels differ")
+        check(self.implicit.lib.hmg_copy_columns_from(self.implicit.ctx, self.level, self.which,
+                                                      other.implicit.ctx, other.which))
+        return self
+
     def fill(self, value):
         check(self.implicit.lib.hmg_fill(self.implicit.ctx, self.level, self.which, float(value)))
         return self

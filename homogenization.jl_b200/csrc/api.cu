@@ -656,6 +656,14 @@ void set_coarse_dense(hmg_ctx* c, int64_t n, const std::vector<int64_t>& colptr,
     if (c->symv_work) { c->dfree(c->symv_work); c->symv_work = nullptr; }
     c->n_interior = n;
     if (c->rank != 0) return;            // the coarsest-grid solve stays on rank 0
+    {
+        // the dense inverse is n^2 doubles (twice that while the 64-bit path forms it): refuse what cannot fit
+        size_t free_b = 0, total_b = 0;
+        CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+        const bool wide_ = n >= 46340 || getenv("HMG_COARSE_64BIT") != nullptr;
+        const double need = (wide_ ? 2.0 : 1.0) * 8.0 * (double)n * (double)n + (double)(256u << 20);
+        HMG_CHECK(need <= (double)free_b, "coarse problem too large for the dense coarse solver (the inverse does not fit the device memory left)");
+    }
     c->interior_idx = c->dupload(interior0);
     c->bint = c->dalloc<double>(n);
     c->xint = c->dalloc<double>(n);
@@ -676,28 +684,60 @@ void set_coarse_dense(hmg_ctx* c, int64_t n, const std::vector<int64_t>& colptr,
             CUDA_OK(cudaMemcpy(c->Ainv + (size_t)c0 * n, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
         }
     }
-    cusolverDnHandle_t h;
-    CUSOLVER_OK(cusolverDnCreate(&h));
-    CUSOLVER_OK(cusolverDnSetStream(h, c->stream));
-    int lwork1 = 0, lwork2 = 0;
-    CUSOLVER_OK(cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_LOWER, (int)n, c->Ainv, (int)n, &lwork1));
-    CUSOLVER_OK(cusolverDnDpotri_bufferSize(h, CUBLAS_FILL_MODE_LOWER, (int)n, c->Ainv, (int)n, &lwork2));
-    const int lwork = std::max(lwork1, lwork2);
-    double* work = c->dalloc<double>(lwork, false);
+    // the handle (and the parameter block of the 64-bit interface) must not outlive a failed check
+    struct Solver {
+        cusolverDnHandle_t h = nullptr;
+        cusolverDnParams_t params = nullptr;
+        ~Solver() {
+            if (params) cusolverDnDestroyParams(params);
+            if (h) cusolverDnDestroy(h);
+        }
+    } sv;
+    CUSOLVER_OK(cusolverDnCreate(&sv.h));
+    CUSOLVER_OK(cusolverDnSetStream(sv.h, c->stream));
     int* info = c->dalloc<int>(1);
-    CUSOLVER_OK(cusolverDnDpotrf(h, CUBLAS_FILL_MODE_LOWER, (int)n, c->Ainv, (int)n, work, lwork, info));
     int hinfo = 0;
-    CUDA_OK(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
-    HMG_CHECK(hinfo == 0, "coarse matrix is not positive definite (potrf failed)");
-    CUSOLVER_OK(cusolverDnDpotri(h, CUBLAS_FILL_MODE_LOWER, (int)n, c->Ainv, (int)n, work, lwork, info));
-    CUDA_OK(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
-    HMG_CHECK(hinfo == 0, "potri failed on the coarse matrix");
+    auto read_info = [&]() {
+        CUDA_OK(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        return hinfo;
+    };
+    // potri indexes the matrix with 32-bit integers: from n = 46 340 (n^2 >= 2^31) on -- or on request, for the tests --
+    // the inverse is formed through the 64-bit interface instead: A = L L', then L L' X = I.  It costs a second n x n
+    // matrix during the setup (the factor is freed afterwards) and 2 n^3 instead of 2/3 n^3 operations.
+    const bool wide = n >= 46340 || getenv("HMG_COARSE_64BIT") != nullptr;
+    if (!wide) {
+        int lwork1 = 0, lwork2 = 0;
+        CUSOLVER_OK(cusolverDnDpotrf_bufferSize(sv.h, CUBLAS_FILL_MODE_LOWER, (int)n, c->Ainv, (int)n, &lwork1));
+        CUSOLVER_OK(cusolverDnDpotri_bufferSize(sv.h, CUBLAS_FILL_MODE_LOWER, (int)n, c->Ainv, (int)n, &lwork2));
+        const int lwork = std::max(lwork1, lwork2);
+        double* work = c->dalloc<double>(lwork, false);
+        CUSOLVER_OK(cusolverDnDpotrf(sv.h, CUBLAS_FILL_MODE_LOWER, (int)n, c->Ainv, (int)n, work, lwork, info));
+        HMG_CHECK(read_info() == 0, "coarse matrix is not positive definite (potrf failed)");
+        CUSOLVER_OK(cusolverDnDpotri(sv.h, CUBLAS_FILL_MODE_LOWER, (int)n, c->Ainv, (int)n, work, lwork, info));
+        HMG_CHECK(read_info() == 0, "potri failed on the coarse matrix");
+        c->dfree(work);
+    } else {
+        CUSOLVER_OK(cusolverDnCreateParams(&sv.params));
+        size_t wdev = 0, whost = 0;
+        CUSOLVER_OK(cusolverDnXpotrf_bufferSize(sv.h, sv.params, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, c->Ainv, n, CUDA_R_64F,
+                                                &wdev, &whost));
+        char* dwork = c->dalloc<char>(wdev, false);
+        std::vector<char> hwork(whost + 1);
+        CUSOLVER_OK(cusolverDnXpotrf(sv.h, sv.params, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, c->Ainv, n, CUDA_R_64F, dwork, wdev,
+                                     hwork.data(), whost, info));
+        HMG_CHECK(read_info() == 0, "coarse matrix is not positive definite (potrf failed)");
+        c->dfree(dwork);
+        double* inv = c->dalloc<double>((size_t)n * n);           // zeroed
+        check_launch(c, launch_set_diagonal(inv, n, 1.0, c->stream));
+        CUSOLVER_OK(cusolverDnXpotrs(sv.h, sv.params, CUBLAS_FILL_MODE_LOWER, n, n, CUDA_R_64F, c->Ainv, n, CUDA_R_64F, inv, n, info));
+        HMG_CHECK(read_info() == 0, "potrs failed on the coarse matrix");
+        c->dfree(c->Ainv);
+        c->Ainv = inv;
+    }
+    // exactly symmetric from the lower triangle (the half-traffic mat-vec reads a tile as T and as T')
     check_launch(c, launch_symmetrize_lower(c->Ainv, n, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    cusolverDnDestroy(h);
-    c->dfree(work);
     c->dfree(info);
 }
 
@@ -844,6 +884,55 @@ int hmg_download(hmg_ctx* c, int level, int which, double* host, int64_t ld_host
     HMG_API_END
 }
 
+int hmg_download_rows(hmg_ctx* c, int level, int which, int64_t nrows, double* host, int64_t ld_host) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    CUDA_OK(cudaSetDevice(c->device));
+    LevelDev& L = c->level(level);
+    const int nf = L.view.nf;
+    HMG_CHECK(nrows >= 0 && nrows <= nf, "download_rows: more rows than the level has nodes");
+    HMG_CHECK(host != nullptr && ld_host >= nrows, "bad host matrix");
+    if (nrows == 0 || c->ne == 0) return 0;
+    const double* src = c->vecp(level, which);
+    // chunks of ~128 MB of *output*; the staging buffers are shared with hmg_upload / hmg_download
+    int64_t chunk = std::max<int64_t>(c->W, (int64_t)(128 << 20) / (nrows * 8) / c->W * c->W);
+    chunk = std::min<int64_t>(chunk, (c->ne + c->W - 1) / c->W * c->W);
+    ensure_staging(c, (size_t)chunk * nrows * 8);
+    int i = 0;
+    for (int64_t c0 = 0; c0 < c->ne; c0 += chunk, ++i) {
+        const int64_t nc = std::min(chunk, c->ne - c0);
+        const int q = i & 1;
+        if (i >= 2) CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copied[q], 0));
+        check_launch(c, launch_permute_rows_out(L.view, L.hier2lat, src, c->staging[q], nrows, (int)nrows, c0, nc, c->stream));
+        CUDA_OK(cudaEventRecord(c->ev_permuted[q], c->stream));
+        CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_permuted[q], 0));
+        CUDA_OK(cudaMemcpy2DAsync(host + c0 * ld_host, (size_t)ld_host * 8, c->staging[q], (size_t)nrows * 8, (size_t)nrows * 8,
+                                  (size_t)nc, cudaMemcpyDeviceToHost, c->copy_stream));
+        CUDA_OK(cudaEventRecord(c->ev_copied[q], c->copy_stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(c->copy_stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    HMG_API_END
+}
+
+int hmg_copy_columns_from(hmg_ctx* dst, int level, int dst_which, hmg_ctx* src, int src_which) {
+    HMG_API_BEGIN
+    NEED_CTX(dst);
+    NEED_CTX(src);
+    HMG_CHECK(dst != src, "copy_columns_from: source and destination are the same context");
+    HMG_CHECK(dst->nranks == 1 && src->nranks == 1, "copy_columns_from: partitioned contexts keep different column sets");
+    HMG_CHECK(dst->dim == src->dim && dst->device == src->device && dst->W == src->W, "copy_columns_from: contexts do not match");
+    HMG_CHECK(dst->level(level).view.nf == src->level(level).view.nf, "copy_columns_from: the level has a different shape");
+    HMG_CHECK(dst->ne <= src->ne, "copy_columns_from: the destination has more columns than the source");
+    CUDA_OK(cudaSetDevice(dst->device));
+    const double* from = src->vecp(level, src_which);
+    double* to = dst->vecp(level, dst_which);
+    CUDA_OK(cudaStreamSynchronize(src->stream));      // the source vector is complete before the other stream reads it
+    check_launch(dst, launch_copy_columns(dst->level(level).view, dst->ne, to, from, dst->stream));
+    CUDA_OK(cudaStreamSynchronize(dst->stream));      // the caller may destroy `src` right away
+    HMG_API_END
+}
+
 int hmg_fill(hmg_ctx* c, int level, int which, double value) {
     HMG_API_BEGIN
     NEED_CTX(c);
@@ -959,7 +1048,6 @@ int hmg_set_coarse_matrix(hmg_ctx* c, int64_t n, const int64_t* colptr, const in
     NEED_CTX(c);
     CUDA_OK(cudaSetDevice(c->device));
     HMG_CHECK(n > 0 && colptr && rowval && nzval && interior_nodes, "bad coarse matrix");
-    HMG_CHECK(n < 46000, "coarse problem too large for the dense coarse solver");
     std::vector<int64_t> cp(colptr, colptr + n + 1), in0(interior_nodes, interior_nodes + n);
     for (auto& v : cp) v -= 1;
     for (auto& v : in0) { v -= 1; HMG_CHECK(v >= 0 && v < c->nn, "interior node out of range"); }
@@ -981,7 +1069,6 @@ int hmg_assemble_coarse(hmg_ctx* c) {
     const std::vector<int64_t>& interior = c->topo.interior_nodes;
     const int64_t n = (int64_t)interior.size();
     HMG_CHECK(n > 0, "base mesh has no interior nodes");
-    HMG_CHECK(n < 46000, "coarse problem too large for the dense coarse solver");
     std::vector<int64_t> pos(c->nn, -1);
     for (int64_t q = 0; q < n; ++q) pos[interior[q]] = q;
     const double fact = dim == 3 ? 6.0 : 2.0;
@@ -1255,6 +1342,20 @@ int hmg_time_op(hmg_ctx* c, int op, int level, int steps, int reps, float* ms_ou
     HMG_API_END
 }
 
+int hmg_refined_mesh(const hmg_ctx* c, int level, double* nodes, int64_t* elems1, int64_t* nel) {
+    HMG_API_BEGIN
+    NEED_CTX(c);
+    HMG_CHECK(level >= 1 && level <= c->nlevels, "level out of range");
+    const RefLevel& L = c->ref.lv[level - 1];
+    const int dim = c->dim;
+    if (nel) *nel = (int64_t)L.cells.size() / (dim + 1);
+    if (nodes)
+        for (int n = 0; n < L.nf; ++n)
+            for (int d = 0; d < dim; ++d) nodes[(size_t)n * dim + d] = (double)L.hier_coords[(size_t)n * 3 + d] / (double)L.m;
+    if (elems1)
+        for (size_t q = 0; q < L.cells.size(); ++q) elems1[q] = (int64_t)L.cells[q] + 1;
+    HMG_API_END
+}
 int64_t hmg_launch_count(const hmg_ctx* c) { return c ? c->launches : -1; }
 void* hmg_device_ptr(hmg_ctx* c, int level, int which) {
     try {

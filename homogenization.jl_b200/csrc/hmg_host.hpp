@@ -64,6 +64,11 @@ struct RefLevel {
     // [6|3][npe], then vertices [4|3]
     std::vector<uint16_t> iface_idx;
     double mass_total = 0.0;         // sum of all entries of the reference mass matrix
+    // refined_mesh(implicit, level) itself (src/implicit_fine_grid.jl:24), for construct_full_grid / the VTK export
+    // only: lattice coordinates of every hierarchical row [nf][3] and the fine elements [(dim+1) x nel] in hierarchical
+    // node ids, each index-sorted as refined_element leaves them (src/multilevel_reference.jl:56-58)
+    std::vector<int32_t> hier_coords;
+    std::vector<int32_t> cells;
 };
 
 struct RefElement {

@@ -171,6 +171,20 @@ int hmg_host_reference(int dim, int nlevels, int level, int64_t* sizes, int32_t*
     HOST_END
 }
 
+// refined_mesh(implicit, level): nodes dim x nf (reference coordinates, hierarchical order), elements (dim+1) x nel, 1-based
+int hmg_host_refined_mesh(int dim, int nlevels, int level, double* nodes, int64_t* elems1, int64_t* nel) {
+    HOST_BEGIN
+    RefElement ref = build_reference(dim, nlevels);
+    const RefLevel& L = get_level(ref, level);
+    if (nel) *nel = (int64_t)L.cells.size() / (dim + 1);
+    if (nodes)
+        for (int n = 0; n < L.nf; ++n)
+            for (int d = 0; d < dim; ++d) nodes[(size_t)n * dim + d] = (double)L.hier_coords[(size_t)n * 3 + d] / (double)L.m;
+    if (elems1)
+        for (size_t q = 0; q < L.cells.size(); ++q) elems1[q] = (int64_t)L.cells[q] + 1;
+    HOST_END
+}
+
 // dense nf x nf (column-major, hierarchical order) matrix of  sum_c coef[c] * (stencil table c)
 int hmg_host_local_matrix(int dim, int nlevels, int level, const double* coef, double* dense) {
     HOST_BEGIN

@@ -1182,6 +1182,25 @@ int launch_fill_columns(const LevelView& L, int64_t ne, double* x, double v, cud
     return 1;
 }
 
+// Column prefix of another context's vector (domain shrink, src/examples/homogenized_coefficients.jl:54-60: l.x[:, OneTo(n)]):
+// both layouts agree on the units of the prefix, only the last unit gets zero columns where the prefix ends.
+__global__ void __launch_bounds__(256) copy_columns_kernel(const LevelView L, int64_t ne, double* __restrict__ dst,
+                                                           const double* __restrict__ src) {
+    const int64_t nunits = (ne + L.W - 1) >> L.wshift;
+    const int64_t per_unit = (int64_t)L.nf * L.W;
+    const int64_t total = nunits * per_unit;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = (t / per_unit) * L.W + (t & (L.W - 1));
+        dst[t] = e < ne ? src[t] : 0.0;
+    }
+}
+int launch_copy_columns(const LevelView& L, int64_t ne, double* dst, const double* src, cudaStream_t st) {
+    if (ne == 0) return 0;
+    const int64_t nunits = (ne + L.W - 1) >> L.wshift;
+    copy_columns_kernel<<<grid_for(nunits * L.nf * L.W, 256, kVecBlocks), 256, 0, st>>>(L, ne, dst, src);
+    return 1;
+}
+
 // ------------------------------------------------------------------------------------------
 // driver functionals on the finest level (src/examples/homogenized_coefficients.jl:449-474, 592-667)
 // ------------------------------------------------------------------------------------------
@@ -1341,6 +1360,27 @@ int launch_permute_out(const LevelView& L, const int32_t* h2l, const double* src
     return 1;
 }
 
+// The first `nrows` hierarchical rows of the columns e0 .. e0+ncols (the nodes of a coarser level, src/examples/
+// homogenized_coefficients.jl:84: x[1 : nnodes(refined_mesh(implicit, level)), :]); lanes run over the columns, so the
+// big array is read in whole 256-byte lines.
+__global__ void __launch_bounds__(256) permute_rows_out_kernel(const LevelView L, const int32_t* __restrict__ h2l,
+                                                               const double* __restrict__ src, double* __restrict__ staged,
+                                                               int64_t lds, int nrows, int64_t e0, int64_t ncols) {
+    const int64_t total = ncols * nrows;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int h = (int)(t / ncols);
+        const int64_t c = t - (int64_t)h * ncols;
+        const int64_t e = e0 + c;
+        staged[c * lds + h] = src[((e >> L.wshift) * (int64_t)L.nf + __ldg(h2l + h)) * L.W + (e & (L.W - 1))];
+    }
+}
+int launch_permute_rows_out(const LevelView& L, const int32_t* h2l, const double* src, double* staged, int64_t lds, int nrows,
+                            int64_t e0, int64_t ncols, cudaStream_t st) {
+    if (ncols == 0 || nrows == 0) return 0;
+    permute_rows_out_kernel<<<grid_for(ncols * nrows, 256), 256, 0, st>>>(L, h2l, src, staged, lds, nrows, e0, ncols);
+    return 1;
+}
+
 // ------------------------------------------------------------------------------------------
 // level 1 <-> base vector, coarse solve helpers
 // ------------------------------------------------------------------------------------------
@@ -1417,6 +1457,14 @@ __global__ void symmetrize_kernel(double* __restrict__ A, int64_t n) {
 }
 int launch_symmetrize_lower(double* A, int64_t n, cudaStream_t st) {
     symmetrize_kernel<<<grid_for(n * n, 256), 256, 0, st>>>(A, n);
+    return 1;
+}
+__global__ void set_diagonal_kernel(double* __restrict__ A, int64_t n, double v) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) A[t * n + t] = v;
+}
+int launch_set_diagonal(double* A, int64_t n, double v, cudaStream_t st) {
+    if (n == 0) return 0;
+    set_diagonal_kernel<<<grid_for(n, 256), 256, 0, st>>>(A, n, v);
     return 1;
 }
 // y = A x for a full symmetric column-major matrix: one warp per column (= row), coalesced

@@ -138,12 +138,18 @@ int launch_permute_in(const LevelView& L, const int32_t* hier2lat, const double*
                       int64_t e0, int64_t ncols, cudaStream_t st);
 int launch_permute_out(const LevelView& L, const int32_t* hier2lat, const double* src, double* staged, int64_t ld_staged,
                        int64_t e0, int64_t ncols, cudaStream_t st);
+// the first `nrows` hierarchical rows only (export of a coarser level's nodes)
+int launch_permute_rows_out(const LevelView& L, const int32_t* hier2lat, const double* src, double* staged, int64_t ld_staged,
+                            int nrows, int64_t e0, int64_t ncols, cudaStream_t st);
+// dst = the first `ne` columns of src (same level shape; the columns padding dst's last unit are zeroed)
+int launch_copy_columns(const LevelView& L, int64_t ne, double* dst, const double* src, cudaStream_t st);
 // level 1 <-> base vector
 int launch_copy_to_base(const LevelView& L1, int64_t nn, const int32_t* node_first, const double* v, double* u, cudaStream_t st);
 int launch_distribute(int dim, const LevelView& L1, int64_t ne, const int32_t* elems, const double* u, double* v, cudaStream_t st);
 int launch_gather(const int64_t* idx, int64_t n, const double* src, double* dst, cudaStream_t st);
 int launch_scatter(const int64_t* idx, int64_t n, const double* src, double* dst, cudaStream_t st);
 int launch_symmetrize_lower(double* A, int64_t n, cudaStream_t st);
+int launch_set_diagonal(double* A, int64_t n, double v, cudaStream_t st);
 int launch_symv_full(const double* A, int64_t n, const double* x, double* y, cudaStream_t st);
 int launch_symv_half(const double* A, int64_t n, const double* x, double* y, double* work, cudaStream_t st);
 

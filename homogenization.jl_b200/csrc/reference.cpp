@@ -247,6 +247,19 @@ RefElement build_reference(int dim, int nlevels) {
         };
         auto pack = [&](const I3& c) { return dim == 3 ? pack3(m, c[0], c[1], c[2]) : pack2(m, c[0], c[1]); };
 
+        // (0) the refined reference mesh of this level (export only)
+        L.hier_coords.resize((size_t)L.nf * 3);
+        for (int n = 0; n < L.nf; ++n) {
+            const I3 c = lat(n);
+            for (int d = 0; d < 3; ++d) L.hier_coords[(size_t)n * 3 + d] = c[d];
+        }
+        L.cells.reserve(mesh.elems.size() * nv);
+        for (const auto& el : mesh.elems) {
+            int v[4] = {el[0], el[1], el[2], el[3]};
+            std::sort(v, v + nv);
+            for (int a = 0; a < nv; ++a) L.cells.push_back(v[a]);
+        }
+
         // (1) permutation hierarchical -> lattice, node info
         L.hier2lat.resize(L.nf);
         L.nodeinfo.assign(L.nf, 0);

@@ -1,7 +1,7 @@
 """Host-side mirror of ``checkerboard_homogenization`` (src/examples/homogenized_coefficients.jl:174-343)
 -- the caller of the hot path -- over the device API: every V-cycle, integral and right-hand side runs
 on the GPU; the host only keeps the outer loop, the radii and the domain shrink (a new context on the
-element / node prefix, the solution moved through the host once per outer step).
+element / node prefix; the solution's column prefix moves device to device, ``hmg_copy_columns_from``).
 
 Randomness is the caller's: ``sigma_cells`` (per unit cell diagonal conductivities) and ``x0`` (initial
 guess before interface sum and constraint) are inputs, because the reference draws them from Julia's
@@ -11,7 +11,7 @@ import math
 
 import numpy as np
 
-from . import api, inputs
+from . import api, inputs, vtk
 
 
 def compute_boundary_layer(lam, n):
@@ -39,9 +39,17 @@ def find_nodes_in_radius(mesh, radius):
 
 
 def checkerboard_homogenization(n, dim, refinements=2, smoothing_steps=3, tolerance=1e-4, xi=None, sigma_cells=None,
-                                x0=None, max_cycles=1000, log=None, device=0):
+                                x0=None, max_cycles=1000, log=None, device=0, save=None, save_prefix="", shrink="device"):
     """Returns (sigma, history); history[k] = [(residual norm, sigma + dsigma, |dsigma - dsigma_prev|), ...]
-    per V-cycle of outer step k -- the @info line of :287."""
+    per V-cycle of outer step k -- the @info line of :287.
+
+    ``save`` (:149-152, :219): a level 1..refinements+1 -- writes ``checkerboard.vtu`` (the base mesh with the
+    conductivities) and, after every outer step k, ``ahom_<k>.vtu`` (v_k on the nodes of that level; the reference
+    defines export_unknown for this but its driver only calls export_domain).  ``shrink``: "device" moves the column
+    prefix of x between the contexts on the GPU, "host" through a download / upload (the round-1 path, kept for
+    the comparison in the tests)."""
+    if shrink not in ("device", "host"):
+        raise ValueError("shrink must be 'device' or 'host'")
     xi = np.ones(dim) / math.sqrt(dim) if xi is None else np.asarray(xi, dtype=np.float64)      # :62-65
     lam = 1.0
     sigma = 0.0
@@ -50,7 +58,12 @@ def checkerboard_homogenization(n, dim, refinements=2, smoothing_steps=3, tolera
     base = inputs.order_by_magnitude(inputs.hypercube(dim, 2 * total_radius, origin=(-float(total_radius),) * dim))
     cond = inputs.conductivity_per_element(base, sigma_cells, (total_radius + 1.0,) * dim)
     grids = refinements + 1
+    if save is not None:
+        if not 1 <= save <= grids:
+            raise ValueError("save must be a level in 1..refinements+1")
+        vtk.export_domain(base, cond, save_prefix + "checkerboard")
     g = api.ImplicitFineGrid(base, grids, cond, lam=lam, device=device)
+    old = None
     top = g.state(grids)
     top.x.set(x0)
     api.broadcast_interfaces(top.x, g, grids)
@@ -76,6 +89,8 @@ def checkerboard_homogenization(n, dim, refinements=2, smoothing_steps=3, tolera
                     break
                 dsigma_prev = dsigma
             history.append(hist)
+            if save is not None:
+                vtk.export_unknown(g, top.x, k, save, save_prefix + f"ahom_{k}")
             sigma += dsigma
             lam /= 2
             box_radius = compute_box_radius(k + 1, n)
@@ -86,16 +101,26 @@ def checkerboard_homogenization(n, dim, refinements=2, smoothing_steps=3, tolera
             total_radius = box_radius + boundary_layer
             nn = find_nodes_in_radius(base, total_radius)
             ne = find_elements_in_radius(base, total_radius)
-            x_host = top.x.get()[:, :ne]
-            g.close()
             base = api.Mesh(base.nodes[:nn], base.elements[:ne])
             cond = np.ascontiguousarray(cond[:ne])
-            g = api.ImplicitFineGrid(base, grids, cond, lam=lam, device=device)
-            top = g.state(grids)
-            top.x.set(np.asfortranarray(x_host))
+            if shrink == "host":
+                x_host = top.x.get()[:, :ne]
+                g.close()
+                g = api.ImplicitFineGrid(base, grids, cond, lam=lam, device=device)
+                top = g.state(grids)
+                top.x.set(np.asfortranarray(x_host))
+            else:
+                old, old_top = g, top
+                g = api.ImplicitFineGrid(base, grids, cond, lam=lam, device=device)
+                top = g.state(grids)
+                top.x.copy_columns_from(old_top.x)         # shrink_level_state (:54-60) on the device
+                old.close()
+                old = None
             api.apply_constraint(top.x, grids, g)
             top.v.copy_from(top.x)                     # v_prev
             api.next_rhs(top.b, top.x, g)
     finally:
         g.close()
+        if old is not None:
+            old.close()
     return sigma, history

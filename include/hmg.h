@@ -75,6 +75,14 @@ int hmg_set_sigma(hmg_ctx* ctx, const double* sigma);
  * ld_host >= Nf(level).  Only the local columns are transferred (ne_local of them). */
 int hmg_upload(hmg_ctx* ctx, int level, int which, const double* host, int64_t ld_host);
 int hmg_download(hmg_ctx* ctx, int level, int which, double* host, int64_t ld_host);
+/* the first `nrows` rows of every local column: x[1 : nnodes(refined_mesh(implicit, k)), :] with nrows = Nf(k) are the
+ * values on the nodes of the coarser level k (export_unknown, src/examples/homogenized_coefficients.jl:81-87); only
+ * nrows x ne_local doubles cross PCIe.  ld_host >= nrows. */
+int hmg_download_rows(hmg_ctx* ctx, int level, int which, int64_t nrows, double* host, int64_t ld_host);
+/* domain shrink without a host round trip: dst.vec[dst_which] = src.vec[src_which][:, OneTo(ne_local(dst))]
+ * (shrink_level_state, src/examples/homogenized_coefficients.jl:54-60, caller :325-327).  Both contexts live on the same
+ * device, are not partitioned, and `dst` was created on an element prefix of `src`'s base mesh. */
+int hmg_copy_columns_from(hmg_ctx* dst, int level, int dst_which, hmg_ctx* src, int src_which);
 int hmg_fill(hmg_ctx* ctx, int level, int which, double value);          /* fill!           */
 int hmg_copy(hmg_ctx* ctx, int level, int dst, int src);                 /* copyto!         */
 int hmg_axpy(hmg_ctx* ctx, int level, double alpha, int x, int y);       /* axpy!           */
@@ -135,6 +143,12 @@ int hmg_integrate_first_term(hmg_ctx* ctx, int which_v, const double* xi, int64_
 int hmg_integrate_terms(hmg_ctx* ctx, int which_vk, int which_vkm1, int64_t nsubset, double* out);
 int hmg_integrate_area(hmg_ctx* ctx, int64_t nsubset, double* out);
 int hmg_next_rhs(hmg_ctx* ctx, int which_b, int which_x);
+
+/* refined_mesh(implicit, level) (src/implicit_fine_grid.jl:24): the refined reference element that construct_full_grid
+ * (src/implicit_fine_grid.jl:41-78) maps into every coarse element for the VTK export.  nodes[dim x Nf(level)] reference
+ * coordinates in hierarchical row order, elems1[(dim+1) x nel] 1-based, index-sorted per element; arrays may be NULL,
+ * *nel is always written.  Host data only. */
+int hmg_refined_mesh(const hmg_ctx* ctx, int level, double* nodes, int64_t* elems1, int64_t* nel);
 
 /* stream control / measurement */
 int hmg_synchronize(hmg_ctx* ctx);

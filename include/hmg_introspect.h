@@ -19,6 +19,10 @@ const char* hmg_host_last_error(void);
  * Restates what refined_element() fixes (src/multilevel_reference.jl:41-61). */
 int hmg_host_reference(int dim, int nlevels, int level, int64_t* sizes, int32_t* hier2lat, double* G,
                        double* mass_total);
+/* refined_mesh(implicit, level) (src/implicit_fine_grid.jl:24, built by refined_element, src/multilevel_reference.jl:41-61):
+ * nodes[dim x nf] reference coordinates in hierarchical row order, elems1[(dim+1) x nel] 1-based and index-sorted per
+ * element; arrays may be NULL (nel is always written).  Used by construct_full_grid for the VTK export. */
+int hmg_host_refined_mesh(int dim, int nlevels, int level, double* nodes, int64_t* elems1, int64_t* nel);
 /* dense nf x nf column-major, hierarchical order: sum_c coef[c] * table_c, i.e. the matrix
  * sum_kl |J| P_kl ops[k,l] + lambda |J| mass of src/apply_local_operators.jl:105-118 */
 int hmg_host_local_matrix(int dim, int nlevels, int level, const double* coef, double* dense);
