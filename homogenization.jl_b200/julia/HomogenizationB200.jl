@@ -15,8 +15,9 @@ module HomogenizationB200
 
 using Homogenization
 using Homogenization: Mesh, ImplicitFineGrid, LevelState, BaseLevel, L2PlusDivAGrad,
-                      ZeroDirichletConstraint, nelements, nnodes, refined_mesh, nlevels
-import Homogenization: broadcast_interfaces!, apply_constraint!, zero_out_all_but_one!,
+                      ZeroDirichletConstraint, nelements, nnodes, refined_mesh, nlevels, construct_full_grid
+using WriteVTK: vtk_grid, vtk_point_data
+import Homogenization: export_unknown, broadcast_interfaces!, apply_constraint!, zero_out_all_but_one!,
                        local_residual!, restrict_to!, interpolate_and_sum_to!, smoothing_steps!,
                        vcycle!, rhs_aξ∇v!, integrate_first_term, integrate_terms, integrate_area, next_rhs!
 import LinearAlgebra: mul!
@@ -213,6 +214,27 @@ function next_rhs!(b::DeviceMatrix, x::DeviceMatrix, implicit::ImplicitFineGrid,
     check(ccall((:hmg_set_lambda, libhmg), Cint, (Ptr{Cvoid}, Float64), b.grid.ctx, ops.λ))
     check(ccall((:hmg_next_rhs, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint), b.grid.ctx, b.which, x.which))
     nothing
+end
+
+# shrink_level_state(l, nf, n)   (src/examples/homogenized_coefficients.jl:54-60): the new grid lives on an element
+# prefix of the old one; l.x[:, OneTo(n)] moves device to device (both contexts on the same GPU).
+function shrink_to!(dst::DeviceMatrix, src::DeviceMatrix)
+    check(ccall((:hmg_copy_columns_from, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Cint),
+                dst.grid.ctx, dst.level, dst.which, src.grid.ctx, src.which))
+    dst
+end
+
+# x[1 : nnodes(refined_mesh(implicit, level)), :]   (export_unknown, :81-87): only the row prefix crosses PCIe
+function first_rows(x::DeviceMatrix, nrows::Integer)
+    out = Matrix{Float64}(undef, nrows, size(x, 2))
+    GC.@preserve out check(ccall((:hmg_download_rows, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Ptr{Float64}, Int64),
+                                 x.grid.ctx, x.level, x.which, nrows, out, max(nrows, 1)))
+    out
+end
+function export_unknown(base::Mesh{dim}, implicit::ImplicitFineGrid, x::DeviceMatrix, k::Int, level::Int) where {dim}
+    vtk_grid("ahom_$k", construct_full_grid(implicit, level)) do vtk
+        vtk_point_data(vtk, first_rows(x, nnodes(refined_mesh(implicit, level)))[:], "v")
+    end
 end
 
 """
