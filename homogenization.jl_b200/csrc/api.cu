@@ -891,8 +891,8 @@ int hmg_download_rows(hmg_ctx* c, int level, int which, int64_t nrows, double* h
     LevelDev& L = c->level(level);
     const int nf = L.view.nf;
     HMG_CHECK(nrows >= 0 && nrows <= nf, "download_rows: more rows than the level has nodes");
-    HMG_CHECK(host != nullptr && ld_host >= nrows, "bad host matrix");
     if (nrows == 0 || c->ne == 0) return 0;
+    HMG_CHECK(host != nullptr && ld_host >= nrows, "bad host matrix");
     const double* src = c->vecp(level, which);
     // chunks of ~128 MB of *output*; the staging buffers are shared with hmg_upload / hmg_download
     int64_t chunk = std::max<int64_t>(c->W, (int64_t)(128 << 20) / (nrows * 8) / c->W * c->W);

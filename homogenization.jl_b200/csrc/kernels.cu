@@ -724,13 +724,66 @@ int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st) {
 // SQ: additionally reduce sum over the touched entries of value^2 ( = owners * sum^2 per shared node) and add it
 // to S_TMP -- the part of rho = dot(r, r) that lives on interfaces; the apply kernel reduces the interior part
 // (src/multigrid.jl:54 without a pass over r).  With SQ the grid is bounded and blocks loop over virtual blocks.
-template <int DIM, int OP, bool SQ>
-__global__ void __launch_bounds__(256) interface_kernel(const LevelView L, const TopoView T, int64_t npair_blocks,
+// VAR 1 / 2 (HMG_IFACE_VARIANT, experiment; 2 = four nodes per step): BOTH owners of a pair work -- the steps of the node loop alternate between
+// them (a node is still handled by exactly one thread, which reads both copies, adds them and writes both), so every
+// lane with a partner is active and the own side of every access is a full 256-byte row; eight nodes per step (sixteen
+// loads in flight per thread) with 32-bit offsets inside the unit.  a + b is commutative, so the bits do not depend on
+// which owner adds.
+template <int DIM, int OP, bool SQ, int VAR = 0>
+__global__ void __launch_bounds__(256, VAR == 1 ? 3 : 1) interface_kernel(const LevelView L, const TopoView T, int64_t npair_blocks,
                                                         int64_t nvirtual, double* __restrict__ x, const Reducer R, int post) {
     constexpr int NF = DIM == 3 ? 4 : 3;
     const int W = L.W, ws = L.wshift, nf = L.nf;
     double sq = 0.0;
     for (int64_t vb = blockIdx.x; vb < nvirtual; vb += gridDim.x) {
+        if (VAR >= 1 && vb < npair_blocks) {
+            const int npc = DIM == 3 ? L.npf : L.npe;
+            const uint16_t* tab = L.iface_idx;
+            const int l = threadIdx.x & (W - 1), ks = threadIdx.x >> ws, nk = blockDim.x >> ws;
+            const int64_t u = vb / NF;
+            const int f = (int)(vb - u * NF);
+            const int64_t e = u * W + l;
+            if (e >= T.ne) continue;
+            const int32_t pr = T.partner[e * 4 + f];
+            if (pr < 0) continue;
+            const int64_t pe = pr >> 3;
+            const bool lower = e < pe;
+            double* own = x + u * (int64_t)nf * W + l;
+            double* oth = x + (pe >> ws) * (int64_t)nf * W + (pe & (W - 1));
+            const uint16_t* ta = tab + f * npc;
+            const uint16_t* tb = tab + (pr & 7) * npc;
+            constexpr int U = VAR == 1 ? 8 : 4;
+            // step s covers the nodes ks + nk * (q + s * U), q < U; the lower owner takes the even steps
+            for (int k0 = ks + (lower ? 0 : nk * U); k0 < npc; k0 += 2 * nk * U) {
+                int oa[U], ob[U];
+                double va[U], vo[U];
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    const int k = min(k0 + q * nk, npc - 1);
+                    oa[q] = (int)__ldg(ta + k) * W;
+                    ob[q] = (int)__ldg(tb + k) * W;
+                }
+                if (OP == 0) {
+#pragma unroll
+                    for (int q = 0; q < U; ++q) { va[q] = own[oa[q]]; vo[q] = oth[ob[q]]; }
+                }
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    if (k0 + q * nk >= npc) break;
+                    if (OP == 0) {
+                        const double sum = va[q] + vo[q];
+                        own[oa[q]] = sum;
+                        oth[ob[q]] = sum;
+                        if (SQ) sq = fma(2.0 * sum, sum, sq);
+                    } else if (lower) {
+                        oth[ob[q]] = 0.0;          // all but the first owner
+                    } else {
+                        own[oa[q]] = 0.0;
+                    }
+                }
+            }
+            continue;
+        }
         if (vb < npair_blocks) {
             const int npc = DIM == 3 ? L.npf : L.npe;
             const uint16_t* tab = L.iface_idx;   // 3D: faces first; 2D: edges first
@@ -839,6 +892,17 @@ static int launch_interface(int dim, const LevelView& L, const TopoView& T, doub
     const int64_t nvirtual = npair_blocks + nmulti_blocks;
     if (nvirtual == 0) return 0;
     const unsigned grid = (unsigned)(SQ ? std::min<int64_t>(nvirtual, R.max_blocks) : nvirtual);
+    static const int variant = getenv("HMG_IFACE_VARIANT") ? atoi(getenv("HMG_IFACE_VARIANT")) : 0;
+    if (variant == 1) {
+        if (dim == 3) interface_kernel<3, OP, SQ, 1><<<grid, 256, 0, st>>>(L, T, npair_blocks, nvirtual, x, R, post);
+        else interface_kernel<2, OP, SQ, 1><<<grid, 256, 0, st>>>(L, T, npair_blocks, nvirtual, x, R, post);
+        return 1;
+    }
+    if (variant == 2) {
+        if (dim == 3) interface_kernel<3, OP, SQ, 2><<<grid, 256, 0, st>>>(L, T, npair_blocks, nvirtual, x, R, post);
+        else interface_kernel<2, OP, SQ, 2><<<grid, 256, 0, st>>>(L, T, npair_blocks, nvirtual, x, R, post);
+        return 1;
+    }
     if (dim == 3) interface_kernel<3, OP, SQ><<<grid, 256, 0, st>>>(L, T, npair_blocks, nvirtual, x, R, post);
     else interface_kernel<2, OP, SQ><<<grid, 256, 0, st>>>(L, T, npair_blocks, nvirtual, x, R, post);
     return 1;

@@ -45,7 +45,7 @@ def test_copy_columns_from_is_the_column_prefix(dim, c, levels):
         x = np.asfortranarray(np.random.default_rng(5).random((big.nf(levels), mesh.nelements)))
         big.state(levels).x.set(x)
         ne = mesh.nelements
-        for n_keep in sorted({ne, ne - 1, max(1, ne // 2), min(ne, 64), min(ne, 33), 1}):
+        for n_keep in sorted({ne, ne - 1, max(1, ne // 2), min(ne, 64), min(ne, 33), 5}):
             used = np.unique(mesh.elements[:n_keep])            # monotone renumbering keeps the elements sorted
             sub = hmg.Mesh(mesh.nodes[used], np.searchsorted(used, mesh.elements[:n_keep]))
             small = hmg.ImplicitFineGrid(sub, levels, np.ascontiguousarray(sigma[:n_keep]))
@@ -66,27 +66,31 @@ def test_copy_columns_from_is_the_column_prefix(dim, c, levels):
 
 
 def test_driver_device_shrink_equals_host_shrink(tmp_path):
-    """checkerboard_homogenization with a domain shrink (n = 1): moving the column prefix on the device gives the very
-    same history as the download / upload path, and `save` writes the files of export_domain / export_unknown."""
-    n, dim, refinements = 1, 2, 3
+    """checkerboard_homogenization with a domain shrink (the outer loop only shrinks from n = 5 on: 56 -> 55 cells of
+    radius after the first step): moving the column prefix on the device gives the very same history as the download /
+    upload path, and `save` writes the files of export_domain / export_unknown."""
+    n, dim, refinements = 5, 2, 1
     rng = np.random.default_rng(42)
     radius = od.compute_box_radius(0, n) + od.compute_boundary_layer(1.0, n)
     cells = np.where(rng.random((2 * radius,) * dim + (dim,)) < 0.5, 1.0, 9.0)
-    base, _ = od.make_base(dim, n)
+    ne0 = 2 * (2 * radius) ** 2
     nf = hmg.inputs.nf_of_level(dim, refinements + 1)
-    x0 = np.asfortranarray(rng.random((nf, base.nelements)))
-    kw = dict(refinements=refinements, tolerance=1e-5, sigma_cells=cells, x0=x0)
+    x0 = np.asfortranarray(rng.random((nf, ne0)))
+    kw = dict(refinements=refinements, tolerance=1e-3, sigma_cells=cells, x0=x0)
     s_host, h_host = hmg.driver.checkerboard_homogenization(n, dim, shrink="host", **kw)
     prefix = str(tmp_path) + os.sep
     s_dev, h_dev = hmg.driver.checkerboard_homogenization(n, dim, shrink="device", save=2, save_prefix=prefix, **kw)
     assert len(h_host) == 2                                   # the outer loop did shrink once
     assert s_dev == s_host and h_dev == h_host                # bit-identical
     mesh, _, cd = hmg.vtk.read_vtu(prefix + "checkerboard.vtu")
-    assert mesh.nelements == base.nelements and cd["a"].shape == (base.nelements, dim)
+    assert mesh.nelements == ne0 and cd["a"].shape == (ne0, dim)
+    sizes = []
     for k in range(2):
         full, pd, _ = hmg.vtk.read_vtu(prefix + f"ahom_{k}.vtu")
-        assert full.nnodes == pd["v"].shape[0] and full.nnodes % hmg.inputs.nf_of_level(dim, 2) == 0
+        assert full.nnodes == pd["v"].shape[0] and full.nnodes % nf == 0
         assert np.all(np.isfinite(pd["v"])) and np.any(pd["v"] != 0.0)
+        sizes.append(full.nnodes // nf)
+    assert sizes[0] == ne0 and sizes[1] < ne0                 # the second step ran on the shrunken mesh
 
 
 def test_export_unknown_is_the_coarse_level_slice(tmp_path):
