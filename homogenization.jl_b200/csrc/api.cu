@@ -1312,6 +1312,8 @@ int hmg_time_op(hmg_ctx* c, int op, int level, int steps, int reps, float* ms_ou
             do_apply(c, level, APPLY_AX, 1.0, c->vecp(level, HMG_P), c->vecp(level, HMG_AP), nullptr);
         } else if (op == 4) {
             do_broadcast(c, level, c->vecp(level, HMG_AP));
+        } else if (op == 13 || op == 14) {
+            check_launch(c, launch_interface_sum(c->dim, c->level(level).view, c->tview, c->vecp(level, HMG_AP), c->stream, op - 12));
         } else if (op == 5) {
             do_apply(c, level, APPLY_RESIDUAL, 1.0, c->vecp(level, HMG_X), c->vecp(level, HMG_R), c->vecp(level, HMG_B));
         } else if (op == 6) {

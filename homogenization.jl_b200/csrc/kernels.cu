@@ -724,66 +724,16 @@ int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st) {
 // SQ: additionally reduce sum over the touched entries of value^2 ( = owners * sum^2 per shared node) and add it
 // to S_TMP -- the part of rho = dot(r, r) that lives on interfaces; the apply kernel reduces the interior part
 // (src/multigrid.jl:54 without a pass over r).  With SQ the grid is bounded and blocks loop over virtual blocks.
-// VAR 1 / 2 (HMG_IFACE_VARIANT, experiment; 2 = four nodes per step): BOTH owners of a pair work -- the steps of the node loop alternate between
-// them (a node is still handled by exactly one thread, which reads both copies, adds them and writes both), so every
-// lane with a partner is active and the own side of every access is a full 256-byte row; eight nodes per step (sixteen
-// loads in flight per thread) with 32-bit offsets inside the unit.  a + b is commutative, so the bits do not depend on
-// which owner adds.
-template <int DIM, int OP, bool SQ, int VAR = 0>
-__global__ void __launch_bounds__(256, VAR == 1 ? 3 : 1) interface_kernel(const LevelView L, const TopoView T, int64_t npair_blocks,
-                                                        int64_t nvirtual, double* __restrict__ x, const Reducer R, int post) {
+// MV (HMG_IFACE_MULTI=1, experiment): the owners of a multi-owner node are read four at a time -- addresses first, then
+// the loads, then the sum in ascending owner order (the same bits) -- instead of one dependent chain per owner.
+template <int DIM, int OP, bool SQ, bool MV = false>
+__global__ void __launch_bounds__(256) interface_kernel(const LevelView L, const TopoView T, int64_t npair_blocks,
+                                                        int64_t vb_begin, int64_t nvirtual, double* __restrict__ x, const Reducer R,
+                                                        int post) {
     constexpr int NF = DIM == 3 ? 4 : 3;
     const int W = L.W, ws = L.wshift, nf = L.nf;
     double sq = 0.0;
-    for (int64_t vb = blockIdx.x; vb < nvirtual; vb += gridDim.x) {
-        if (VAR >= 1 && vb < npair_blocks) {
-            const int npc = DIM == 3 ? L.npf : L.npe;
-            const uint16_t* tab = L.iface_idx;
-            const int l = threadIdx.x & (W - 1), ks = threadIdx.x >> ws, nk = blockDim.x >> ws;
-            const int64_t u = vb / NF;
-            const int f = (int)(vb - u * NF);
-            const int64_t e = u * W + l;
-            if (e >= T.ne) continue;
-            const int32_t pr = T.partner[e * 4 + f];
-            if (pr < 0) continue;
-            const int64_t pe = pr >> 3;
-            const bool lower = e < pe;
-            double* own = x + u * (int64_t)nf * W + l;
-            double* oth = x + (pe >> ws) * (int64_t)nf * W + (pe & (W - 1));
-            const uint16_t* ta = tab + f * npc;
-            const uint16_t* tb = tab + (pr & 7) * npc;
-            constexpr int U = VAR == 1 ? 8 : 4;
-            // step s covers the nodes ks + nk * (q + s * U), q < U; the lower owner takes the even steps
-            for (int k0 = ks + (lower ? 0 : nk * U); k0 < npc; k0 += 2 * nk * U) {
-                int oa[U], ob[U];
-                double va[U], vo[U];
-#pragma unroll
-                for (int q = 0; q < U; ++q) {
-                    const int k = min(k0 + q * nk, npc - 1);
-                    oa[q] = (int)__ldg(ta + k) * W;
-                    ob[q] = (int)__ldg(tb + k) * W;
-                }
-                if (OP == 0) {
-#pragma unroll
-                    for (int q = 0; q < U; ++q) { va[q] = own[oa[q]]; vo[q] = oth[ob[q]]; }
-                }
-#pragma unroll
-                for (int q = 0; q < U; ++q) {
-                    if (k0 + q * nk >= npc) break;
-                    if (OP == 0) {
-                        const double sum = va[q] + vo[q];
-                        own[oa[q]] = sum;
-                        oth[ob[q]] = sum;
-                        if (SQ) sq = fma(2.0 * sum, sum, sq);
-                    } else if (lower) {
-                        oth[ob[q]] = 0.0;          // all but the first owner
-                    } else {
-                        own[oa[q]] = 0.0;
-                    }
-                }
-            }
-            continue;
-        }
+    for (int64_t vb = vb_begin + blockIdx.x; vb < nvirtual; vb += gridDim.x) {
         if (vb < npair_blocks) {
             const int npc = DIM == 3 ? L.npf : L.npe;
             const uint16_t* tab = L.iface_idx;   // 3D: faces first; 2D: edges first
@@ -855,6 +805,43 @@ __global__ void __launch_bounds__(256, VAR == 1 ? 3 : 1) interface_kernel(const 
         }
         const int64_t b = off[cell], en = off[cell + 1];
         double s = 0.0;
+        if (MV) {
+            auto entry = [&](int64_t o) -> double* {
+                const int32_t id = own[o];
+                const int64_t el = id >> 3;
+                return x + ((el >> ws) * (int64_t)nf + __ldg(tab + (id & 7) * npc + k)) * W + (el & (W - 1));
+            };
+            constexpr int Q = 4;
+            for (int64_t o0 = b; o0 < en; o0 += Q) {
+                double* ptr[Q];
+                double v[Q];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) ptr[q] = entry(min(o0 + q, en - 1));
+                if (OP == 0) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) v[q] = *ptr[q];
+#pragma unroll
+                    for (int q = 0; q < Q; ++q)
+                        if (o0 + q < en) s += v[q];                 // ascending owner order, as the serial loop
+                } else {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q)
+                        if (o0 + q < en && o0 + q > b) *ptr[q] = 0.0;
+                }
+            }
+            if (OP == 0) {
+                for (int64_t o0 = b; o0 < en; o0 += Q) {
+                    double* ptr[Q];
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) ptr[q] = entry(min(o0 + q, en - 1));
+#pragma unroll
+                    for (int q = 0; q < Q; ++q)
+                        if (o0 + q < en) *ptr[q] = s;
+                }
+                if (SQ) sq = fma((double)(en - b) * s, s, sq);
+            }
+            continue;
+        }
         for (int64_t o = b; o < en; ++o) {
             const int32_t id = own[o];
             const int64_t el = id >> 3;
@@ -881,34 +868,32 @@ static unsigned grid_for(int64_t n, int block, int max_blocks = 148 * 16) {
     return (unsigned)g;
 }
 
-// returns the number of launches (0: the level has no shared cell on this rank)
+// returns the number of launches (0: the level has no shared cell on this rank).  part: 3 = everything, 1 = only the
+// two-owner cells (faces 3D / edges 2D), 2 = only the cells with more owners -- the partial runs exist for hmg_time_op.
 template <int OP, bool SQ>
-static int launch_interface(int dim, const LevelView& L, const TopoView& T, double* x, const Reducer& R, int post, cudaStream_t st) {
+static int launch_interface(int dim, const LevelView& L, const TopoView& T, double* x, const Reducer& R, int post, cudaStream_t st,
+                            int part = 3) {
     const int npc = dim == 3 ? L.npf : L.npe;
     const int64_t nunits = (T.ne + L.W - 1) / L.W;
     const int64_t npair_blocks = npc > 0 ? nunits * (dim == 3 ? 4 : 3) : 0;
     const int64_t multi = (dim == 3 ? T.nedges * L.npe : 0) + T.nverts;
     const int64_t nmulti_blocks = (multi + 255) / 256;
-    const int64_t nvirtual = npair_blocks + nmulti_blocks;
-    if (nvirtual == 0) return 0;
-    const unsigned grid = (unsigned)(SQ ? std::min<int64_t>(nvirtual, R.max_blocks) : nvirtual);
-    static const int variant = getenv("HMG_IFACE_VARIANT") ? atoi(getenv("HMG_IFACE_VARIANT")) : 0;
-    if (variant == 1) {
-        if (dim == 3) interface_kernel<3, OP, SQ, 1><<<grid, 256, 0, st>>>(L, T, npair_blocks, nvirtual, x, R, post);
-        else interface_kernel<2, OP, SQ, 1><<<grid, 256, 0, st>>>(L, T, npair_blocks, nvirtual, x, R, post);
+    const int64_t vb_begin = (part & 1) ? 0 : npair_blocks;
+    const int64_t nvirtual = (part & 2) ? npair_blocks + nmulti_blocks : npair_blocks;
+    if (nvirtual <= vb_begin) return 0;
+    const unsigned grid = (unsigned)(SQ ? std::min<int64_t>(nvirtual - vb_begin, R.max_blocks) : nvirtual - vb_begin);
+    static const bool multi_var = getenv("HMG_IFACE_MULTI") && atoi(getenv("HMG_IFACE_MULTI")) == 1;
+    if (multi_var) {
+        if (dim == 3) interface_kernel<3, OP, SQ, true><<<grid, 256, 0, st>>>(L, T, npair_blocks, vb_begin, nvirtual, x, R, post);
+        else interface_kernel<2, OP, SQ, true><<<grid, 256, 0, st>>>(L, T, npair_blocks, vb_begin, nvirtual, x, R, post);
         return 1;
     }
-    if (variant == 2) {
-        if (dim == 3) interface_kernel<3, OP, SQ, 2><<<grid, 256, 0, st>>>(L, T, npair_blocks, nvirtual, x, R, post);
-        else interface_kernel<2, OP, SQ, 2><<<grid, 256, 0, st>>>(L, T, npair_blocks, nvirtual, x, R, post);
-        return 1;
-    }
-    if (dim == 3) interface_kernel<3, OP, SQ><<<grid, 256, 0, st>>>(L, T, npair_blocks, nvirtual, x, R, post);
-    else interface_kernel<2, OP, SQ><<<grid, 256, 0, st>>>(L, T, npair_blocks, nvirtual, x, R, post);
+    if (dim == 3) interface_kernel<3, OP, SQ><<<grid, 256, 0, st>>>(L, T, npair_blocks, vb_begin, nvirtual, x, R, post);
+    else interface_kernel<2, OP, SQ><<<grid, 256, 0, st>>>(L, T, npair_blocks, vb_begin, nvirtual, x, R, post);
     return 1;
 }
-int launch_interface_sum(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st) {
-    return launch_interface<0, false>(dim, L, T, x, Reducer{}, 0, st);
+int launch_interface_sum(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st, int part) {
+    return launch_interface<0, false>(dim, L, T, x, Reducer{}, 0, st, part);
 }
 int launch_interface_sum_sq(int dim, const LevelView& L, const TopoView& T, double* x, const Reducer& R, int post, cudaStream_t st) {
     return launch_interface<0, true>(dim, L, T, x, R, post, st);

@@ -102,7 +102,8 @@ struct ApplyArgs {
 // launchers (all asynchronous on `st`); return the number of kernels launched
 int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st);
 ApplyConfig make_apply_config(int dim, int m, int nf, int W, bool fused = false, bool streaming_rhs = false);
-int launch_interface_sum(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
+// part (measurement only): 3 = all shared cells, 1 = two-owner cells only, 2 = cells with more owners only
+int launch_interface_sum(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st, int part = 3);
 int launch_interface_sum_sq(int dim, const LevelView& L, const TopoView& T, double* x, const Reducer& R, int post, cudaStream_t st);
 int launch_zero_all_but_one(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
 // all three kinds (faces / edges / vertices) in one launch; base[kind] = first slot of the kind in the level's

@@ -158,8 +158,9 @@ int hmg_synchronize(hmg_ctx* ctx);
  * 5 = local residual, 6 / 7 / 8 = the fused CG vector kernels (x,r update; p update; p = r with
  * rho), 9 = restriction level -> level-1, 10 = interpolation level-1 -> level, 11 = local apply with
  * the fused owner-weighted dot, 12 = the fused direction update + product of a CG step (p' = R + beta P
- * formed inside the apply kernel, AP = broadcast(constraint(A p'))).  The operation is launched `reps`
- * times back to back. */
+ * formed inside the apply kernel, AP = broadcast(constraint(A p'))), 13 / 14 = the interface kernel restricted to the
+ * two-owner cells (faces in 3D, edges in 2D) / to the cells with more owners (local cells only).  The operation is
+ * launched `reps` times back to back. */
 int hmg_time_op(hmg_ctx* ctx, int op, int level, int steps, int reps, float* ms_out);
 /* number of kernel launches issued on the context's stream since creation */
 int64_t hmg_launch_count(const hmg_ctx* ctx);

@@ -1,0 +1,22 @@
+#!/bin/bash
+# GPU check 2: interface kernel split (pairs / multi-owner cells), multi-owner variant, full GPU suite of the final code
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+t0=$(date +%s)
+el() { echo "[t+$(( $(date +%s) - t0 ))s] $*"; }
+el start
+timeout 45 python tools/microbench.py 3 16 6 20 v > gpurun_out/r01s_mb3d_default.log 2>&1; el "mb3d default rc=$?"
+HMG_IFACE_MULTI=1 timeout 45 python tools/microbench.py 3 16 6 20 v > gpurun_out/r01s_mb3d_multi1.log 2>&1; el "mb3d multi1 rc=$?"
+HMG_IFACE_MULTI=1 timeout 60 python -m pytest tests/test_gpu_parity.py -x -q > gpurun_out/r01s_parity_multi1.log 2>&1; el "parity multi1 rc=$?"; tail -2 gpurun_out/r01s_parity_multi1.log
+timeout 45 python tools/microbench.py 3 6 6 20 > gpurun_out/r01s_mb3d_c6_L2resident.log 2>&1; el "mb3d c6 rc=$?"
+timeout 100 python -m pytest tests -m gpu -x -q > gpurun_out/r01s_pytest_gpu.log 2>&1; el "pytest gpu rc=$?"; tail -3 gpurun_out/r01s_pytest_gpu.log
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/r01s_mb*.log')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, {k:(d[k]['ms'] if isinstance(d[k],dict) else d[k]) for k in ('apply','interface','interface_pairs','interface_multi','global_product','vcycle') if k in d})
+    except Exception as ex:
+        print(f,'unreadable',ex)
+PY
+el done
