@@ -1,5 +1,6 @@
 #!/bin/bash
-# GPU check 2: interface kernel split (pairs / multi-owner cells), multi-owner variant, full GPU suite of the final code
+# GPU check used at the end of round 1: interface kernel split (pairs / multi-owner cells), the multi-owner variant,
+# an L2-resident problem, and the full GPU suite.  Run through gpurun from the repository root.
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 t0=$(date +%s)
