@@ -11,7 +11,7 @@ from oracle.mesh import (Mesh, refine_uniformly, hypercube, sort_element_nodes, 
 from oracle.sorting import (sort_bitonic, radix_sort, remove_singletons, remove_repeated_pairs,
                             remove_duplicates, left_minus_right, complement, binary_search)
 from oracle.reference_element import refined_element, nodes_on_ref_faces, nodes_on_ref_edges
-from oracle.interfaces import compress, list_boundary_nodes_edges_faces
+from oracle.interfaces import compress, list_boundary_nodes_edges_faces, list_interior_nodes
 from oracle.fem import build_local_diffusion_operators, assemble_matrix, Geometry
 from oracle.implicit import (ImplicitFineGrid, ZeroDirichletConstraint, broadcast_interfaces,
                              construct_full_grid, distribute, new_state)
@@ -179,3 +179,38 @@ def test_operator_matches_assembled_matrix():
 def test_operator_matches_assembled_matrix_reference_size():
     """test/test_operator.jl exactly as written: levels = 5, base refined once."""
     assert _example_operator(levels=5, times=1) <= 20 * np.finfo(float).eps
+
+
+def test_list_faces():
+    """test/list_faces.jl:6-27 (not part of runtests.jl, but it pins the maps the zero Dirichlet constraint is built
+    from, src/interface.jl:207-284): one tetrahedron has 4 boundary faces, 6 edges, 4 nodes; after two refinements
+    every face is split in 16, and the boundary nodes are the face lattices minus the doubly counted edges and the
+    triply counted vertices.  Also: the library's host tables (csrc/topology.cpp) agree cell for cell."""
+    import ctypes as C
+    import hmgb200 as hmg
+    nodes = np.array([(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)], dtype=np.float64)
+    mesh = Mesh(nodes, np.array([[0, 1, 2, 3]]))
+    n, e, f = list_boundary_nodes_edges_faces(mesh)
+    assert (f.ncells, e.ncells, n.ncells) == (4, 6, 4)
+    mesh = refine_uniformly(mesh, times=2)
+    mesh.elements = sort_element_nodes(mesh.elements)
+    n, e, f = list_boundary_nodes_edges_faces(mesh)
+    assert f.ncells == 4 * 16
+    assert e.ncells == 2 * 16 * 3                       # 4 * 16 * 3 edges, each counted twice
+    assert n.ncells == sum(range(1, 6)) * 4 - 6 * 3 - 2 * 4
+    interior = list_interior_nodes(mesh)
+    assert len(interior) == mesh.nnodes - n.ncells == 1   # the lattice of m = 4 has one interior point
+    # the product's own boundary detection on the same mesh
+    lib = hmg.load()
+    el1 = np.ascontiguousarray(mesh.elements + 1, dtype=np.int64)
+    cmask = np.zeros(mesh.nelements, dtype=np.uint16)
+    flag = np.zeros(mesh.nnodes, dtype=np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    hmg._lib.check_host(lib.hmg_host_boundary(3, mesh.nelements, mesh.nnodes, vp(el1), vp(cmask), vp(flag)))
+    assert np.array_equal(np.nonzero(flag)[0], interior)
+    # every boundary face of the oracle shows up as the face class bit of its owning element
+    face_bit = [hmg.load().hmg_host_class_of(3, 0, lf) for lf in range(4)]
+    cell = np.repeat(np.arange(f.ncells), np.diff(f.offset))
+    for el, lid in zip(f.element[cell], f.local_id[cell]):
+        assert cmask[el] & (1 << face_bit[lid])
+    assert sum(bin(int(c) & sum(1 << b for b in face_bit)).count("1") for c in cmask) == f.ncells
