@@ -246,6 +246,13 @@ def test_four_ranks_share_edges_and_vertices():
     mp.spawn(_worker, args=(4, _free_port(), (3, 2, 3)), nprocs=4, join=True)
 
 
+def test_eight_ranks_octants():
+    """2 x 2 x 2 blocks (the partition of the 8-GPU bench): the centre vertex is shared by all eight ranks, the axes'
+    edges by four, the mid-planes' faces by two; every rank exchanges with its seven neighbours."""
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(8, _free_port(), (3, 2, 2)), nprocs=8, join=True)
+
+
 def test_single_rank_partition_is_the_whole_mesh():
     lib = hmg.load()
     mesh, _ = hmg.inputs.checkerboard_problem(3, 2)
