@@ -25,8 +25,8 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 # dim, cells per side, grids (= refinements + 1); BASELINE.md section 4
 WORKLOADS = {
     "C1": dict(dim=2, c=48, levels=5, name="C1: 2D Tri64 checkerboard c=48 refinements=4 (README example shape)"),
-    # c = 192 is the largest "large base mesh" whose coarsest-grid problem (191^2 interior nodes) fits the
-    # exact dense coarse solver on GPU 0 (n < 46 340, cuSOLVER's 32-bit potri); BASELINE.md proposed c = 256
+    # c = 192: the base mesh all round-1 measurements were taken on (191^2 interior nodes, the largest the 32-bit
+    # potri path of the dense coarse solver takes; the 64-bit path lifts that limit, c = 256 of BASELINE.md is untimed)
     "C2": dict(dim=2, c=192, levels=8, name="C2: 2D Tri64 checkerboard c=192 refinements=7"),
     "C3": dict(dim=3, c=20, levels=5, name="C3: 3D Tet64 checkerboard c=20 refinements=4"),
     "C4": dict(dim=3, c=32, levels=6, name="C4: 3D Tet64 checkerboard c=32 refinements=5"),
