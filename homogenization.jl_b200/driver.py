@@ -43,11 +43,12 @@ def checkerboard_homogenization(n, dim, refinements=2, smoothing_steps=3, tolera
     """Returns (sigma, history); history[k] = [(residual norm, sigma + dsigma, |dsigma - dsigma_prev|), ...]
     per V-cycle of outer step k -- the @info line of :287.
 
-    ``save`` (:149-152, :219): a level 1..refinements+1 -- writes ``checkerboard.vtu`` (the base mesh with the
-    conductivities) and, after every outer step k, ``ahom_<k>.vtu`` (v_k on the nodes of that level; the reference
-    defines export_unknown for this but its driver only calls export_domain).  ``shrink``: "device" moves the column
-    prefix of x between the contexts on the GPU, "host" through a download / upload (the round-1 path, kept for
-    the comparison in the tests)."""
+    ``save`` (:149-152, :219, :302): a level 1..refinements+1 -- writes ``checkerboard.vtu`` (export_domain: the base
+    mesh with the conductivities) and, after every outer step k, ``ahom_<k>.vtu`` (export_unknown: v_k on the nodes of
+    that level).  ``shrink``: "device" moves the column prefix of x between the contexts on the GPU, "host" through
+    a download / upload (kept for the comparison in the tests).  The reference's shrink_level_state (:54-60) slices all
+    five vectors of every level; only the finest x carries information across the shrink (b is rebuilt by next_rhs!,
+    r / p / Ap and the coarser levels are overwritten by the next V-cycle), so only that prefix is moved."""
     if shrink not in ("device", "host"):
         raise ValueError("shrink must be 'device' or 'host'")
     xi = np.ones(dim) / math.sqrt(dim) if xi is None else np.asarray(xi, dtype=np.float64)      # :62-65
