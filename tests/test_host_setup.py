@@ -161,7 +161,17 @@ def _meshes():
     t = refine_uniformly(hypercube(2, 2), times=1)
     t.elements = sort_element_nodes(t.elements)
     out.append(t)
+    # irregular topologies: a third of the elements removed at random (holes, re-entrant corners, faces and edges
+    # that end up on the boundary from the inside, nodes no element uses any more), the rest in shuffled order
+    rng = np.random.default_rng(11)
+    for dim, c in ((3, 3), (2, 6)):
+        full = hypercube(dim, c)
+        keep = rng.permutation(full.nelements)[: (2 * full.nelements) // 3]
+        out.append(type(full)(full.nodes, full.elements[keep]))
     return out
+
+
+MESH_IDS = ["cube5x2", "hyper3", "hyper2", "tri-refined", "tet-holes-shuffled", "tri-holes-shuffled"]
 
 
 def host_map(mesh, kind):
@@ -177,7 +187,7 @@ def host_map(mesh, kind):
     return off, el, lid
 
 
-@pytest.mark.parametrize("mesh", _meshes(), ids=["cube5x2", "hyper3", "hyper2", "tri-refined"])
+@pytest.mark.parametrize("mesh", _meshes(), ids=MESH_IDS)
 def test_interface_maps_match_oracle(mesh):
     inter = interfaces(mesh)
     kinds = [(1, inter.edges), (2, inter.nodes), (3, inter.all_nodes)]
@@ -195,7 +205,7 @@ def test_interface_maps_match_oracle(mesh):
         assert np.array_equal(lid, om.local_id)
 
 
-@pytest.mark.parametrize("mesh", _meshes(), ids=["cube5x2", "hyper3", "hyper2", "tri-refined"])
+@pytest.mark.parametrize("mesh", _meshes(), ids=MESH_IDS)
 def test_dirichlet_classes_and_interior_nodes_match_oracle(mesh):
     dim = mesh.dim
     el1 = np.ascontiguousarray(mesh.elements + 1, dtype=np.int64)

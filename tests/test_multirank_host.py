@@ -81,10 +81,15 @@ def _worker(rank, world, port, case):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
         import torch
-        dim, c, levels = case
+        dim, c, levels = case[:3]
         lib = hmg.load()
         mesh, _ = hmg.inputs.checkerboard_problem(dim, c)
-        owner = hmg.inputs.spatial_partition(mesh, world)
+        if len(case) > 3 and case[3] == "random":
+            # every element on a random rank: cut cells everywhere, owners of a cell on any subset of the ranks
+            owner = np.random.default_rng(17).integers(0, world, mesh.nelements).astype(np.int32)
+            owner[:world] = np.arange(world)
+        else:
+            owner = hmg.inputs.spatial_partition(mesh, world)
         assert set(owner.tolist()) == set(range(world))
         P = partition_of(lib, mesh, owner, rank, world)
         l2g = P["l2g"]
@@ -244,6 +249,14 @@ def test_four_ranks_share_edges_and_vertices():
     """2 x 2 blocks: the cut cells along the middle are shared by up to four ranks (several peers per cell)."""
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(4, _free_port(), (3, 2, 3)), nprocs=4, join=True)
+
+
+def test_three_ranks_random_ownership():
+    """No spatial structure at all: every coarse element on a random one of three ranks (an odd count, so no message
+    layout is symmetric by accident) -- the cut-cell enumeration, the pairwise message layouts and the rank-ordered
+    sums must still reproduce the global interface sums."""
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(3, _free_port(), (3, 2, 3, "random")), nprocs=3, join=True)
 
 
 def test_eight_ranks_octants():
