@@ -271,6 +271,33 @@ def distribute(implicit, v, u):
     return v
 
 
+def local_rhs_host(base, levels):
+    """The matrix local_rhs!(b, implicit) fills (src/implicit_fine_grid.jl:391-409): b[:, e] = b_ref * |det J_e| with
+    b_ref = assemble_vector(refined_mesh(implicit, levels), identity), i.e. the integral of every P1 hat function over
+    the refined reference element (each fine element gives volume / (dim + 1) to its vertices).  O(Nf * Ne) host work,
+    done once per problem; returns an (Nf, Ne) Fortran-ordered array."""
+    from .vtk import refined_mesh
+    dim = base.dim
+    ref = refined_mesh(dim, levels, levels)
+    p = ref.nodes[ref.elements]                                          # (nel, dim+1, dim)
+    vol = np.abs(np.linalg.det(p[:, 1:, :] - p[:, :1, :])) / (2.0 if dim == 2 else 6.0)
+    b_ref = np.zeros(ref.nnodes)
+    np.add.at(b_ref, ref.elements.ravel(), np.repeat(vol / (dim + 1), dim + 1))
+    q = base.nodes[base.elements]
+    det = np.abs(np.linalg.det(q[:, 1:, :] - q[:, :1, :]))
+    return np.asfortranarray(b_ref[:, None] * det[None, :])
+
+
+def local_rhs(b, implicit):
+    """local_rhs!(b, implicit): the un-summed functional of f = 1 on the finest level, computed on the host and uploaded."""
+    if b.level != implicit.levels:
+        raise ValueError("local_rhs!: b must be a finest-level matrix")
+    full = local_rhs_host(implicit.base, implicit.levels)
+    if implicit.ne_local != implicit.base.nelements:
+        full = np.asfortranarray(full[:, implicit.local_elements()])
+    return b.set(full)
+
+
 # ---- driver functionals on the finest level (src/examples/homogenized_coefficients.jl) -----------
 def _xi(implicit, xi):
     xi = np.ascontiguousarray(xi, dtype=np.float64)

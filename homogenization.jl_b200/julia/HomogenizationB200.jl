@@ -17,7 +17,7 @@ using Homogenization
 using Homogenization: Mesh, ImplicitFineGrid, LevelState, BaseLevel, L2PlusDivAGrad,
                       ZeroDirichletConstraint, nelements, nnodes, refined_mesh, nlevels, construct_full_grid
 using WriteVTK: vtk_grid, vtk_point_data
-import Homogenization: export_unknown, broadcast_interfaces!, apply_constraint!, zero_out_all_but_one!,
+import Homogenization: export_unknown, local_rhs!, broadcast_interfaces!, apply_constraint!, zero_out_all_but_one!,
                        local_residual!, restrict_to!, interpolate_and_sum_to!, smoothing_steps!,
                        vcycle!, rhs_aξ∇v!, integrate_first_term, integrate_terms, integrate_area, next_rhs!
 import LinearAlgebra: mul!
@@ -214,6 +214,14 @@ function next_rhs!(b::DeviceMatrix, x::DeviceMatrix, implicit::ImplicitFineGrid,
     check(ccall((:hmg_set_lambda, libhmg), Cint, (Ptr{Cvoid}, Float64), b.grid.ctx, ops.λ))
     check(ccall((:hmg_next_rhs, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint), b.grid.ctx, b.which, x.which))
     nothing
+end
+
+# local_rhs!(b, implicit)   (src/implicit_fine_grid.jl:391-409): O(Nf * Ne) once per problem -- the reference's own host
+# method fills a Matrix, which is uploaded
+function local_rhs!(b::DeviceMatrix, implicit::ImplicitFineGrid)
+    h = Matrix{Float64}(undef, size(b)...)
+    local_rhs!(h, implicit)
+    copyto!(b, h)
 end
 
 # shrink_level_state(l, nf, n)   (src/examples/homogenized_coefficients.jl:54-60): the new grid lives on an element

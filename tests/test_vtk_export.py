@@ -53,3 +53,20 @@ def test_vtu_round_trip_and_export_domain(dim, tmp_path):
     assert np.array_equal(pd["v"], v) and back.nelements == full.nelements
     with pytest.raises(ValueError):
         hmg.vtk.write_vtu(str(tmp_path / "bad"), full, point_data={"v": v[:-1]})
+
+
+@pytest.mark.parametrize("dim,c,levels", [(2, 3, 5), (3, 2, 4)])
+def test_local_rhs_host_matches_oracle(dim, c, levels):
+    """local_rhs! (src/implicit_fine_grid.jl:391-409) as the product's host mirror computes it (from the library's own
+    refined reference mesh) against the oracle, on a sheared and scaled mesh (|det J| differs from 1)."""
+    from oracle.implicit import local_rhs as o_local_rhs
+    mesh, _ = hmg.inputs.checkerboard_problem(dim, c)
+    shear = 1.5 * (np.eye(dim) + 0.25 * np.triu(np.ones((dim, dim)), 1))
+    mesh = hmg.Mesh(mesh.nodes @ shear.T, mesh.elements)
+    oimp = OImplicit(OMesh(mesh.nodes, mesh.elements), levels)
+    expect = o_local_rhs(np.zeros((oimp.nf(levels), mesh.nelements), order="F"), oimp)
+    got = hmg.local_rhs_host(mesh, levels)
+    assert got.shape == expect.shape and got.flags.f_contiguous
+    assert np.allclose(got, expect, rtol=1e-13, atol=0)
+    # the functional of f = 1 sums to the volume of the domain, every element counted once
+    assert abs(got.sum() - (c ** dim) * abs(np.linalg.det(shear))) <= 1e-12 * got.sum()
