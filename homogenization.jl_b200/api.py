@@ -142,6 +142,15 @@ class ImplicitFineGrid:
         self.ne_local = int(self.lib.hmg_ne_local(self.ctx))
         self.states = [LevelState(self, l) for l in range(1, self.levels + 1)]
 
+    @classmethod
+    def simple_diffusion(cls, base, levels, a=1.0, **kw):
+        """The grid of SimpleDiffusion(ops, bc, a), L = -a * Laplacian with the zero Dirichlet constraint
+        (src/build_local_operators.jl:19-23, product src/apply_local_operators.jl:40-72: P = Jinv' * Jinv scaled by
+        a * |J|): the same operator as L2PlusDivAGrad with sigma = (a, ..., a) and lambda = 0, whose mass term the
+        kernels skip exactly like the reference does (src/apply_local_operators.jl:116)."""
+        sigma = np.full((base.nelements, base.dim), float(a))
+        return cls(base, levels, sigma, lam=0.0, **kw)
+
     def close(self):
         if getattr(self, "ctx", None):
             self.lib.hmg_destroy(self.ctx)

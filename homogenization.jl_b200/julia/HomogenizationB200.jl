@@ -14,7 +14,7 @@
 module HomogenizationB200
 
 using Homogenization
-using Homogenization: Mesh, ImplicitFineGrid, LevelState, BaseLevel, L2PlusDivAGrad,
+using Homogenization: Mesh, ImplicitFineGrid, LevelState, BaseLevel, L2PlusDivAGrad, SimpleDiffusion,
                       ZeroDirichletConstraint, nelements, nnodes, refined_mesh, nlevels, construct_full_grid
 using WriteVTK: vtk_grid, vtk_point_data
 import Homogenization: export_unknown, local_rhs!, broadcast_interfaces!, apply_constraint!, zero_out_all_but_one!,
@@ -213,6 +213,22 @@ end
 function next_rhs!(b::DeviceMatrix, x::DeviceMatrix, implicit::ImplicitFineGrid, ops::L2PlusDivAGrad)
     check(ccall((:hmg_set_lambda, libhmg), Cint, (Ptr{Cvoid}, Float64), b.grid.ctx, ops.λ))
     check(ccall((:hmg_next_rhs, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint), b.grid.ctx, b.which, x.which))
+    nothing
+end
+
+# SimpleDiffusion(ops, bc, a)   (src/build_local_operators.jl:19-23, product src/apply_local_operators.jl:40-72) is
+# L2PlusDivAGrad with sigma = (a, ..., a) and lambda = 0: create the grid with DeviceGrid(implicit, A) below and the
+# same entry points serve it.
+DeviceGrid(implicit::ImplicitFineGrid{dim}, A::SimpleDiffusion; device::Integer = 0) where {dim} =
+    DeviceGrid(implicit, fill(SVector{dim,Float64}(ntuple(_ -> A.a, dim)), nelements(implicit.base)), 0.0; device = device)
+function mul!(α::Float64, base::Mesh, A::SimpleDiffusion, x::DeviceMatrix, y::DeviceMatrix)
+    check(ccall((:hmg_set_lambda, libhmg), Cint, (Ptr{Cvoid}, Float64), x.grid.ctx, 0.0))
+    check(ccall((:hmg_mul, libhmg), Cint, (Ptr{Cvoid}, Cint, Float64, Cint, Cint), x.grid.ctx, x.level, α, x.which, y.which))
+    y
+end
+function local_residual!(implicit::ImplicitFineGrid, A::SimpleDiffusion, curr::LevelState{Float64,DeviceMatrix}, k::Int)
+    check(ccall((:hmg_set_lambda, libhmg), Cint, (Ptr{Cvoid}, Float64), curr.x.grid.ctx, 0.0))
+    check(ccall((:hmg_local_residual, libhmg), Cint, (Ptr{Cvoid}, Cint), curr.x.grid.ctx, k))
     nothing
 end
 
