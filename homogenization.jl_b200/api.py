@@ -172,6 +172,16 @@ class ImplicitFineGrid:
         """1-based level, as in the reference."""
         return self.states[level - 1]
 
+    def refined_mesh(self, level):
+        """refined_mesh(implicit, level) (src/implicit_fine_grid.jl:24): the refined reference element, host data."""
+        from .vtk import refined_mesh
+        return refined_mesh(self.dim, self.levels, level)
+
+    def construct_full_grid(self, level):
+        """construct_full_grid(implicit, level) (src/implicit_fine_grid.jl:41-78), host data."""
+        from .vtk import construct_full_grid
+        return construct_full_grid(self.base, self.levels, level)
+
     def local_elements(self):
         out = np.empty(self.ne_local, dtype=np.int64)
         check(self.lib.hmg_local_elements(self.ctx, out.ctypes.data_as(C.c_void_p)))
