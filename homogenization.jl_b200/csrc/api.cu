@@ -162,6 +162,9 @@ struct hmg_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_permuted[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // HMG_IFACE_SPLIT=1 (experiment): second stream for the multi-owner cells of an interface sum
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int64_t launches = 0;
 
     ~hmg_ctx() {
@@ -169,6 +172,7 @@ struct hmg_ctx {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         if (copy_stream) cudaStreamSynchronize(copy_stream);
+        if (side_stream) cudaStreamSynchronize(side_stream);
         if (comm) nccl_destroy(comm);
         for (void* p : allocs) cudaFree(p);
         for (int q = 0; q < 2; ++q) {
@@ -176,6 +180,9 @@ struct hmg_ctx {
             if (ev_permuted[q]) cudaEventDestroy(ev_permuted[q]);
         }
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (side_stream) cudaStreamDestroy(side_stream);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -495,7 +502,25 @@ void do_cut_exchange(hmg_ctx* c, int l, double* x) {
     do_cut_exchange_impl(c, l, x, false);
 }
 void do_broadcast(hmg_ctx* c, int l, double* x) {
-    check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->stream));
+    // HMG_IFACE_SPLIT=1 (experiment, untimed): the cells with more than two owners take a third of the interface kernel
+    // for a tenth of its bytes (latency-bound chains, scheduled after all the face blocks); as a second kernel on a
+    // second stream their blocks share the SMs with the face blocks instead.  The two parts touch disjoint entries.
+    static const bool split = getenv("HMG_IFACE_SPLIT") && atoi(getenv("HMG_IFACE_SPLIT")) == 1;
+    if (split) {
+        if (!c->side_stream) {
+            CUDA_OK(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+            CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        }
+        CUDA_OK(cudaEventRecord(c->ev_fork, c->stream));
+        CUDA_OK(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+        check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->stream, 1));
+        check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->side_stream, 2));
+        CUDA_OK(cudaEventRecord(c->ev_join, c->side_stream));
+        CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    } else {
+        check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->stream));
+    }
     do_cut_exchange(c, l, x);
 }
 void do_zero_all_but_one(hmg_ctx* c, int l, double* x) {
