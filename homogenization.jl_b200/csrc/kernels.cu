@@ -196,7 +196,13 @@ template <int DIM, int W, int MODE, bool DOT> struct OutDev {
         for (int q = 0; q < TD; ++q) tq[q] = __ldcs(tl + min(k0 + q, klast) * APPLY_W);
     }
     template <int CLS> __device__ __forceinline__ void put(int k, double acc, double x0) {
+#ifdef HMG_LEAN_PUT
+        // build variant (make HMG_EXTRA=-DHMG_LEAN_PUT, untimed): bit 0 of the class mask is never set -- topology.cpp only
+        // sets the bits of face / edge / vertex classes -- so interior nodes need no Dirichlet select (4 FSEL per two nodes)
+        const bool fixed = CLS != 0 && MODE != APPLY_MULADD && ((cm >> CLS) & 1u);
+#else
         const bool fixed = MODE != APPLY_MULADD && ((cm >> CLS) & 1u);
+#endif
         double v;
         if (MODE == APPLY_AX) v = fixed ? 0.0 : acc;
         else {
