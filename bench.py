@@ -25,9 +25,9 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 # dim, cells per side, grids (= refinements + 1); BASELINE.md section 4
 WORKLOADS = {
     "C1": dict(dim=2, c=48, levels=5, name="C1: 2D Tri64 checkerboard c=48 refinements=4 (README example shape)"),
-    # c = 192: the base mesh all round-1 measurements were taken on (191^2 interior nodes, the largest the 32-bit
-    # potri path of the dense coarse solver takes; the 64-bit path lifts that limit, c = 256 of BASELINE.md is untimed)
-    "C2": dict(dim=2, c=192, levels=8, name="C2: 2D Tri64 checkerboard c=192 refinements=7"),
+    # c = 256: BASELINE.md section 4 (65 025 interior base nodes: the dense coarse inverse takes 34 GB and the 64-bit
+    # cuSOLVER path; "coarse_solver_setup_s" in the output is that factorisation)
+    "C2": dict(dim=2, c=256, levels=8, name="C2: 2D Tri64 checkerboard c=256 refinements=7"),
     "C3": dict(dim=3, c=20, levels=5, name="C3: 3D Tet64 checkerboard c=20 refinements=4"),
     "C4": dict(dim=3, c=32, levels=6, name="C4: 3D Tet64 checkerboard c=32 refinements=5"),
 }
@@ -190,7 +190,7 @@ def traffic_per_launch(name, dofs_local):
         return None, None
 
 
-def measure(w, args, torch, hmg, dist, rank, world, device, steps, warmup, with_e2e, with_clocks):
+def measure(w, args, torch, hmg, dist, rank, world, device, steps, warmup, with_e2e, with_clocks, with_history=False):
     """One workload on this process' GPU (its share of the coarse elements when world > 1)."""
     dim, levels = w["dim"], w["levels"]
     mesh, sigma = build_inputs(w)
@@ -213,13 +213,21 @@ def measure(w, args, torch, hmg, dist, rank, world, device, steps, warmup, with_
     dofs_total = nf * mesh.nelements
     dofs_local = nf * ne_local
 
-    # inputs: x0 ~ U(0,1) then interface-sum + zero Dirichlet; b = local functional of 1 (un-summed)
-    rng = np.random.default_rng(1234 + rank)
+    # inputs: x0 ~ U(0,1) then interface-sum + zero Dirichlet; b = local functional of 1 (un-summed).  The value of an
+    # entry depends on the GLOBAL element index only (one Philox stream per block of 4096 elements), so every
+    # partition of the mesh starts from the same vector -- which is what "parity_vs_single_gpu" compares.
     st = g.state(levels)
+    l2g = g.local_elements() if world > 1 else np.arange(ne_local, dtype=np.int64)
     hx = torch.empty((ne_local, nf), dtype=torch.float64, pin_memory=True)      # column-major Nf x Ne
-    chunk = max(1, (1 << 24) // nf)
-    for c0 in range(0, ne_local, chunk):
-        hx[c0:c0 + chunk] = torch.from_numpy(rng.random((min(chunk, ne_local - c0), nf)))
+    BLK = 4096
+    blocks = l2g // BLK
+    starts = np.flatnonzero(np.r_[True, blocks[1:] != blocks[:-1]])
+    ends = np.r_[starts[1:], len(l2g)]
+    for a, z in zip(starts, ends):
+        gb = int(blocks[a])
+        n_in_block = min(BLK, mesh.nelements - gb * BLK)
+        blk = np.random.Generator(np.random.Philox(key=1234, counter=[0, 0, 0, gb])).random((n_in_block, nf))
+        hx[a:z] = torch.from_numpy(blk[l2g[a:z] - gb * BLK])
     X = hx.numpy().T
     st.x.set(X)
     bval = 1.0 / (nf * (2 if dim == 2 else 6))
@@ -243,6 +251,14 @@ def measure(w, args, torch, hmg, dist, rank, world, device, steps, warmup, with_
         t = torch.tensor([v], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    # --- residual history of the first V-cycles (the parity observable; compared across partitions at N > 1) ----
+    history = None
+    if with_history:
+        history = [float(v) for v in hmg.vcycles(g, bl, levels, SMOOTHING_STEPS, 3)]
+        st.x.set(X)
+        hmg.broadcast_interfaces(st.x, g, levels)
+        hmg.apply_constraint(st.x, levels, g)
 
     # --- V-cycle, inputs resident in HBM -------------------------------------------------------
     for _ in range(warmup):
@@ -318,7 +334,7 @@ def measure(w, args, torch, hmg, dist, rank, world, device, steps, warmup, with_
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": apply_bytes, "ms_per_launch": ms_apply},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "residual_history": history,
     }
     g.close()
     del hx
@@ -335,29 +351,23 @@ def main():
     ap.add_argument("--cells", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-also", action="store_true", help="skip the secondary (3D) workload")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary workload (N = 1) / the single-GPU run (N > 1)")
     args = ap.parse_args()
     warmup = max(3, args.warmup)
     steps = max(1, args.steps)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    # BASELINE.json: configs[1] (C2: 2D Tri64, refinements = 7, large base mesh, "on 1xB200") is the workload at
-    # N = 1; configs[3] (C4: 3D Tet64, refinements = 5, "coarse elements sharded over 2/4/8xB200") is the workload
-    # at N > 1 (strong scaling of the same mesh).  The other one is measured in the same run and reported under
-    # "also", and at N > 1 rank 0 additionally times the primary workload on its own GPU ("single_gpu").
-    name = ("C2" if world == 1 else "C4") if args.workload == "auto" else args.workload
+    # One workload at every N, so that value_N / (N x value_1) is a strong-scaling efficiency: C4 (BASELINE.json
+    # configs[3]: 3D Tet64, refinements = 5, 32^3 cells) -- it fits one GPU, is the largest configuration and the one
+    # north_star states the 0.8 target on.  configs[1] (C2: 2D Tri64, refinements = 7, 256^2 cells) is measured in the
+    # same run at N = 1 and reported under "also".  At N > 1 rank 0 additionally runs the SAME workload from the SAME
+    # inputs on its own GPU ("single_gpu") and the residual histories are compared ("parity_vs_single_gpu").
+    name = "C4" if args.workload == "auto" else args.workload
     w = dict(WORKLOADS[name], key=name)
     if args.cells:
         w["c"] = args.cells
         w["name"] = w["name"].replace(f"c={WORKLOADS[name]['c']}", f"c={args.cells}")
-    elif args.impl == "b200" and args.workload == "auto":
-        # three pinned host matrices of the local share (x, b, result) must fit the host comfortably
-        nel = 2 * w["c"] ** 2 if w["dim"] == 2 else 6 * w["c"] ** 3
-        need = 3 * 8 * nf_of(w["dim"], w["levels"]) * nel // max(1, world)
-        if name == "C2" and need * 1.5 > host_memory_available():
-            w["c"] = 128
-            w["name"] = w["name"].replace("c=192", "c=128 (host memory too small for c=192)")
     dim, levels = w["dim"], w["levels"]
 
     if args.impl == "reference":
@@ -391,23 +401,32 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = local_rank
 
-    main_r = measure(w, args, torch, hmg, dist, rank, world, device, steps, warmup, not args.no_e2e, True)
+    main_r = measure(w, args, torch, hmg, dist, rank, world, device, steps, warmup, not args.no_e2e, True,
+                     with_history=world > 1)
     also = None
     single = None
-    if args.workload == "auto" and not args.no_also:
-        other = "C4" if name == "C2" else "C2"
-        w3 = dict(WORKLOADS[other], key=other)
-        r3 = measure(w3, args, torch, hmg, dist, rank, world, device, min(steps, 5), 3, False, False)
-        also = {other: {k: r3[k] for k in ("value", "ms_per_step", "config", "ax", "vcycle_model", "roofline", "gpu_launches")}}
-        also[other]["unit"] = "GDOF/s"
-        if world > 1:
-            # the primary workload on ONE GPU, timed in this very job (rank 0 alone, the others wait): the
-            # denominator of the strong-scaling efficiency, free of run-to-run and box-to-box variation
-            if rank == 0:
-                r1 = measure(w, args, torch, hmg, None, 0, 1, device, min(steps, 3), 3, False, False)
-                single = {"workload": r1["config"]["workload"], "value": r1["value"], "unit": "GDOF/s",
-                          "ms_per_step": r1["ms_per_step"], "ax": r1["ax"]["value"]}
-            dist.barrier()
+    parity = None
+    if world > 1 and not args.no_also:
+        # the same workload, the same inputs, ONE GPU, in this very job (rank 0 alone, the others wait): the
+        # denominator of the strong-scaling efficiency free of box-to-box variation, and the multi-GPU parity record
+        if rank == 0:
+            r1 = measure(w, args, torch, hmg, None, 0, 1, device, min(steps, 3), 3, False, False, with_history=True)
+            single = {"workload": r1["config"]["workload"], "value": r1["value"], "unit": "GDOF/s",
+                      "ms_per_step": r1["ms_per_step"], "ax": r1["ax"]["value"],
+                      "residual_history": r1["residual_history"]}
+            hp, h1 = np.array(main_r["residual_history"]), np.array(r1["residual_history"])
+            parity = {"max_rel_diff": float(np.max(np.abs(hp - h1) / h1)), "tolerance": 1e-10, "cycles": len(h1),
+                      "what": "residual norm after each of the first V-cycles, partitioned context vs one GPU, same inputs"}
+        dist.barrier()
+    if world == 1 and args.workload == "auto" and not args.no_also:
+        w2 = dict(WORKLOADS["C2"], key="C2")
+        # the 2D workload needs ~140 GB of device memory during the coarse factorisation and 9 GB of pinned host memory
+        if 1.5 * 8 * nf_of(2, 8) * 2 * w2["c"] ** 2 > host_memory_available():
+            w2["c"] = 192
+            w2["name"] = w2["name"].replace("c=256", "c=192 (host memory too small for c=256)")
+        r2 = measure(w2, args, torch, hmg, dist, rank, world, device, min(steps, 5), 3, False, False)
+        also = {"C2": {k: r2[k] for k in ("value", "ms_per_step", "config", "ax", "vcycle_model", "roofline", "gpu_launches")}}
+        also["C2"]["unit"] = "GDOF/s"
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -424,6 +443,7 @@ def main():
             "config": main_r["config"], "ax": main_r["ax"], "vcycle_model": main_r["vcycle_model"],
             "roofline": main_r["roofline"], "clocks": main_r["clocks"], "e2e": main_r["e2e"],
             "gpu_launches": main_r["gpu_launches"], "cpu_baseline": cpu, "also": also, "single_gpu": single,
+            "parity_vs_single_gpu": parity,
         }
         print(json.dumps(line))
     if dist is not None:

@@ -26,8 +26,17 @@ def test_workloads_are_the_baseline_configs():
     assert bench.WORKLOADS["C2"]["dim"] == 2 and bench.WORKLOADS["C2"]["levels"] == 8
     assert bench.WORKLOADS["C3"]["dim"] == 3 and bench.WORKLOADS["C3"]["levels"] == 5 and bench.WORKLOADS["C3"]["c"] == 20
     assert bench.WORKLOADS["C4"]["dim"] == 3 and bench.WORKLOADS["C4"]["levels"] == 6 and bench.WORKLOADS["C4"]["c"] == 32
-    # the dense coarse solver on GPU 0 takes fewer than 46 340 interior base nodes
-    assert (bench.WORKLOADS["C2"]["c"] - 1) ** 2 < 46340 and (bench.WORKLOADS["C4"]["c"] - 1) ** 3 < 46340
+    assert bench.WORKLOADS["C2"]["c"] == 256
+    # C4's coarse problem fits the 32-bit potrf + potri path (fewer than 46 340 interior base nodes); C2 at c = 256
+    # (65 025) takes the 64-bit one
+    assert (bench.WORKLOADS["C4"]["c"] - 1) ** 3 < 46340 <= (bench.WORKLOADS["C2"]["c"] - 1) ** 2
+
+
+def test_one_workload_at_every_gpu_count():
+    """The scaling curve is one problem: the primary workload does not depend on WORLD_SIZE."""
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert 'name = "C4" if args.workload == "auto" else args.workload' in src
+    assert "parity_vs_single_gpu" in src
 
 
 @pytest.mark.slow

@@ -125,3 +125,19 @@ def test_four_gpus_match_the_oracle_on_the_whole_mesh(case):
     mp.spawn(_worker, args=(4, bytes(raw), case, results), nprocs=4, join=True)
     got = dict(results.get() for _ in range(4))
     assert got[0] == got[1] == got[2] == got[3]
+
+
+def test_eight_gpus_match_the_oracle_on_the_whole_mesh():
+    """2 x 2 x 2 octants of a 4^3-cell mesh, 4 grids: every rank has seven neighbours, the centre vertex is shared by all
+    eight ranks, cut edges by four.  The same comparison with the oracle on the whole mesh as on two ranks."""
+    if _ngpus() < 8:
+        pytest.skip("needs eight GPUs")
+    import torch
+    import torch.multiprocessing as mp
+    raw = (C.c_ubyte * 128)()
+    hmg._lib.check(hmg.load().hmg_nccl_unique_id(raw))
+    ctx = mp.get_context("spawn")
+    results = ctx.SimpleQueue()
+    mp.spawn(_worker, args=(8, bytes(raw), (3, 4, 4), results), nprocs=8, join=True)
+    got = dict(results.get() for _ in range(8))
+    assert all(got[r] == got[0] for r in range(1, 8))

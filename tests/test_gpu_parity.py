@@ -22,6 +22,10 @@ IDS = ["tri-c5-L5", "tri-c3-L7", "tet-c3-L4", "tet-c2-L5", "tri-c4-L1", "tet-c2-
 # (elements of a cell are no longer consecutive)
 CASES += [(2, 4, 5, "random"), (3, 2, 4, "random"), (3, 3, 3, "ordered")]
 IDS += ["tri-c4-L5-random", "tet-c2-L4-random", "tet-c3-L3-ordered"]
+# the depths the bench quotes (C4: 3D with 6 grids, C2: 2D with 8 grids): other launch shapes of the apply kernel
+# (lines per task, chunk size, two staging slots per converter warp in the fused direction update)
+CASES += [(3, 2, 6), (2, 2, 8)]
+IDS += ["tet-c2-L6", "tri-c2-L8"]
 
 
 @pytest.fixture(params=CASES, ids=IDS)

@@ -82,6 +82,52 @@ def test_stencil_tables_reproduce_the_reference_operators(dim, nlevels):
         assert abs(mt - mass.sum()) <= 1e-15
 
 
+@pytest.mark.parametrize("dim,nlevels", [(2, 8), (3, 6)], ids=["tri-L8", "tet-L6"])
+def test_benchmarked_depths_numbering_and_stencil(dim, nlevels):
+    """The finest level of the BENCHMARKED hierarchies (C2: 2D with 8 grids, C4: 3D with 6 grids): lattice numbering and
+    the expanded stencil against the oracle's explicit operators, compared in sparse form (the dense matrix of 3D level 6
+    has 6545^2 entries)."""
+    import scipy.sparse as sp
+    ref = refined_element(nlevels, dim)
+    level = nlevels
+    mesh = ref.levels[level - 1]
+    nf = mesh.nnodes
+    m = 2 ** (level - 1)
+    sizes, h2l, mt = host_reference(dim, nlevels, level)
+    assert sizes[0] == m and sizes[1] == nf
+    lat = np.rint(mesh.nodes * m).astype(int)
+    order = np.lexsort((lat[:, 1], lat[:, 0])) if dim == 2 else np.lexsort((lat[:, 2], lat[:, 0], lat[:, 0] + lat[:, 1]))
+    expect_perm = np.empty(nf, dtype=int)
+    expect_perm[order] = np.arange(nf)
+    assert np.array_equal(h2l, expect_perm)
+    ops = build_local_diffusion_operators_level(mesh)
+    mass = mass_matrix(mesh)
+    rng = np.random.default_rng(6)
+    Pm = rng.standard_normal((dim, dim))
+    Pm = Pm @ Pm.T
+    lam_detj = 0.7
+    expect = lam_detj * mass.tocsr()
+    coef = []
+    for k in range(dim):
+        for l in range(k, dim):
+            coef.append(Pm[k, l])
+        for l in range(dim):
+            expect = expect + Pm[k, l] * ops[k][l].tocsr()
+    coef = np.array(coef + [lam_detj])
+    dense = np.zeros((nf, nf), order="F")
+    L.check_host(lib.hmg_host_local_matrix(dim, nlevels, level, vp(coef), vp(dense)))
+    got = sp.csr_matrix(dense)
+    del dense
+    diff = (got - expect)
+    scale = np.abs(expect.data).max()
+    assert (np.abs(diff.data).max() if diff.nnz else 0.0) <= 1e-14 * scale
+    assert abs(mt - mass.sum()) <= 1e-15
+    P = ref.interops[level - 2]
+    dense = np.zeros(P.shape, order="F")
+    L.check_host(lib.hmg_host_transfer_matrix(dim, nlevels, level, vp(dense)))
+    assert (sp.csr_matrix(dense) != P.tocsr()).nnz == 0
+
+
 @pytest.mark.parametrize("dim,nlevels", [(2, 6), (3, 5)])
 def test_transfer_structure_matches_interpolation_operator(dim, nlevels):
     ref = refined_element(nlevels, dim)

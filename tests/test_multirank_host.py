@@ -273,3 +273,10 @@ def test_single_rank_partition_is_the_whole_mesh():
     assert np.array_equal(P["l2g"], np.arange(mesh.nelements))
     assert all(P[(1, k)]["nglobal"] == 0 for k in range(3))
     assert P["node_contrib"].min() == 1
+
+
+def test_eight_ranks_octants():
+    """2 x 2 x 2 octants (the partition of the 8-GPU runs): seven neighbours per rank, the centre vertex shared by all
+    eight ranks, the cut edges along the three axes by four."""
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(8, _free_port(), (3, 2, 2)), nprocs=8, join=True)

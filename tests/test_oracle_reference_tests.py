@@ -38,14 +38,39 @@ def test_counting_sort():
 
 
 def test_tricks():
-    """test/tricks.jl:5-36 -- exact integer expectations."""
+    """test/tricks.jl:5-36 -- every vector of the reference's file, verbatim (the values are data, not indices)."""
+    # "Remove duplicates from sorted vector" (test/tricks.jl:5-9)
+    assert remove_duplicates([]) == []
+    assert remove_duplicates([2]) == [2]
+    assert remove_duplicates([1, 1, 2, 3, 4, 4, 4, 5]) == [1, 2, 3, 4, 5]
+    # "Remove singletons from sorted vector" (test/tricks.jl:11-18)
+    assert remove_singletons([]) == []
+    assert remove_singletons([2]) == []
+    assert remove_singletons([2, 3]) == []
+    assert remove_singletons([1, 1]) == [1, 1]
+    assert remove_singletons([1, 2, 2, 4, 4, 4, 5]) == [2, 2, 4, 4, 4]
+    assert remove_singletons([1, 1, 2, 3, 4, 4, 4, 5]) == [1, 1, 4, 4, 4]
+    # "Remove sorted array from sorted array" (test/tricks.jl:20-27)
+    assert left_minus_right([], []) == []
+    assert left_minus_right([2], []) == [2]
+    assert left_minus_right([], [1]) == []
+    assert left_minus_right([1, 2, 3], [4, 5, 6]) == [1, 2, 3]
+    assert left_minus_right([1, 3, 6, 9], [3, 9]) == [1, 6]
+    assert left_minus_right([1, 2, 3, 4], [1, 2, 3, 4]) == []
+    # "Remove repeated pairs array" (test/tricks.jl:29-36)
+    assert remove_repeated_pairs([]) == []
+    assert remove_repeated_pairs([1]) == [1]
+    assert remove_repeated_pairs([1, 1]) == []
+    assert remove_repeated_pairs([1, 1, 2]) == [2]
+    assert remove_repeated_pairs([1, 1, 2, 3, 3, 4]) == [2, 4]
+    assert remove_repeated_pairs([1, 1, 2, 3, 3, 4, 4]) == [2]
+
+
+def test_tricks_more():
+    """further cases of the same helpers plus complement / binary_search (src/sorting_tricks.jl:197-217, src/utils.jl)."""
     assert remove_duplicates([1, 1, 2, 3, 3, 3, 4]) == [1, 2, 3, 4]
     assert remove_singletons([1, 2, 2, 3, 4, 4, 4, 5]) == [2, 2, 4, 4, 4]
-    assert remove_singletons([1, 1]) == [1, 1]
-    assert remove_singletons([1]) == []
-    assert remove_repeated_pairs([1, 1, 2, 3, 3, 4]) == [2, 4]
     assert remove_repeated_pairs([1, 2, 2]) == [1]
-    assert remove_repeated_pairs([1, 1, 2]) == [2]
     assert left_minus_right([1, 2, 3, 4, 5, 6], [2, 4, 7]) == [1, 3, 5, 6]
     assert list(complement([1, 3, 4], 6)) == [0, 2, 5]
     assert list(complement([], 3)) == [0, 1, 2]
