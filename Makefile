@@ -3,12 +3,13 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 CUDA_LIB  ?= /usr/local/cuda/lib64
 PKG       := homogenization.jl_b200
 CSRC      := $(PKG)/csrc
-LIB       := $(PKG)/libhmg_b200.so
-NVFLAGS   := $(HMG_EXTRA) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
+LIB       ?= $(PKG)/libhmg_b200.so
+BUILD     ?= build
+NVFLAGS   := $(HMG_EXTRA) -DHMG_NVTX=1 -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
              -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude -diag-suppress 20014
 SRCS      := $(CSRC)/api.cu $(CSRC)/kernels.cu $(CSRC)/reference.cpp $(CSRC)/topology.cpp $(CSRC)/introspect.cpp
 HDRS      := include/hmg.h $(CSRC)/hmg_host.hpp $(CSRC)/kernels.cuh $(CSRC)/lattice.hpp $(CSRC)/apply_core.cuh
-OBJS      := $(patsubst $(CSRC)/%,build/%.o,$(SRCS))
+OBJS      := $(patsubst $(CSRC)/%,$(BUILD)/%.o,$(SRCS))
 
 all: $(LIB) oracle
 
@@ -16,12 +17,12 @@ $(LIB): $(OBJS)
 	$(NVCC) -shared -o $@ $(OBJS) -L$(CUDA_LIB) -lcusolver -lcublas -ldl \
 	    -Xlinker -rpath=$(CUDA_LIB)
 
-build/%.cu.o: $(CSRC)/%.cu $(HDRS)
-	@mkdir -p build
-	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
+$(BUILD)/%.cu.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; false)
 
-build/%.cpp.o: $(CSRC)/%.cpp $(HDRS)
-	@mkdir -p build
+$(BUILD)/%.cpp.o: $(CSRC)/%.cpp $(HDRS)
+	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@
 
 oracle:

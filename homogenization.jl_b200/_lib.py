@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhmg_b200.so")
+# HMG_LIB: a variant build of the same library (kernel experiments, tools/); the product is the in-tree default
+LIB_PATH = os.environ.get("HMG_LIB") or os.path.join(_HERE, "libhmg_b200.so")
 
 HMG_X, HMG_B, HMG_R, HMG_P, HMG_AP, HMG_V, HMG_W = range(7)
 VEC_IDS = {"x": HMG_X, "b": HMG_B, "r": HMG_R, "p": HMG_P, "Ap": HMG_AP, "v": HMG_V, "w": HMG_W}

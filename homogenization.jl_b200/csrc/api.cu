@@ -17,11 +17,33 @@
 #include "hmg_host.hpp"
 #include "kernels.cuh"
 
+// NVTX ranges per V-cycle, level and phase (build flag HMG_NVTX, on in the Makefile; NVTX 3 is header-only and costs a
+// null-pointer test per range unless a profiler is attached)
+#ifdef HMG_NVTX
+#include <nvtx3/nvToolsExt.h>
+#endif
+
 using namespace hmg;
 
 namespace {
 
 thread_local std::string g_err;
+
+struct Range {
+#ifdef HMG_NVTX
+    explicit Range(const char* name, int level = -1) {
+        if (level < 0) { nvtxRangePushA(name); return; }
+        char buf[64];
+        snprintf(buf, sizeof(buf), "%s L%d", name, level);
+        nvtxRangePushA(buf);
+    }
+    ~Range() { nvtxRangePop(); }
+#else
+    explicit Range(const char*, int = -1) {}
+#endif
+    Range(const Range&) = delete;
+    Range& operator=(const Range&) = delete;
+};
 
 #define CUDA_OK(call)                                                                        \
     do {                                                                                     \
@@ -122,11 +144,8 @@ struct hmg_ctx {
     ncclComm_t comm = nullptr;
     CutView cutv[3] = {};
     int64_t cut_nglobal[3] = {0, 0, 0};
-    std::vector<double*> cut_send;       // per level: packed partial sums, slots of foreign cells stay zero
-    double* cut_recv = nullptr;
-    // neighbour exchange (default): one message per rank that shares a cut cell, laid out per level as
+    // neighbour exchange: one message per rank that shares a cut cell, laid out per level as
     // [shared faces x npf][shared edges x npe][shared vertices]
-    bool cut_p2p = true;
     std::vector<int> neighbors;
     std::vector<std::vector<int64_t>> msg_off, msg_len;   // [level][neighbour]
     std::vector<int64_t*> kbase;         // per level, device: [nranks * 3] first entry of a kind's section
@@ -154,6 +173,10 @@ struct hmg_ctx {
     int64_t n_interior = 0;
     int64_t* interior_idx = nullptr;
     double* Ainv = nullptr;
+    // lambda / sigma the coarse inverse was built for: op_gen counts the changes of the operator, coarse_gen is the
+    // count the inverse belongs to; coarse_internal = the library assembled the matrix itself (it can do so again)
+    int64_t op_gen = 0, coarse_gen = -1;
+    bool coarse_internal = false;
     double *ubase = nullptr, *bint = nullptr, *xint = nullptr;
     double* symv_work = nullptr;         // per-tile partial sums of the half-traffic coarse mat-vec
     // staging
@@ -162,9 +185,6 @@ struct hmg_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_permuted[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // HMG_IFACE_SPLIT=1 (experiment): second stream for the multi-owner cells of an interface sum
-    cudaStream_t side_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int64_t launches = 0;
 
     ~hmg_ctx() {
@@ -172,7 +192,6 @@ struct hmg_ctx {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         if (copy_stream) cudaStreamSynchronize(copy_stream);
-        if (side_stream) cudaStreamSynchronize(side_stream);
         if (comm) nccl_destroy(comm);
         for (void* p : allocs) cudaFree(p);
         for (int q = 0; q < 2; ++q) {
@@ -180,9 +199,6 @@ struct hmg_ctx {
             if (ev_permuted[q]) cudaEventDestroy(ev_permuted[q]);
         }
         if (copy_stream) cudaStreamDestroy(copy_stream);
-        if (ev_fork) cudaEventDestroy(ev_fork);
-        if (ev_join) cudaEventDestroy(ev_join);
-        if (side_stream) cudaStreamDestroy(side_stream);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -297,15 +313,9 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const 
         std::memcpy(&id, nccl_id, sizeof(id));
         NCCL_OK(nccl().CommInitRank(&c->comm, nranks, id, rank));
     }
-    // interleave width: one warp lane per element of a unit.  Units of 16 (a warp takes two lines of a 3D
-    // plane, HMG_GROUP_WIDTH=16) leave more room for prefetch in the ring at level 6 but lose more to
-    // unpaired lines than they gain (measured: 0.72 vs 0.59 ms on 24 576 elements), so 32 is the default
+    // interleave width: one warp lane per element of a unit
     c->W = 32;
-    if (const char* w = getenv("HMG_GROUP_WIDTH")) {
-        const int v = atoi(w);
-        if (v == 32 || (v == 16 && dim == 3)) c->W = v;
-    }
-    c->wshift = c->W == 32 ? 5 : 4;
+    c->wshift = 5;
     c->nunits = (ne + c->W - 1) / c->W;
 
     // per-level tables and state vectors
@@ -332,7 +342,7 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const 
         L.cfg_rhs = make_apply_config(dim, R.m, R.nf, c->W, false, true);
         if (L.cfg_rhs.ring_rows <= 0) L.cfg_rhs = L.cfg;
         L.cfg_fused = make_apply_config(dim, R.m, R.nf, c->W, true);
-        if (c->W != 32 || (getenv("HMG_FUSE_P") && atoi(getenv("HMG_FUSE_P")) == 0)) L.cfg_fused.ring_rows = -1;
+        if (getenv("HMG_FUSE_P") && atoi(getenv("HMG_FUSE_P")) == 0) L.cfg_fused.ring_rows = -1;     // tests: the unfused path
         if (getenv("HMG_DEBUG_CFG"))
             for (const ApplyConfig* q : {&L.cfg, &L.cfg_rhs, &L.cfg_fused})
                 fprintf(stderr, "hmg: level %d (m=%d) %s: warps %d ring %d spill %d chunk %d run %d seg %d conv %d slots %d smem %zu\n", l, R.m,
@@ -364,10 +374,8 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const 
         c->tview.vert_off = c->dupload(P.verts.offset);
         c->tview.vert_own = c->dupload(P.verts.owner);
     }
-    // cut cells (owners on several ranks): packed exchange buffers, one layout per level
+    // cut cells (owners on several ranks)
     if (nranks > 1) {
-        int64_t max_slots = 1;
-        c->cut_send.assign(nlevels, nullptr);
         for (int kind = 0; kind < 3; ++kind) {
             const CutCells& C = P.cut[kind];
             c->cut_nglobal[kind] = C.nglobal;
@@ -377,12 +385,6 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const 
             c->cutv[kind].own = c->dupload(C.owner);
             c->cutv[kind].first_local = c->dupload(C.first_local);
         }
-        for (int l = 1; l <= nlevels; ++l) {
-            const int64_t slots = c->cut_slots(l);
-            max_slots = std::max(max_slots, slots);
-            c->cut_send[l - 1] = c->dalloc<double>((size_t)std::max<int64_t>(slots, 1));
-        }
-        c->cut_recv = c->dalloc<double>((size_t)max_slots);
         c->node_contrib = c->dupload(P.node_contrib);
         for (int kind = 0; kind < 3; ++kind) {
             const CutCells& C = P.cut[kind];
@@ -391,7 +393,6 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const 
             c->cutv[kind].peer_idx = c->dupload(C.peer_idx);
             c->cutv[kind].my_pos = c->dupload(C.my_pos);
         }
-        if (const char* v = getenv("HMG_CUT_ALLREDUCE")) c->cut_p2p = atoi(v) == 0;
         for (int q = 0; q < nranks; ++q)
             if (q != rank && P.shared_with[(size_t)q * 3] + P.shared_with[(size_t)q * 3 + 1] + P.shared_with[(size_t)q * 3 + 2] > 0)
                 c->neighbors.push_back(q);
@@ -469,32 +470,22 @@ void do_apply(hmg_ctx* c, int l, int mode, double alpha, const double* x, double
     HMG_CHECK(n >= 0, "apply kernel refused the launch configuration");
     check_launch(c, n);
 }
-// cut cells: only interface partial sums move (NCCL over NVLink).  Default: every rank sends the partial sum of a
-// cut node to the ranks that share it (grouped ncclSend / ncclRecv with its <= 7 neighbours in a block partition)
-// and adds the partial sums in ascending rank order.  HMG_CUT_ALLREDUCE=1: one all-reduce of a packed buffer that
-// covers the cut cells of all ranks (simpler, 7x the traffic on 8 ranks).  sq: also add owners x total^2 to S_TMP.
+// cut cells: only interface partial sums move (NCCL over NVLink).  Every rank sends the partial sum of a cut node to
+// the ranks that share it (grouped ncclSend / ncclRecv with its <= 7 neighbours in a block partition) and adds the
+// partial sums in ascending rank order.  sq: also add owners x total^2 to S_TMP.
 void do_cut_exchange_impl(hmg_ctx* c, int l, double* x, bool sq) {
     const LevelView& V = c->level(l).view;
-    if (c->cut_p2p) {
-        const std::vector<int64_t>& off = c->msg_off[l - 1];
-        const std::vector<int64_t>& len = c->msg_len[l - 1];
-        check_launch(c, launch_cut_p2p(c->dim, CUT_PACK, V, c->cutv, c->kbase[l - 1], x, c->p2p_send, false, c->red, c->stream));
-        NCCL_OK(nccl().GroupStart());
-        for (size_t q = 0; q < c->neighbors.size(); ++q) {
-            if (len[q] == 0) continue;
-            NCCL_OK(nccl().Send(c->p2p_send + off[q], (size_t)len[q], ncclDouble, c->neighbors[q], c->comm, c->stream));
-            NCCL_OK(nccl().Recv(c->p2p_recv + off[q], (size_t)len[q], ncclDouble, c->neighbors[q], c->comm, c->stream));
-        }
-        NCCL_OK(nccl().GroupEnd());
-        check_launch(c, launch_cut_p2p(c->dim, CUT_UNPACK, V, c->cutv, c->kbase[l - 1], x, c->p2p_recv, sq, c->red, c->stream));
-        return;
+    const std::vector<int64_t>& off = c->msg_off[l - 1];
+    const std::vector<int64_t>& len = c->msg_len[l - 1];
+    check_launch(c, launch_cut_p2p(c->dim, CUT_PACK, V, c->cutv, c->kbase[l - 1], x, c->p2p_send, false, c->red, c->stream));
+    NCCL_OK(nccl().GroupStart());
+    for (size_t q = 0; q < c->neighbors.size(); ++q) {
+        if (len[q] == 0) continue;
+        NCCL_OK(nccl().Send(c->p2p_send + off[q], (size_t)len[q], ncclDouble, c->neighbors[q], c->comm, c->stream));
+        NCCL_OK(nccl().Recv(c->p2p_recv + off[q], (size_t)len[q], ncclDouble, c->neighbors[q], c->comm, c->stream));
     }
-    const int64_t slots = c->cut_slots(l);
-    double* send = c->cut_send[l - 1];
-    const int64_t base[3] = {c->cut_base(l, 0), c->cut_base(l, 1), c->cut_base(l, 2)};
-    check_launch(c, launch_cut(c->dim, CUT_PACK, V, c->cutv, base, x, send, false, c->red, c->stream));
-    NCCL_OK(nccl().AllReduce(send, c->cut_recv, (size_t)slots, ncclDouble, ncclSum, c->comm, c->stream));
-    check_launch(c, launch_cut(c->dim, CUT_UNPACK, V, c->cutv, base, x, c->cut_recv, sq, c->red, c->stream));
+    NCCL_OK(nccl().GroupEnd());
+    check_launch(c, launch_cut_p2p(c->dim, CUT_UNPACK, V, c->cutv, c->kbase[l - 1], x, c->p2p_recv, sq, c->red, c->stream));
 }
 void do_cut_exchange(hmg_ctx* c, int l, double* x) {
     const int64_t slots = c->cut_slots(l);
@@ -502,25 +493,7 @@ void do_cut_exchange(hmg_ctx* c, int l, double* x) {
     do_cut_exchange_impl(c, l, x, false);
 }
 void do_broadcast(hmg_ctx* c, int l, double* x) {
-    // HMG_IFACE_SPLIT=1 (experiment, untimed): the cells with more than two owners take a third of the interface kernel
-    // for a tenth of its bytes (latency-bound chains, scheduled after all the face blocks); as a second kernel on a
-    // second stream their blocks share the SMs with the face blocks instead.  The two parts touch disjoint entries.
-    static const bool split = getenv("HMG_IFACE_SPLIT") && atoi(getenv("HMG_IFACE_SPLIT")) == 1;
-    if (split) {
-        if (!c->side_stream) {
-            CUDA_OK(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
-            CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-            CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-        }
-        CUDA_OK(cudaEventRecord(c->ev_fork, c->stream));
-        CUDA_OK(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
-        check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->stream, 1));
-        check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->side_stream, 2));
-        CUDA_OK(cudaEventRecord(c->ev_join, c->side_stream));
-        CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-    } else {
-        check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->stream));
-    }
+    check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->stream));
     do_cut_exchange(c, l, x);
 }
 void do_zero_all_but_one(hmg_ctx* c, int l, double* x) {
@@ -543,11 +516,23 @@ void do_local_residual(hmg_ctx* c, int l) {
     do_apply(c, l, APPLY_RESIDUAL, 1.0, c->vecp(l, HMG_X), c->vecp(l, HMG_R), c->vecp(l, HMG_B));
 }
 // y = broadcast(constraint(A x)); with dot_post >= 0 the apply kernel also reduces
-// sum_entries owners(entry) * x * y_local = dot(x, y) over all stored entries (x consistent across owners)
-void do_global_product(hmg_ctx* c, int l, const double* x, double* y, int dot_post = -1) {
-    do_apply(c, l, APPLY_AX, 1.0, x, y, nullptr, dot_post >= 0 ? kernel_post(c, dot_post) : -1);   // y = constraint(A x), column-local
+// sum_entries owners(entry) * x * y_local = dot(x, y) over all stored entries (x consistent across owners).
+// dot_only: nothing but that reduction is wanted -- y is neither stored nor interface-summed.
+void do_global_product(hmg_ctx* c, int l, const double* x, double* y, int dot_post = -1, bool dot_only = false) {
+    LevelDev& L = c->level(l);
+    ApplyArgs a;
+    a.L = L.view; a.cfg = L.cfg; a.cfg_fused = L.cfg_fused; a.cfg_rhs = L.cfg_rhs;
+    a.nunits = c->nunits; a.tab = L.tab.data();
+    a.coef = c->elem_coef; a.cmask = c->cmask; a.mult = c->mult;
+    a.x = x; a.y = y; a.b = nullptr;
+    a.alpha = 1.0; a.lambda = c->lambda; a.mode = APPLY_AX;
+    a.dot_post = dot_post >= 0 ? kernel_post(c, dot_post) : -1; a.red = c->red;
+    a.store = !dot_only;
+    const int n = launch_apply(c->dim, a, c->stream);                // y = constraint(A x), column-local
+    HMG_CHECK(n >= 0, "apply kernel refused the launch configuration");
+    check_launch(c, n);
     if (dot_post >= 0) finish_reduction(c, dot_post, S_TMP);
-    do_broadcast(c, l, y);                                       // interface sums
+    if (!dot_only) do_broadcast(c, l, y);                            // interface sums
 }
 // r = broadcast(r) and rho = dot(r, r) over all stored entries without a pass over r: the residual apply
 // left the interior part in S_TMP; the interface kernels add (owners x sum^2) of every shared node
@@ -565,8 +550,9 @@ void do_broadcast_rho(hmg_ctx* c, int l, double* r) {
     finish_reduction(c, POST_RHO, S_TMP);
 }
 // p' = r + beta p and Ap = broadcast(constraint(A p')) with p' applied straight out of shared memory: the new
-// direction goes to the level's second p buffer (other CTAs still read the old one), then the buffers swap
-void do_fused_direction_product(hmg_ctx* c, int l) {
+// direction goes to the level's second p buffer (other CTAs still read the old one), then the buffers swap.
+// dot_only: p' and p'.Ap only (Ap is neither stored nor summed).
+void do_fused_direction_product(hmg_ctx* c, int l, bool dot_only = false) {
     LevelDev& L = c->level(l);
     if (!L.p2) L.p2 = c->dalloc<double>((size_t)c->nstored(l));
     ApplyArgs a;
@@ -577,14 +563,20 @@ void do_fused_direction_product(hmg_ctx* c, int l) {
     a.y = c->vecp(l, HMG_AP); a.b = nullptr;
     a.alpha = 1.0; a.lambda = c->lambda; a.mode = APPLY_AX;
     a.dot_post = kernel_post(c, POST_PAP); a.red = c->red;
+    a.store = !dot_only;
     const int n = launch_apply(c->dim, a, c->stream);
     HMG_CHECK(n >= 0, "apply kernel refused the fused launch configuration");
     check_launch(c, n);
     std::swap(L.vec[HMG_P], L.p2);
     finish_reduction(c, POST_PAP, S_TMP);
-    do_broadcast(c, l, c->vecp(l, HMG_AP));
+    if (!dot_only) do_broadcast(c, l, c->vecp(l, HMG_AP));
 }
-void do_smoothing(hmg_ctx* c, int l, int steps) {
+// smoothing_steps! (src/multigrid.jl:46-71).  need_r = false (inside a V-cycle, wherever nothing reads the residual of
+// the last step: before the restriction -- local_residual! recomputes r -- and after the correction on every level
+// below the top): the last step shrinks to alpha = rho / p.Ap and x += alpha p; its r-update, rho', the interface sum
+// of Ap and Ap itself are dead in the reference too.  x is bit-identical either way.
+void do_smoothing(hmg_ctx* c, int l, int steps, bool need_r = true) {
+    Range range("hmg smoothing_steps", l);
     const int64_t n = c->nstored(l);
     double *x = c->vecp(l, HMG_X), *r = c->vecp(l, HMG_R), *p = c->vecp(l, HMG_P), *Ap = c->vecp(l, HMG_AP);
     // r = broadcast(constraint(b - A x)), rho = r.r (src/multigrid.jl:50-54); the copy p = r is folded into the
@@ -594,13 +586,19 @@ void do_smoothing(hmg_ctx* c, int l, int steps) {
     if (steps == 0) CUDA_OK(cudaMemcpyAsync(p, r, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     const bool fuse = c->level(l).cfg_fused.ring_rows > 0;
     for (int i = 0; i < steps; ++i) {
+        const bool x_only = !need_r && i == steps - 1;
         // Ap = broadcast(constraint(A p)), alpha = rho / p.Ap; after the first step the direction update
         // p = r + beta p (src/multigrid.jl:68) happens inside the product
-        if (i == 0) do_global_product(c, l, r, Ap, POST_PAP);
-        else if (fuse) { do_fused_direction_product(c, l); p = c->vecp(l, HMG_P); }
+        const double* dir = p;
+        if (i == 0) { do_global_product(c, l, r, Ap, POST_PAP, x_only); dir = r; }
+        else if (fuse) { do_fused_direction_product(c, l, x_only); p = c->vecp(l, HMG_P); dir = p; }
         else {
             check_launch(c, launch_p_update(c->red, p, r, n, c->stream));
-            do_global_product(c, l, p, Ap, POST_PAP);
+            do_global_product(c, l, p, Ap, POST_PAP, x_only);
+        }
+        if (x_only) {
+            check_launch(c, launch_x_update(c->red, x, dir, n, c->stream));
+            break;
         }
         check_launch(c, launch_cg_update(c->red, x, p, r, Ap, n, kernel_post(c, POST_RSQR), i == 0, c->stream));
         finish_reduction(c, POST_RSQR, S_TMP);
@@ -608,8 +606,15 @@ void do_smoothing(hmg_ctx* c, int l, int steps) {
         // (the next smoothing call starts from a fresh residual)
     }
 }
+void assemble_coarse_impl(hmg_ctx* c);
 void do_coarse_solve(hmg_ctx* c) {
+    Range range("hmg coarse solve", 1);
     HMG_CHECK(c->n_interior > 0, "coarse matrix not set: call hmg_set_coarse_matrix or hmg_assemble_coarse first");
+    if (c->coarse_gen != c->op_gen) {
+        // hmg_set_lambda / hmg_set_sigma after the factorisation: the inverse belongs to another operator
+        HMG_CHECK(c->coarse_internal, "lambda or sigma changed after hmg_set_coarse_matrix: hand over the new coarse matrix first");
+        assemble_coarse_impl(c);
+    }
     LevelDev& L1 = c->level(1);
     do_broadcast(c, 1, c->vecp(1, HMG_B));
     if (c->nranks == 1) {
@@ -630,17 +635,24 @@ void do_coarse_solve(hmg_ctx* c) {
     if (c->nranks > 1) NCCL_OK(nccl().Broadcast(c->ubase, c->ubase, (size_t)c->nn, ncclDouble, 0, c->comm, c->stream));
     check_launch(c, launch_distribute(c->dim, L1.view, c->ne, c->elems32, c->ubase, c->vecp(1, HMG_X), c->stream));
 }
-void do_vcycle(hmg_ctx* c, int k, int steps) {
+void do_vcycle(hmg_ctx* c, int k, int steps, int top) {
     if (k == 1) { do_coarse_solve(c); return; }
-    do_smoothing(c, k, steps);
+    Range range("hmg vcycle", k);
+    do_smoothing(c, k, steps, false);
+    {
+    Range transfer("hmg residual + restrict", k);
     do_local_residual(c, k);
     check_launch(c, launch_restrict(c->dim, c->level(k).view, c->level(k - 1).view, c->nunits, c->vecp(k, HMG_R),
                                     c->vecp(k - 1, HMG_B), c->stream));
     check_launch(c, launch_fill(c->vecp(k - 1, HMG_X), 0.0, c->nstored(k - 1), c->stream));
-    do_vcycle(c, k - 1, 2);   // the reference does not forward `steps` (src/multigrid.jl:109)
+    }
+    do_vcycle(c, k - 1, 2, top);   // the reference does not forward `steps` (src/multigrid.jl:109)
+    {
+    Range transfer("hmg interpolate", k);
     check_launch(c, launch_interp_add(c->dim, c->level(k).view, c->level(k - 1).view, c->nunits, c->vecp(k, HMG_X),
                                       c->vecp(k - 1, HMG_X), c->stream));
-    do_smoothing(c, k, steps);
+    }
+    do_smoothing(c, k, steps, k == top);      // the residual of the top level is the caller's (logged norm)
 }
 double read_scalar(hmg_ctx* c, int slot) {
     double v = 0.0;
@@ -766,6 +778,52 @@ void set_coarse_dense(hmg_ctx* c, int64_t n, const std::vector<int64_t>& colptr,
     c->dfree(info);
 }
 
+void assemble_coarse_impl(hmg_ctx* c) {
+    // P1 assembly of lambda*M + K(sigma) on the base mesh, restricted to the interior nodes
+    const int dim = c->dim, nv = dim + 1, cs = dim == 3 ? 8 : 4, nc = dim == 3 ? 7 : 4;
+    std::vector<double> coef;            // of ALL elements: the coarse operator couples the whole base mesh
+    element_coefficients(dim, c->ne_global, c->nodes.data(), c->elems_global.data(), c->sigma_global.data(), coef, cs);
+    const std::vector<int64_t>& interior = c->topo.interior_nodes;
+    const int64_t n = (int64_t)interior.size();
+    HMG_CHECK(n > 0, "base mesh has no interior nodes");
+    std::vector<int64_t> pos(c->nn, -1);
+    for (int64_t q = 0; q < n; ++q) pos[interior[q]] = q;
+    const double fact = dim == 3 ? 6.0 : 2.0;
+    const double gref[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    std::vector<std::map<int64_t, double>> cols(n);
+    c->coarse_internal = true;
+    c->coarse_gen = c->op_gen;
+    if (c->rank != 0) { c->n_interior = n; return; }
+    for (int64_t e = 0; e < c->ne_global; ++e) {
+        const double* ec = &coef[(size_t)e * cs];
+        double P[3][3];
+        int q = 0;
+        for (int k = 0; k < dim; ++k)
+            for (int l = k; l < dim; ++l, ++q) P[k][l] = P[l][k] = ec[q];
+        const double detJ = ec[nc - 1];
+        for (int a = 0; a < nv; ++a) {
+            const int64_t ra = pos[c->elems_global[e * nv + a]];
+            if (ra < 0) continue;
+            for (int b = 0; b < nv; ++b) {
+                const int64_t rb = pos[c->elems_global[e * nv + b]];
+                if (rb < 0) continue;
+                double s = 0.0;
+                for (int k = 0; k < dim; ++k)
+                    for (int l = 0; l < dim; ++l) s += gref[a][k] * P[k][l] * gref[b][l];
+                const double mass = detJ * (a == b ? 2.0 : 1.0) / (fact * (dim + 1) * (dim + 2));
+                cols[rb][ra] += s / fact + c->lambda * mass;
+            }
+        }
+    }
+    std::vector<int64_t> cp(n + 1, 0), rv;
+    std::vector<double> nz;
+    for (int64_t j = 0; j < n; ++j) {
+        for (const auto& kv : cols[j]) { rv.push_back(kv.first); nz.push_back(kv.second); }
+        cp[j + 1] = (int64_t)rv.size();
+    }
+    set_coarse_dense(c, n, cp, rv, nz, interior);
+}
+
 }  // namespace
 
 #define HMG_API_BEGIN try {
@@ -841,6 +899,7 @@ int hmg_local_elements(const hmg_ctx* c, int64_t* out) {
 int hmg_set_lambda(hmg_ctx* c, double lambda) {
     HMG_API_BEGIN
     NEED_CTX(c);
+    if (lambda != c->lambda) ++c->op_gen;      // the coarse inverse (if any) belongs to the old operator
     c->lambda = lambda;
     HMG_API_END
 }
@@ -850,6 +909,7 @@ int hmg_set_sigma(hmg_ctx* c, const double* sigma) {
     HMG_CHECK(sigma != nullptr, "null sigma");
     CUDA_OK(cudaSetDevice(c->device));
     upload_operator(c, sigma);
+    ++c->op_gen;
     HMG_API_END
 }
 
@@ -1080,6 +1140,8 @@ int hmg_set_coarse_matrix(hmg_ctx* c, int64_t n, const int64_t* colptr, const in
     for (auto& v : rv) { v -= 1; HMG_CHECK(v >= 0 && v < n, "coarse matrix row out of range"); }
     std::vector<double> nz(nzval, nzval + cp[n]);
     set_coarse_dense(c, n, cp, rv, nz, in0);
+    c->coarse_internal = false;
+    c->coarse_gen = c->op_gen;
     HMG_API_END
 }
 
@@ -1087,47 +1149,7 @@ int hmg_assemble_coarse(hmg_ctx* c) {
     HMG_API_BEGIN
     NEED_CTX(c);
     CUDA_OK(cudaSetDevice(c->device));
-    // P1 assembly of lambda*M + K(sigma) on the base mesh, restricted to the interior nodes
-    const int dim = c->dim, nv = dim + 1, cs = dim == 3 ? 8 : 4, nc = dim == 3 ? 7 : 4;
-    std::vector<double> coef;            // of ALL elements: the coarse operator couples the whole base mesh
-    element_coefficients(dim, c->ne_global, c->nodes.data(), c->elems_global.data(), c->sigma_global.data(), coef, cs);
-    const std::vector<int64_t>& interior = c->topo.interior_nodes;
-    const int64_t n = (int64_t)interior.size();
-    HMG_CHECK(n > 0, "base mesh has no interior nodes");
-    std::vector<int64_t> pos(c->nn, -1);
-    for (int64_t q = 0; q < n; ++q) pos[interior[q]] = q;
-    const double fact = dim == 3 ? 6.0 : 2.0;
-    const double gref[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-    std::vector<std::map<int64_t, double>> cols(n);
-    if (c->rank != 0) { c->n_interior = n; return 0; }
-    for (int64_t e = 0; e < c->ne_global; ++e) {
-        const double* ec = &coef[(size_t)e * cs];
-        double P[3][3];
-        int q = 0;
-        for (int k = 0; k < dim; ++k)
-            for (int l = k; l < dim; ++l, ++q) P[k][l] = P[l][k] = ec[q];
-        const double detJ = ec[nc - 1];
-        for (int a = 0; a < nv; ++a) {
-            const int64_t ra = pos[c->elems_global[e * nv + a]];
-            if (ra < 0) continue;
-            for (int b = 0; b < nv; ++b) {
-                const int64_t rb = pos[c->elems_global[e * nv + b]];
-                if (rb < 0) continue;
-                double s = 0.0;
-                for (int k = 0; k < dim; ++k)
-                    for (int l = 0; l < dim; ++l) s += gref[a][k] * P[k][l] * gref[b][l];
-                const double mass = detJ * (a == b ? 2.0 : 1.0) / (fact * (dim + 1) * (dim + 2));
-                cols[rb][ra] += s / fact + c->lambda * mass;
-            }
-        }
-    }
-    std::vector<int64_t> cp(n + 1, 0), rv;
-    std::vector<double> nz;
-    for (int64_t j = 0; j < n; ++j) {
-        for (const auto& kv : cols[j]) { rv.push_back(kv.first); nz.push_back(kv.second); }
-        cp[j + 1] = (int64_t)rv.size();
-    }
-    set_coarse_dense(c, n, cp, rv, nz, interior);
+    assemble_coarse_impl(c);
     HMG_API_END
 }
 
@@ -1157,7 +1179,7 @@ int hmg_distribute(hmg_ctx* c, int which, const double* u_host) {
 }
 
 static void vcycle_with_norm(hmg_ctx* c, int top, int steps, bool want_norm, int slot) {
-    do_vcycle(c, top, steps);
+    do_vcycle(c, top, steps, top);
     if (want_norm) {
         double* r = c->vecp(top, HMG_R);
         do_zero_all_but_one(c, top, r);
@@ -1330,7 +1352,7 @@ int hmg_time_op(hmg_ctx* c, int op, int level, int steps, int reps, float* ms_ou
         if (op == 0) {
             do_global_product(c, level, c->vecp(level, HMG_P), c->vecp(level, HMG_AP));
         } else if (op == 1) {
-            do_vcycle(c, level, steps);
+            do_vcycle(c, level, steps, level);
         } else if (op == 2) {
             do_apply(c, level, APPLY_MULADD, 1.0, c->vecp(level, HMG_P), c->vecp(level, HMG_AP), nullptr);
         } else if (op == 3) {

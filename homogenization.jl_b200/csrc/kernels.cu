@@ -113,10 +113,8 @@ __device__ __forceinline__ void block_reduce_finish(double v, const Reducer& R, 
 // ------------------------------------------------------------------------------------------
 // K1: local operator apply
 // ------------------------------------------------------------------------------------------
-// Lanes are coarse elements (W = 32 interleaved columns; W = 16 for 6-level 3D hierarchies, where a warp
-// takes TWO lines of a plane, one per half-warp -- all interior lines of a diagonal plane have the same
-// length and classes), so node class, neighbour offsets and control flow are warp-uniform and every
-// shared/global access of a warp is one (two) conflict-free row(s) of W doubles.
+// Lanes are coarse elements (W = 32 interleaved columns), so node class, neighbour offsets and control flow are
+// warp-uniform and every shared/global access of a warp is one conflict-free row of W doubles.
 // A CTA owns a contiguous range of (element group, lattice plane) pairs, balanced by rows.  Its input
 // rows stream ONCE from HBM through a shared-memory ring: one elected thread issues TMA bulk copies
 // (cp.async.bulk, completion on mbarriers) of fixed-size chunks, consumer warps take the lines of the
@@ -165,9 +163,10 @@ template <int DIM> __device__ __forceinline__ int64_t plane_at_or_after(int64_t 
     return (u + 1) * (m + 1);
 }
 
-template <int DIM, int W, int MODE, bool DOT> struct OutDev {
+// STORE = false: only the fused reduction of the product is wanted (the last CG step of a smoothing call whose residual
+// nobody reads: alpha = rho / p.Ap needs the dot, x += alpha p needs p -- the vector Ap itself is dead)
+template <int DIM, int W, int MODE, bool DOT, bool STORE = true> struct OutDev {
     static constexpr int APPLY_W = W;
-    bool active;           // false: this half-warp repeats its sibling's line (its results are dropped)
     double* yl;            // output row of node 0 of the current line (lane included)
     const double* tl;
     double sa;
@@ -196,13 +195,9 @@ template <int DIM, int W, int MODE, bool DOT> struct OutDev {
         for (int q = 0; q < TD; ++q) tq[q] = __ldcs(tl + min(k0 + q, klast) * APPLY_W);
     }
     template <int CLS> __device__ __forceinline__ void put(int k, double acc, double x0) {
-#ifdef HMG_LEAN_PUT
-        // build variant (make HMG_EXTRA=-DHMG_LEAN_PUT, untimed): bit 0 of the class mask is never set -- topology.cpp only
-        // sets the bits of face / edge / vertex classes -- so interior nodes need no Dirichlet select (4 FSEL per two nodes)
+        // bit 0 of the class mask is never set (topology.cpp only sets face / edge / vertex classes): interior nodes need no
+        // Dirichlet select
         const bool fixed = CLS != 0 && MODE != APPLY_MULADD && ((cm >> CLS) & 1u);
-#else
-        const bool fixed = MODE != APPLY_MULADD && ((cm >> CLS) & 1u);
-#endif
         double v;
         if (MODE == APPLY_AX) v = fixed ? 0.0 : acc;
         else {
@@ -212,12 +207,10 @@ template <int DIM, int W, int MODE, bool DOT> struct OutDev {
             tq[TD - 1] = __ldcs(tl + min(k + TD, klast) * APPLY_W);
             v = MODE == APPLY_RESIDUAL ? (fixed ? 0.0 : tv - acc) : fma(sa, acc, tv);
         }
-        if (W == 32 || active) {
-            yl[k * APPLY_W] = v;
-            if (DOT) {
-                if (MODE == APPLY_AX) dsum = fma(weight<CLS>() * x0, v, dsum);
-                else if (CLS == 0) dsum = fma(v, v, dsum);      // interior part of dot(r, r); interfaces: K2
-            }
+        if (STORE) yl[k * APPLY_W] = v;
+        if (DOT) {
+            if (MODE == APPLY_AX) dsum = fma(weight<CLS>() * x0, v, dsum);
+            else if (CLS == 0) dsum = fma(v, v, dsum);      // interior part of dot(r, r); interfaces: K2
         }
     }
 };
@@ -231,18 +224,19 @@ struct SmemLoad {
 // src/multigrid.jl:68.  The producer warp bulk-copies chunks of r and p into a small staging area, converts them
 // into the ring (p' is what the stencil reads) and stores p' to the OTHER p buffer (neighbouring CTAs still read
 // the old p for their halo planes), so p' never makes a round trip through HBM before it is applied.
-template <int DIM, int W, int MODE, bool DOT, bool FUSEP>
+template <int DIM, int W, int MODE, bool DOT, bool FUSEP, bool STORE = true>
 __global__ void __launch_bounds__(DIM == 3 ? HMG_MAXT3 : APPLY_MAXT, 1) apply_kernel(const __grid_constant__ ApplyParams<DIM> a) {
     using D = Dims<DIM>;
     constexpr int APPLY_W = W;
-    static_assert(W == 32 || (W == 16 && DIM == 3), "W = 16 pairs two lines of a 3D plane per warp");
+    static_assert(W == 32, "a unit is one warp wide");
+    static_assert(STORE || (DOT && MODE == APPLY_AX), "without the store only the fused p.Ap is left");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[APPLY_Q], empty_bar[APPLY_Q], stage_bar[APPLY_STAGES];
     double* sm = reinterpret_cast<double*>(smem_raw);
     const int m = a.m, nf = a.nf, NW = a.nwarps, R = a.R, SP = a.SP, CS = a.cs, CH = 1 << a.cs;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
-    const int el = lane & (W - 1), half = lane / W;     // element of the unit, line of the pair (W = 16)
+    const int el = lane;                                 // element of the unit
     const int NPL = m + 1;
 
     if (threadIdx.x == 0) {
@@ -383,8 +377,7 @@ __global__ void __launch_bounds__(DIM == 3 ? HMG_MAXT3 : APPLY_MAXT, 1) apply_ke
     } else if (nchunks > 0) {
         // ---------------- consumers ----------------
         SmemLoad mem{sm};
-        OutDev<DIM, W, MODE, DOT> out;
-        out.active = true;
+        OutDev<DIM, W, MODE, DOT, STORE> out;
         out.sa = a.sa;
         out.dsum = 0.0;
         out.cm = 0; out.ml = out.mh = 0ull;
@@ -507,34 +500,17 @@ __global__ void __launch_bounds__(DIM == 3 ? HMG_MAXT3 : APPLY_MAXT, 1) apply_ke
             if constexpr (DIM == 3) {
                 const int L = g.L;
                 auto adv = [&](int& p, int d) { p += d; if (p >= R) p -= R; };
-                auto kind = [&](int i) { return i == 0 ? 0 : (i == t ? 2 : 1); };
-                int li = 0;
-                while (li < nl) {
-                    const int i0 = il + li;
-                    // W = 16: the second half-warp takes the next line if it is of the same kind, else it repeats
-                    // this one (results dropped)
-                    const bool pair = W == 16 && li + 1 < nl && kind(i0) == kind(i0 + 1);
-                    const int hs = W == 16 && pair ? half : 0;
-                    if (W == 16) out.active = pair || half == 0;
-                    int pc = qc, pm0 = qm[0], pm1 = qm[1], pm2 = qm[2], pp0 = qp[0], pp1 = qp[1], pp2 = qp[2];
-                    if (hs) { adv(pc, L); adv(pm0, L - 1); adv(pm1, L - 1); adv(pm2, L); adv(pp0, L + 1); adv(pp1, L + 1); adv(pp2, L); }
-                    g.bc = pc * APPLY_W + el;
-                    g.bm[0] = pm0 * APPLY_W + el; g.bm[1] = pm1 * APPLY_W + el; g.bm[2] = pm2 * APPLY_W + el;
-                    g.bp[0] = pp0 * APPLY_W + el; g.bp[1] = pp1 * APPLY_W + el; g.bp[2] = pp2 * APPLY_W + el;
-                    double* const yl0 = out.yl;
-                    const double* const tl0 = out.tl;
-                    if (hs) { out.yl += L * APPLY_W; if (MODE != APPLY_AX) out.tl += L * APPLY_W; }
+                for (int li = 0; li < nl; ++li) {
+                    g.bc = qc * APPLY_W + el;
+                    g.bm[0] = qm[0] * APPLY_W + el; g.bm[1] = qm[1] * APPLY_W + el; g.bm[2] = qm[2] * APPLY_W + el;
+                    g.bp[0] = qp[0] * APPLY_W + el; g.bp[1] = qp[1] * APPLY_W + el; g.bp[2] = qp[2] * APPLY_W + el;
                     out.begin(0, L);
-                    run_line3(op, a.T, mem, APPLY_W, g, t, i0, out);
-                    // the next line(s) of the plane: every base moves by one line of its own plane
-                    const int step_lines = pair ? 2 : 1;
-                    for (int q = 0; q < step_lines; ++q) {
-                        adv(qc, L); adv(qm[0], L - 1); adv(qm[1], L - 1); adv(qm[2], L);
-                        adv(qp[0], L + 1); adv(qp[1], L + 1); adv(qp[2], L);
-                    }
-                    out.yl = yl0 + step_lines * L * APPLY_W;
-                    if (MODE != APPLY_AX) out.tl = tl0 + step_lines * L * APPLY_W;
-                    li += step_lines;
+                    run_line3(op, a.T, mem, APPLY_W, g, t, il + li, out);
+                    // the next line of the plane: every base moves by one line of its own plane
+                    adv(qc, L); adv(qm[0], L - 1); adv(qm[1], L - 1); adv(qm[2], L);
+                    adv(qp[0], L + 1); adv(qp[1], L + 1); adv(qp[2], L);
+                    out.yl += L * APPLY_W;
+                    if (MODE != APPLY_AX) out.tl += L * APPLY_W;
                 }
             } else {
                 // ring rows are taken at node kb = k0 - 1 of each line (the first node the segment reads), so that
@@ -586,6 +562,7 @@ static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool f
     const int maxw = (dim == 3 ? HMG_MAXT3 : APPLY_MAXT) / 32;      // warps of a CTA (consumers + producer / converters)
     c.nwarps = std::max(1, std::min(maxw - 1, envi("HMG_APPLY_WARPS", maxw - 1)));
     c.ctas_per_sm = 1;
+    c.oversub = envi("HMG_APPLY_OVERSUB", 0);
     c.seg = dim == 2 ? std::max(2, std::min(8, envi("HMG_APPLY_SEG_SHIFT", 5))) : 30;
     c.spill_rows = dim == 2 ? (1 << c.seg) + 3 : m + 3;       // rows a task may run past the base of a line
     const int rowb = W * 8;
@@ -656,12 +633,13 @@ static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool f
     return c;
 }
 
-template <int DIM, int W, int MODE, bool DOT, bool FUSEP = false>
+template <int DIM, int W, int MODE, bool DOT, bool FUSEP = false, bool STORE = true>
 static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
-    // per device: the opt-in shared-memory size is a per-device function attribute
+    // per device: the opt-in shared-memory size is a per-device function attribute.  One host thread per process drives
+    // the library (include/hmg.h), so these caches need no lock.
     static size_t configured_dev[64] = {0};
     static int sms_dev[64] = {0};
-    auto kern = apply_kernel<DIM, W, MODE, DOT, FUSEP>;
+    auto kern = apply_kernel<DIM, W, MODE, DOT, FUSEP, STORE>;
     const ApplyConfig& cfg = FUSEP ? a.cfg_fused : (MODE == APPLY_AX ? a.cfg : a.cfg_rhs);
     int dev = 0;
     cudaGetDevice(&dev);
@@ -669,7 +647,7 @@ static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
     size_t& configured = configured_dev[dev];
     int& sms = sms_dev[dev];
     if (cfg.smem_bytes > configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes) != cudaSuccess) return 0;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes) != cudaSuccess) return -1;
         configured = cfg.smem_bytes;
     }
     if (sms == 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -692,9 +670,8 @@ static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
     // first (SMs do not all see the same memory latency); every CTA still streams >= 8192 rows
     const int64_t planes = a.nunits * (a.L.m + 1);
     const int64_t rows_per_sm = a.nunits * a.L.nf / sms;
-    static const int over_env = getenv("HMG_APPLY_OVERSUB") ? atoi(getenv("HMG_APPLY_OVERSUB")) : 0;
     // (measured: + 6 % in 2D; in 3D the extra halo planes and pipeline fills cost more than they gain)
-    const int64_t over = over_env > 0 ? over_env : (DIM == 2 ? std::max<int64_t>(1, std::min<int64_t>(8, rows_per_sm / 8192)) : 1);
+    const int64_t over = cfg.oversub > 0 ? cfg.oversub : (DIM == 2 ? std::max<int64_t>(1, std::min<int64_t>(8, rows_per_sm / 8192)) : 1);
     int64_t grid = std::min<int64_t>((int64_t)sms * cfg.ctas_per_sm * over, planes);
     if (DOT) grid = std::min<int64_t>(grid, a.red.max_blocks);
     kern<<<(unsigned)grid, (cfg.nwarps + (FUSEP ? cfg.nconv : 1)) * 32, cfg.smem_bytes, st>>>(p);
@@ -702,21 +679,23 @@ static int launch_apply_t(const ApplyArgs& a, cudaStream_t st) {
 }
 
 template <int DIM, int W> static int launch_apply_d(const ApplyArgs& a, cudaStream_t st) {
+    if (!a.store && (a.mode != APPLY_AX || a.dot_post < 0)) return -1;       // nothing would be left of the product
     if (a.mode == APPLY_AX && a.r2 != nullptr) {
-        if (W != 32 || a.dot_post < 0 || a.cfg_fused.ring_rows <= 0) return -1;
-        return launch_apply_t<DIM, 32, APPLY_AX, true, true>(a, st);
+        if (a.dot_post < 0 || a.cfg_fused.ring_rows <= 0) return -1;
+        return a.store ? launch_apply_t<DIM, 32, APPLY_AX, true, true>(a, st) : launch_apply_t<DIM, 32, APPLY_AX, true, true, false>(a, st);
     }
-    if (a.mode == APPLY_AX) return a.dot_post >= 0 ? launch_apply_t<DIM, W, APPLY_AX, true>(a, st) : launch_apply_t<DIM, W, APPLY_AX, false>(a, st);
+    if (a.mode == APPLY_AX) {
+        if (a.dot_post < 0) return launch_apply_t<DIM, W, APPLY_AX, false>(a, st);
+        return a.store ? launch_apply_t<DIM, W, APPLY_AX, true>(a, st) : launch_apply_t<DIM, W, APPLY_AX, true, false, false>(a, st);
+    }
     if (a.mode == APPLY_RESIDUAL) return a.dot_post >= 0 ? launch_apply_t<DIM, W, APPLY_RESIDUAL, true>(a, st) : launch_apply_t<DIM, W, APPLY_RESIDUAL, false>(a, st);
     return launch_apply_t<DIM, W, APPLY_MULADD, false>(a, st);
 }
 
 int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st) {
     if (a.nunits == 0) return 0;
-    if (a.cfg.ring_rows <= 0) return -1;
-    if (a.L.W == 32) return dim == 3 ? launch_apply_d<3, 32>(a, st) : launch_apply_d<2, 32>(a, st);
-    if (a.L.W == 16 && dim == 3) return launch_apply_d<3, 16>(a, st);
-    return -1;
+    if (a.cfg.ring_rows <= 0 || a.L.W != 32) return -1;
+    return dim == 3 ? launch_apply_d<3, 32>(a, st) : launch_apply_d<2, 32>(a, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -724,15 +703,17 @@ int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 // Codimension-1 cells (3D faces, 2D edges) have exactly two owners: lanes are the elements of a
 // unit, the lower owner of a pair reads both copies, adds them in ascending owner order
-// (src/implicit_fine_grid.jl:219-244) and writes both.  Cells with more owners (3D edges, vertices)
-// are processed cell by cell: one thread per shared fine node.  OP 0: sum + broadcast; OP 1: zero
-// all but the first owner (src/implicit_fine_grid.jl:334-386).
+// (src/implicit_fine_grid.jl:219-244) and writes both.  Cells with more owners (3D edges, vertices):
+// a group of 8 threads per shared fine node, one owner per thread -- all owner copies are loaded at
+// once, every thread of the group adds them in ascending owner order (the same bits as the serial loop
+// of src/implicit_fine_grid.jl:262-283) and writes the sum to its own owner's copy.  OP 0: sum +
+// broadcast; OP 1: zero all but the first owner (src/implicit_fine_grid.jl:334-386).
 // SQ: additionally reduce sum over the touched entries of value^2 ( = owners * sum^2 per shared node) and add it
 // to S_TMP -- the part of rho = dot(r, r) that lives on interfaces; the apply kernel reduces the interior part
 // (src/multigrid.jl:54 without a pass over r).  With SQ the grid is bounded and blocks loop over virtual blocks.
-// MV (HMG_IFACE_MULTI=1, experiment): the owners of a multi-owner node are read four at a time -- addresses first, then
-// the loads, then the sum in ascending owner order (the same bits) -- instead of one dependent chain per owner.
-template <int DIM, int OP, bool SQ, bool MV = false>
+constexpr int MULTI_G = 8;                      // threads per shared node of a multi-owner cell
+constexpr int MULTI_ITEMS = 256 / MULTI_G;      // shared nodes per virtual block
+template <int DIM, int OP, bool SQ>
 __global__ void __launch_bounds__(256) interface_kernel(const LevelView L, const TopoView T, int64_t npair_blocks,
                                                         int64_t vb_begin, int64_t nvirtual, double* __restrict__ x, const Reducer R,
                                                         int post) {
@@ -786,12 +767,15 @@ __global__ void __launch_bounds__(256) interface_kernel(const LevelView L, const
             }
             continue;
         }
-        // multi-owner cells: 256 (cell, node) items per virtual block
+        // multi-owner cells: MULTI_ITEMS (cell, node) items per virtual block, MULTI_G threads each
         const int nel = DIM == 3 ? 6 : 3, nfl = DIM == 3 ? 4 : 0;
         const int64_t nedge_items = DIM == 3 ? T.nedges * L.npe : 0;
         const int64_t total = nedge_items + T.nverts;
-        const int64_t t = (vb - npair_blocks) * blockDim.x + threadIdx.x;
-        if (t >= total) continue;
+        const int sub = threadIdx.x & (MULTI_G - 1);
+        const int lane0 = (threadIdx.x & 31) & ~(MULTI_G - 1);         // first lane of the group
+        const unsigned gmask = ((1u << MULTI_G) - 1u) << lane0;
+        const int64_t t = (vb - npair_blocks) * MULTI_ITEMS + (threadIdx.x / MULTI_G);
+        if (t >= total) continue;                                      // whole groups leave together
         const int64_t* off;
         const int32_t* own;
         const uint16_t* tab;
@@ -810,59 +794,28 @@ __global__ void __launch_bounds__(256) interface_kernel(const LevelView L, const
             tab = L.iface_idx + nfl * L.npf + nel * L.npe;
         }
         const int64_t b = off[cell], en = off[cell + 1];
-        double s = 0.0;
-        if (MV) {
-            auto entry = [&](int64_t o) -> double* {
-                const int32_t id = own[o];
-                const int64_t el = id >> 3;
-                return x + ((el >> ws) * (int64_t)nf + __ldg(tab + (id & 7) * npc + k)) * W + (el & (W - 1));
-            };
-            constexpr int Q = 4;
-            for (int64_t o0 = b; o0 < en; o0 += Q) {
-                double* ptr[Q];
-                double v[Q];
-#pragma unroll
-                for (int q = 0; q < Q; ++q) ptr[q] = entry(min(o0 + q, en - 1));
-                if (OP == 0) {
-#pragma unroll
-                    for (int q = 0; q < Q; ++q) v[q] = *ptr[q];
-#pragma unroll
-                    for (int q = 0; q < Q; ++q)
-                        if (o0 + q < en) s += v[q];                 // ascending owner order, as the serial loop
-                } else {
-#pragma unroll
-                    for (int q = 0; q < Q; ++q)
-                        if (o0 + q < en && o0 + q > b) *ptr[q] = 0.0;
-                }
-            }
-            if (OP == 0) {
-                for (int64_t o0 = b; o0 < en; o0 += Q) {
-                    double* ptr[Q];
-#pragma unroll
-                    for (int q = 0; q < Q; ++q) ptr[q] = entry(min(o0 + q, en - 1));
-#pragma unroll
-                    for (int q = 0; q < Q; ++q)
-                        if (o0 + q < en) *ptr[q] = s;
-                }
-                if (SQ) sq = fma((double)(en - b) * s, s, sq);
-            }
+        auto entry = [&](int64_t o) -> double* {
+            const int32_t id = __ldg(own + o);
+            const int64_t el = id >> 3;
+            return x + ((el >> ws) * (int64_t)nf + __ldg(tab + (id & 7) * npc + k)) * W + (el & (W - 1));
+        };
+        if (OP == 1) {
+            for (int64_t o = b + 1 + sub; o < en; o += MULTI_G) *entry(o) = 0.0;
             continue;
         }
-        for (int64_t o = b; o < en; ++o) {
-            const int32_t id = own[o];
-            const int64_t el = id >> 3;
-            double* ptr = x + ((el >> ws) * (int64_t)nf + __ldg(tab + (id & 7) * npc + k)) * W + (el & (W - 1));
-            if (OP == 0) s += *ptr;
-            else if (o > b) *ptr = 0.0;
+        double s = 0.0;
+        double* mine = nullptr;                                        // this thread's owner copy of the first round
+        for (int64_t o0 = b; o0 < en; o0 += MULTI_G) {
+            const bool have = o0 + sub < en;
+            double* ptr = have ? entry(o0 + sub) : nullptr;
+            const double v = have ? *ptr : 0.0;
+            if (o0 == b) mine = ptr;
+            const int cnt = (int)min((int64_t)MULTI_G, en - o0);       // uniform within the group
+            for (int j = 0; j < cnt; ++j) s += __shfl_sync(gmask, v, lane0 + j);
         }
-        if (OP == 0) {
-            for (int64_t o = b; o < en; ++o) {
-                const int32_t id = own[o];
-                const int64_t el = id >> 3;
-                x[((el >> ws) * (int64_t)nf + __ldg(tab + (id & 7) * npc + k)) * W + (el & (W - 1))] = s;
-            }
-            if (SQ) sq = fma((double)(en - b) * s, s, sq);
-        }
+        if (mine) *mine = s;
+        for (int64_t o = b + MULTI_G + sub; o < en; o += MULTI_G) *entry(o) = s;      // more than MULTI_G owners: rare
+        if (SQ && sub == 0) sq = fma((double)(en - b) * s, s, sq);
     }
     if (SQ) block_reduce_finish(sq, R, post, S_TMP);
 }
@@ -883,17 +836,11 @@ static int launch_interface(int dim, const LevelView& L, const TopoView& T, doub
     const int64_t nunits = (T.ne + L.W - 1) / L.W;
     const int64_t npair_blocks = npc > 0 ? nunits * (dim == 3 ? 4 : 3) : 0;
     const int64_t multi = (dim == 3 ? T.nedges * L.npe : 0) + T.nverts;
-    const int64_t nmulti_blocks = (multi + 255) / 256;
+    const int64_t nmulti_blocks = (multi + MULTI_ITEMS - 1) / MULTI_ITEMS;
     const int64_t vb_begin = (part & 1) ? 0 : npair_blocks;
     const int64_t nvirtual = (part & 2) ? npair_blocks + nmulti_blocks : npair_blocks;
     if (nvirtual <= vb_begin) return 0;
     const unsigned grid = (unsigned)(SQ ? std::min<int64_t>(nvirtual - vb_begin, R.max_blocks) : nvirtual - vb_begin);
-    static const bool multi_var = getenv("HMG_IFACE_MULTI") && atoi(getenv("HMG_IFACE_MULTI")) == 1;
-    if (multi_var) {
-        if (dim == 3) interface_kernel<3, OP, SQ, true><<<grid, 256, 0, st>>>(L, T, npair_blocks, vb_begin, nvirtual, x, R, post);
-        else interface_kernel<2, OP, SQ, true><<<grid, 256, 0, st>>>(L, T, npair_blocks, vb_begin, nvirtual, x, R, post);
-        return 1;
-    }
     if (dim == 3) interface_kernel<3, OP, SQ><<<grid, 256, 0, st>>>(L, T, npair_blocks, vb_begin, nvirtual, x, R, post);
     else interface_kernel<2, OP, SQ><<<grid, 256, 0, st>>>(L, T, npair_blocks, vb_begin, nvirtual, x, R, post);
     return 1;
@@ -1181,6 +1128,22 @@ __global__ void __launch_bounds__(256) p_update_kernel(const double* __restrict_
     }
 }
 
+// x += alpha p with alpha on the device: all that is left of the last CG step of a smoothing call whose residual nobody
+// reads (src/multigrid.jl:65; the r-update, rho' and the p-update of that step are dead)
+__global__ void __launch_bounds__(256) x_update_kernel(const double* __restrict__ scalars, double* __restrict__ x,
+                                                       const double* __restrict__ p, int64_t n) {
+    const double alpha = scalars[S_ALPHA];
+    const int64_t n2 = n >> 1;
+    double2* x2 = reinterpret_cast<double2*>(x);
+    const double2* p2 = reinterpret_cast<const double2*>(p);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n2; t += (int64_t)gridDim.x * blockDim.x) {
+        double2 xv = x2[t];
+        const double2 pv = p2[t];
+        xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+        x2[t] = xv;
+    }
+}
+
 __global__ void __launch_bounds__(256) axpy_kernel(double alpha, const double* __restrict__ x, double* __restrict__ y, int64_t n) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
         y[t] = fma(alpha, x[t], y[t]);
@@ -1206,6 +1169,10 @@ int launch_cg_update(const Reducer& R, double* x, double* p, double* r, const do
 }
 int launch_p_update(const Reducer& R, double* p, const double* r, int64_t n, cudaStream_t st) {
     p_update_kernel<<<grid_for(n / 2 + 1, 256, kVecBlocks), 256, 0, st>>>(R.scalars, p, r, n);
+    return 1;
+}
+int launch_x_update(const Reducer& R, double* x, const double* p, int64_t n, cudaStream_t st) {
+    x_update_kernel<<<grid_for(n / 2 + 1, 256, kVecBlocks), 256, 0, st>>>(R.scalars, x, p, n);
     return 1;
 }
 int launch_axpy(double alpha, const double* x, double* y, int64_t n, cudaStream_t st) {

@@ -73,6 +73,7 @@ struct ApplyConfig {
     int stage_shift, nstage;   // fused p-update: log2(rows per staging slot), staging slots (0: not fused)
     int nconv, slot_shift;     // ... converter warps, log2(staging slots per converter warp)
     int ctas_per_sm;
+    int oversub;       // CTAs per SM slot of the grid (0: chosen from the problem size)
     size_t smem_bytes;
 };
 
@@ -97,6 +98,7 @@ struct ApplyArgs {
     // src/multigrid.jl:62 ) -> Reducer post-op; only with APPLY_AX
     int dot_post;              // -1: none
     Reducer red;
+    bool store = true;         // false (APPLY_AX with dot_post >= 0 only): y is not written, only the reduction is wanted
 };
 
 // launchers (all asynchronous on `st`); return the number of kernels launched
@@ -131,6 +133,7 @@ int launch_dot(const Reducer& R, const double* a, const double* b, int64_t n, in
 int launch_copy_dot(const Reducer& R, const double* r, double* p, int64_t n, int post, cudaStream_t st);
 int launch_cg_update(const Reducer& R, double* x, double* p, double* r, const double* Ap, int64_t n, int post, bool first, cudaStream_t st);
 int launch_p_update(const Reducer& R, double* p, const double* r, int64_t n, cudaStream_t st);
+int launch_x_update(const Reducer& R, double* x, const double* p, int64_t n, cudaStream_t st);   // x += S_ALPHA * p
 int launch_axpy(double alpha, const double* x, double* y, int64_t n, cudaStream_t st);
 int launch_fill(double* x, double v, int64_t n, cudaStream_t st);
 int launch_fill_columns(const LevelView& L, int64_t ne, double* x, double v, cudaStream_t st);

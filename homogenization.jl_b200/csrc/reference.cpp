@@ -410,17 +410,9 @@ RefElement build_reference(int dim, int nlevels) {
             }
             // the device enumerates face nodes lexicographically in (a, b) -- any fixed enumeration pairs
             // the owners consistently once the sequences above agree -- for better memory locality.
-            // HMG_FACE_ORDER=1 (experiment, untimed): weight b on the second vertex outermost, weight m - a - b on the
-            // third innermost -- consecutive nodes of the reference faces y = 0 and x = 0 are then consecutive rows of
-            // one lattice line, and the eight warps of an interface block touch eight neighbouring rows.
-            static const bool along_lines = getenv("HMG_FACE_ORDER") && atoi(getenv("HMG_FACE_ORDER")) == 1;
-            if (along_lines) {
-                for (int b = 1; b <= m - 2; ++b)
-                    for (int w2 = 1; b + w2 <= m - 1; ++w2) L.face_bary.push_back((uint16_t)((m - b - w2) | (b << 8)));
-            } else {
-                for (int a = 1; a <= m - 2; ++a)
-                    for (int b = 1; a + b <= m - 1; ++b) L.face_bary.push_back((uint16_t)(a | (b << 8)));
-            }
+            // (enumerating along the lattice lines instead was timed at the C4 size in round 2: no difference.)
+            for (int a = 1; a <= m - 2; ++a)
+                for (int b = 1; a + b <= m - 1; ++b) L.face_bary.push_back((uint16_t)(a | (b << 8)));
             HMG_CHECK((int)L.face_bary.size() == (m - 1) * (m - 2) / 2, "unexpected face-interior count");
         }
         {

@@ -45,7 +45,9 @@ LevelStates, resident on one GPU (hmg_create).  Freed by a finalizer (hmg_destro
 mutable struct DeviceGrid
     ctx::Ptr{Cvoid}
     implicit::ImplicitFineGrid
-    DeviceGrid(ctx::Ptr{Cvoid}, implicit::ImplicitFineGrid) = new(ctx, implicit)
+    σs_hash::UInt          # hash of the coefficient vector the context holds (see sync_operator!)
+    constraint::Any        # the ZeroDirichletConstraint the context was built for: derived from `implicit.base` at creation
+    DeviceGrid(ctx::Ptr{Cvoid}, implicit::ImplicitFineGrid) = new(ctx, implicit, UInt(0), nothing)
     function DeviceGrid(implicit::ImplicitFineGrid{dim}, σs::Vector{SVector{dim,Float64}}, λ::Float64; device::Integer = 0) where {dim}
         base = implicit.base
         ctx = Ref{Ptr{Cvoid}}(C_NULL)
@@ -57,7 +59,7 @@ mutable struct DeviceGrid
                 (Cint, Cint, Int64, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Float64, Cint, Ref{Ptr{Cvoid}}),
                 dim, nlevels(implicit), nelements(base), nnodes(base), nodes, elems, sig, λ, device, ctx))
         end
-        g = new(ctx[], implicit)
+        g = new(ctx[], implicit, hash(σs), nothing)
         finalizer(x -> (x.ctx == C_NULL || ccall((:hmg_destroy, libhmg), Cint, (Ptr{Cvoid},), x.ctx); x.ctx = C_NULL), g)
         return g
     end
@@ -111,9 +113,38 @@ end
 
 # ---- device methods of the reference's generic functions -------------------------------------
 
+"""
+    sync_operator!(grid, A::L2PlusDivAGrad)
+
+The context holds its own copy of the operator data.  Every device method that applies `A` forwards what the
+reference's operator struct may have had mutated since (src/build_local_operators.jl:26-32 is a `mutable struct`):
+λ always (a changed λ re-factorises an internally assembled coarse matrix on the next V-cycle), σs when its contents
+changed (`hmg_set_sigma`).  The Dirichlet constraint is derived from the base mesh when the context is created; an
+operator whose `constraint` is another object than the first one seen (the reference's driver builds a new one after
+every domain shrink, src/examples/homogenized_coefficients.jl:331-333) needs a new `DeviceGrid` on the shrunk mesh --
+that is an error here, not a silent mismatch.
+"""
+function sync_operator!(g::DeviceGrid, A::L2PlusDivAGrad)
+    check(ccall((:hmg_set_lambda, libhmg), Cint, (Ptr{Cvoid}, Float64), g.ctx, A.λ))
+    h = hash(A.σs)
+    if h != g.σs_hash
+        @assert length(A.σs) == nelements(g.implicit.base) "σs does not belong to the mesh of this DeviceGrid"
+        sig = reinterpret(Float64, A.σs)
+        GC.@preserve sig check(ccall((:hmg_set_sigma, libhmg), Cint, (Ptr{Cvoid}, Ptr{Float64}), g.ctx, sig))
+        g.σs_hash = h
+    end
+    if g.constraint === nothing
+        g.constraint = A.constraint
+    elseif g.constraint !== A.constraint
+        throw(HmgError("the operator carries another constraint than the one this DeviceGrid was used with: " *
+                       "a new constraint (domain shrink) requires a new DeviceGrid on the shrunk mesh"))
+    end
+    nothing
+end
+
 # mul!(α, base, A, x, y): y ← αAx + y   (src/apply_local_operators.jl:85-91)
 function mul!(α::Float64, base::Mesh, A::L2PlusDivAGrad, x::DeviceMatrix, y::DeviceMatrix)
-    check(ccall((:hmg_set_lambda, libhmg), Cint, (Ptr{Cvoid}, Float64), x.grid.ctx, A.λ))
+    sync_operator!(x.grid, A)
     check(ccall((:hmg_mul, libhmg), Cint, (Ptr{Cvoid}, Cint, Float64, Cint, Cint), x.grid.ctx, x.level, α, x.which, y.which))
     y
 end
@@ -132,7 +163,7 @@ zero_out_all_but_one!(x::DeviceMatrix, implicit::ImplicitFineGrid, level::Int) =
 
 # local_residual!(implicit, A, curr, k)   (src/apply_local_operators.jl:18-27)
 function local_residual!(implicit::ImplicitFineGrid, A::L2PlusDivAGrad, curr::LevelState{Float64,DeviceMatrix}, k::Int)
-    check(ccall((:hmg_set_lambda, libhmg), Cint, (Ptr{Cvoid}, Float64), curr.x.grid.ctx, A.λ))
+    sync_operator!(curr.x.grid, A)
     check(ccall((:hmg_local_residual, libhmg), Cint, (Ptr{Cvoid}, Cint), curr.x.grid.ctx, k))
 end
 
@@ -144,7 +175,7 @@ interpolate_and_sum_to!(y::DeviceMatrix, P::SparseMatrixCSC, x::DeviceMatrix) =
 
 # smoothing_steps!(steps, implicit, ops, curr, k)   (src/multigrid.jl:46-71)
 function smoothing_steps!(steps::Integer, implicit::ImplicitFineGrid, ops::L2PlusDivAGrad, curr::LevelState{Float64,DeviceMatrix}, k::Int)
-    check(ccall((:hmg_set_lambda, libhmg), Cint, (Ptr{Cvoid}, Float64), curr.x.grid.ctx, ops.λ))
+    sync_operator!(curr.x.grid, ops)
     check(ccall((:hmg_smoothing_steps, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint), curr.x.grid.ctx, k, steps))
 end
 
@@ -167,7 +198,7 @@ end
 # vcycle!(implicit, base, ops, levels, k, steps)   (src/multigrid.jl:73-119): one ccall per V-cycle
 function vcycle!(implicit::ImplicitFineGrid, base::DeviceBaseLevel, ops::Vector{<:L2PlusDivAGrad},
                  levels::Vector{LevelState{Float64,DeviceMatrix}}, k::Int, steps = 2)
-    check(ccall((:hmg_set_lambda, libhmg), Cint, (Ptr{Cvoid}, Float64), base.grid.ctx, ops[k].λ))
+    sync_operator!(base.grid, ops[k])
     check(ccall((:hmg_vcycle, libhmg), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}), base.grid.ctx, k, steps, C_NULL))
     nothing
 end

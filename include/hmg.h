@@ -117,7 +117,10 @@ int hmg_set_coarse_matrix(hmg_ctx* ctx, int64_t n_interior, const int64_t* colpt
                           const int64_t* rowval, const double* nzval,
                           const int64_t* interior_nodes);
 /* or: assemble_checkerboard(base, sigma, lambda)[interior, interior] + list_interior_nodes
- * inside the library (src/examples/homogenized_coefficients.jl:358-402, src/grid.jl:176-202) */
+ * inside the library (src/examples/homogenized_coefficients.jl:358-402, src/grid.jl:176-202).
+ * Size ceiling of both: the inverse is DENSE on GPU 0, 8 n^2 bytes for n interior base nodes (twice that while it is
+ * factorised), next to the state vectors: n = 29 791 (C4) takes 7 GB, n = 65 025 (C2 at 256^2 cells) 34 GB; the call
+ * fails with a message when the device memory left does not suffice. */
 int hmg_assemble_coarse(hmg_ctx* ctx);
 /* copy_to_base!(u, v, implicit) / distribute!(v, u, implicit) on level 1
  * (src/implicit_fine_grid.jl:148-202); u has nn entries (host) */
@@ -126,9 +129,16 @@ int hmg_distribute(hmg_ctx* ctx, int which, const double* u_host);
 
 /* vcycle!(implicit, base, ops, levels, k, steps) (src/multigrid.jl:73-119).  Levels below
  * `top_level` use 2 smoothing steps (the reference does not forward `steps`, :109).
- * out_resnorm (may be NULL): norm(zero_out_all_but_one!(copy of r_top)) -- the logged residual of
- * src/examples/homogenized_coefficients.jl:286-287; r itself is left untouched when
- * keep_r != 0, else zeroed like the reference does. */
+ * out_resnorm (may be NULL): norm(zero_out_all_but_one!(r_top)) -- the logged residual of
+ * src/examples/homogenized_coefficients.jl:286-287.  With out_resnorm != NULL r_top is zeroed all-but-one IN PLACE, as
+ * the reference's driver does; with out_resnorm == NULL it is left as the CG recurrence left it.
+ * After the call x_top and r_top are the reference's; everything else (p, Ap on every level; x, b, r below the top) is
+ * scratch: where nothing reads them, the r-update, rho', the interface sum of Ap and Ap itself of the LAST CG step of a
+ * smoothing call are not computed (before the restriction local_residual! recomputes r; below the top nobody reads r).
+ * x is bit-identical either way.
+ * If lambda or sigma changed since the coarse matrix was factorised (hmg_set_lambda / hmg_set_sigma), a matrix from
+ * hmg_assemble_coarse is re-assembled and re-factorised first; one from hmg_set_coarse_matrix makes the call fail
+ * (the caller owns that matrix). */
 int hmg_vcycle(hmg_ctx* ctx, int top_level, int steps, double* out_resnorm);
 /* `ncycles` V-cycles back to back without host synchronisation (benchmark / batch use);
  * resnorms[ncycles] may be NULL. */
@@ -164,7 +174,9 @@ int hmg_synchronize(hmg_ctx* ctx);
 int hmg_time_op(hmg_ctx* ctx, int op, int level, int steps, int reps, float* ms_out);
 /* number of kernel launches issued on the context's stream since creation */
 int64_t hmg_launch_count(const hmg_ctx* ctx);
-/* raw device pointer of a state vector (element-interleaved, lattice row order; see hmg_group_width) */
+/* raw device pointer of a state vector (element-interleaved, lattice row order; see hmg_group_width).  The pointer of
+ * HMG_P is invalidated by every hmg_smoothing_steps / hmg_vcycle(s) call (the fused direction update swaps the p buffer
+ * with an internal one): fetch it again after such a call. */
 void* hmg_device_ptr(hmg_ctx* ctx, int level, int which);
 /* permutation: lattice position (0-based) of hierarchical row i (0-based) at `level` */
 int hmg_hier_to_lattice(const hmg_ctx* ctx, int level, int32_t* out);

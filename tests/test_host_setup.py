@@ -167,36 +167,6 @@ def test_interface_pairing_matches_local_numbering(dim, nlevels):
                 assert rows == [expect[q] for q in perm]
 
 
-def test_line_ordered_face_enumeration_keeps_the_pairing():
-    """HMG_FACE_ORDER=1 (an untimed experiment for the interface kernel: face nodes enumerated along lattice lines)
-    is read when the reference element is built, so it is exercised in a child process: the pairing test above must
-    hold unchanged, and the nodes of the reference faces y = 0 and x = 0 must come out as runs of consecutive rows."""
-    import os
-    import subprocess
-    import sys
-    env = dict(os.environ, HMG_FACE_ORDER="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
-                        "test_interface_pairing_matches_local_numbering"], env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:]
-    code = (
-        "import sys, ctypes as C, numpy as np\n"
-        f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
-        "import hmgb200 as hmg\n"
-        "lib = hmg.load(); L = hmg._lib\n"
-        "nl = 5; m = 16\n"
-        "h2l = np.zeros(969, np.int32); sizes = (C.c_int64 * 8)()\n"
-        "L.check_host(lib.hmg_host_reference(3, nl, nl, sizes, h2l.ctypes.data_as(C.c_void_p), None, None))\n"
-        "for lid in (1, 2):\n"
-        "    n = C.c_int64(); rows = np.zeros(105, np.int32)\n"
-        "    L.check_host(lib.hmg_host_interface_rows(3, nl, nl, 0, lid, rows.ctypes.data_as(C.c_void_p), C.byref(n)))\n"
-        "    lat = h2l[rows[:n.value]]\n"
-        "    steps = np.diff(lat)\n"
-        "    assert n.value == 105 and np.count_nonzero(steps == 1) == 105 - 14, (lid, steps)\n"
-        "print('ok')\n")
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
-
-
 def _meshes():
     out = []
     b = refine_uniformly(cube5_mesh(), times=2)
