@@ -7,7 +7,7 @@ LIB       ?= $(PKG)/libhmg_b200.so
 BUILD     ?= build
 NVFLAGS   := $(HMG_EXTRA) -DHMG_NVTX=1 -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
              -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude -diag-suppress 20014
-SRCS      := $(CSRC)/api.cu $(CSRC)/kernels.cu $(CSRC)/reference.cpp $(CSRC)/topology.cpp $(CSRC)/introspect.cpp
+SRCS      := $(CSRC)/api.cu $(CSRC)/kernels.cu $(CSRC)/field.cu $(CSRC)/reference.cpp $(CSRC)/topology.cpp $(CSRC)/introspect.cpp
 HDRS      := include/hmg.h $(CSRC)/hmg_host.hpp $(CSRC)/kernels.cuh $(CSRC)/lattice.hpp $(CSRC)/apply_core.cuh
 OBJS      := $(patsubst $(CSRC)/%,$(BUILD)/%.o,$(SRCS))
 

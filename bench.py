@@ -322,6 +322,7 @@ def measure(w, args, torch, hmg, dist, rank, world, device, steps, warmup, with_
                    "field": "checkerboard sigma in {1,9} per axis, seed 1", "lambda": 1.0,
                    "l2": f"inputs larger than L2 ({8 * dofs_local / 1e6:.0f} MB per vector per GPU vs 126 MB)",
                    "partition": "spatial blocks of whole cells, strong scaling" if world > 1 else "single GPU",
+                   "comm": g.comm_mode(),
                    "coarse_solver_setup_s": t_setup},
         "ax": {"value": dofs_total / (ms_ax * 1e-3) / 1e9, "unit": "GDOF/s", "ms": ms_ax,
                "what": "Ap = broadcast(constraint(A p)) on the finest level, 16 B per stored DOF",

@@ -25,6 +25,7 @@ PROTOTYPES = {
     "hmg_ne_local": (_i64, [_p]),
     "hmg_ld": (_i64, [_p, _i32]),
     "hmg_group_width": (_i32, [_p]),
+    "hmg_comm_mode": (_i32, [_p]),
     "hmg_local_elements": (_i32, [_p, _p]),
     "hmg_set_lambda": (_i32, [_p, _f64]),
     "hmg_set_sigma": (_i32, [_p, _p]),
@@ -56,6 +57,7 @@ PROTOTYPES = {
     "hmg_integrate_terms": (_i32, [_p, _i32, _i32, _i64, _pd]),
     "hmg_integrate_area": (_i32, [_p, _i64, _pd]),
     "hmg_next_rhs": (_i32, [_p, _i32, _i32]),
+    "hmg_generate_field": (_i32, [_i32, _p, C.c_uint64, _f64, _f64, _i32, _p, _p, _i32]),
     "hmg_refined_mesh": (_i32, [_p, _i32, _p, _p, C.POINTER(_i64)]),
     "hmg_synchronize": (_i32, [_p]),
     "hmg_time_op": (_i32, [_p, _i32, _i32, _i32, _i32, C.POINTER(C.c_float)]),

@@ -187,6 +187,10 @@ class ImplicitFineGrid:
         check(self.lib.hmg_local_elements(self.ctx, out.ctypes.data_as(C.c_void_p)))
         return out - 1
 
+    def comm_mode(self):
+        """'single', 'nccl' or 'peer' (hmg_comm_mode): how the ranks of a partitioned context exchange data."""
+        return {0: "single", 1: "nccl", 2: "peer"}[int(self.lib.hmg_comm_mode(self.ctx))]
+
     def set_lambda(self, lam):
         """operator.λ = λ (src/examples/homogenized_coefficients.jl:331)."""
         check(self.lib.hmg_set_lambda(self.ctx, float(lam)))

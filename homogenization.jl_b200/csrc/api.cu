@@ -72,6 +72,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -98,6 +99,7 @@ const NcclApi& nccl() {
     api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
     api.Reduce = reinterpret_cast<decltype(api.Reduce)>(sym("ncclReduce"));
     api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
     api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
@@ -150,6 +152,14 @@ struct hmg_ctx {
     std::vector<std::vector<int64_t>> msg_off, msg_len;   // [level][neighbour]
     std::vector<int64_t*> kbase;         // per level, device: [nranks * 3] first entry of a kind's section
     double *p2p_send = nullptr, *p2p_recv = nullptr;
+    // peer memory (NVLink, CUDA IPC): scalar all-reduces inside the reduction kernels and the cut exchange without a
+    // collective call.  peer_on is agreed on by all ranks at creation (HMG_PEER=0 or a failed mapping: NCCL path).
+    bool peer_on = false;
+    // the two-owner part of the interface sum of Ap inside the CG update (HMG_CG_PAIRS=0: as its own pass)
+    bool cg_pairs = true;
+    void* peer_buf = nullptr;                    // this rank's communication buffer (exported)
+    std::vector<void*> peer_mapped;              // the other ranks' buffers as mapped here (nullptr for the own rank)
+    std::vector<CutPeer> cut_peer;               // per level
     uint8_t* node_contrib = nullptr;
     // driver functionals (finest level)
     double* dphi = nullptr;              // [nf][dim]
@@ -192,6 +202,7 @@ struct hmg_ctx {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         if (copy_stream) cudaStreamSynchronize(copy_stream);
+        if (peer_on) peer_teardown();
         if (comm) nccl_destroy(comm);
         for (void* p : allocs) cudaFree(p);
         for (int q = 0; q < 2; ++q) {
@@ -203,6 +214,7 @@ struct hmg_ctx {
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
     }
+    void peer_teardown();
     template <class T> T* dalloc(size_t n, bool zero = true) {
         void* p = nullptr;
         if (n == 0) n = 1;
@@ -242,7 +254,27 @@ struct hmg_ctx {
     int64_t cut_slots(int l) { return cut_base(l, 2) + cut_nglobal[2]; }
 };
 
+// collective: nobody unmaps or frees a buffer a peer may still touch
+void hmg_ctx::peer_teardown() {
+    int* d = nullptr;
+    auto barrier = [&]() {
+        if (!comm || !d) return;
+        nccl().AllReduce(d, d, 1, ncclInt, ncclSum, comm, stream);
+        cudaStreamSynchronize(stream);
+    };
+    if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) d = nullptr;
+    if (d) cudaMemsetAsync(d, 0, sizeof(int), stream);
+    barrier();
+    for (void*& m : peer_mapped) if (m) { cudaIpcCloseMemHandle(m); m = nullptr; }
+    barrier();
+    if (peer_buf) { cudaFree(peer_buf); peer_buf = nullptr; }
+    if (d) cudaFree(d);
+    peer_on = false;
+}
+
 namespace {
+
+void peer_setup(hmg_ctx* c, int64_t max_msg);
 
 void check_launch(hmg_ctx* c, int n) {
     c->launches += n;
@@ -263,6 +295,116 @@ void upload_operator(hmg_ctx* c, const double* sigma /* dim x ne_global */) {
     if (!c->elem_coef) c->elem_coef = c->dalloc<double>(inter.size(), false);
     CUDA_OK(cudaMemcpyAsync(c->elem_coef, inter.data(), inter.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
+}
+
+// Collective over the ranks of the context: agree on the size of the receive areas, allocate and export the own
+// communication buffer, map everybody else's (CUDA IPC; the devices reach each other over NVLink), exchange the
+// message layouts.  Any rank that cannot do it makes ALL ranks keep the NCCL path (the decision is all-reduced).
+void peer_setup(hmg_ctx* c, int64_t max_msg) {
+    const int nr = c->nranks, nl = c->nlevels;
+    const char* env = getenv("HMG_PEER");
+    int ok = !(env && atoi(env) == 0) && nr <= 32;
+    // 1. sizes and layouts: max message length, and every rank's kbase table of every level
+    std::vector<int64_t> mine((size_t)1 + (size_t)nl * nr * 3, 0), all((size_t)nr * mine.size(), 0);
+    mine[0] = max_msg;
+    for (int l = 0; l < nl; ++l)
+        CUDA_OK(cudaMemcpyAsync(&mine[1 + (size_t)l * nr * 3], c->kbase[l], (size_t)nr * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    int64_t* d_mine = c->dupload(mine);
+    int64_t* d_all = c->dalloc<int64_t>(all.size());
+    NCCL_OK(nccl().AllGather(d_mine, d_all, mine.size() * sizeof(int64_t), ncclChar, c->comm, c->stream));
+    CUDA_OK(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    int64_t stride = 1;
+    for (int q = 0; q < nr; ++q) stride = std::max(stride, all[(size_t)q * mine.size()]);
+    stride = (stride + 15) / 16 * 16;
+    // 2. the own buffer: [mail PEER_SLOTS x nr][flags nr][ticket, counters][recv 2 x stride]
+    const size_t mail_bytes = (size_t)PEER_SLOTS * nr * sizeof(PeerMail);
+    const size_t flag_bytes = ((size_t)nr * sizeof(unsigned long long) + 127) / 128 * 128;
+    const size_t ctr_bytes = 128;
+    const size_t recv_off = (mail_bytes + flag_bytes + ctr_bytes + 255) / 256 * 256;
+    const size_t total = recv_off + (size_t)2 * stride * sizeof(double);
+    cudaIpcMemHandle_t handle;
+    std::memset(&handle, 0, sizeof(handle));
+    if (ok) {
+        if (cudaMalloc(&c->peer_buf, total) != cudaSuccess) { cudaGetLastError(); c->peer_buf = nullptr; ok = 0; }
+    }
+    if (ok) {
+        CUDA_OK(cudaMemsetAsync(c->peer_buf, 0, total, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        if (cudaIpcGetMemHandle(&handle, c->peer_buf) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    }
+    // 3. everybody's handle, then the mapping
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    std::vector<char> hmine(64 + 8, 0), hall((size_t)nr * hmine.size(), 0);
+    std::memcpy(hmine.data(), &handle, 64);
+    hmine[64] = (char)ok;
+    char* d_hm = c->dupload(hmine);
+    char* d_ha = c->dalloc<char>(hall.size());
+    NCCL_OK(nccl().AllGather(d_hm, d_ha, hmine.size(), ncclChar, c->comm, c->stream));
+    CUDA_OK(cudaMemcpyAsync(hall.data(), d_ha, hall.size(), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    for (int q = 0; q < nr; ++q) ok = ok && hall[(size_t)q * hmine.size() + 64];
+    c->peer_mapped.assign(nr, nullptr);
+    if (ok) {
+        for (int q = 0; q < nr && ok; ++q) {
+            if (q == c->rank) continue;
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, &hall[(size_t)q * hmine.size()], 64);
+            if (cudaIpcOpenMemHandle(&c->peer_mapped[q], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                c->peer_mapped[q] = nullptr;
+                ok = 0;
+            }
+        }
+    }
+    // 4. the decision is collective: one rank without the mapping and everybody stays on NCCL
+    int* d_ok = c->dupload(std::vector<int>(1, ok));
+    NCCL_OK(nccl().AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c->comm, c->stream));
+    CUDA_OK(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->dfree(d_mine); c->dfree(d_all); c->dfree(d_hm); c->dfree(d_ha); c->dfree(d_ok);
+    if (!ok) {
+        for (void*& m : c->peer_mapped) if (m) { cudaIpcCloseMemHandle(m); m = nullptr; }
+        if (c->peer_buf) { cudaFree(c->peer_buf); c->peer_buf = nullptr; }
+        if (getenv("HMG_DEBUG_CFG")) fprintf(stderr, "hmg: rank %d: peer memory off, NCCL path\n", c->rank);
+        return;
+    }
+    // 5. device views
+    std::vector<PeerMail*> mail(nr);
+    std::vector<unsigned long long*> flag(nr);
+    std::vector<double*> recv(nr);
+    for (int q = 0; q < nr; ++q) {
+        char* base = static_cast<char*>(q == c->rank ? c->peer_buf : c->peer_mapped[q]);
+        mail[q] = reinterpret_cast<PeerMail*>(base);
+        flag[q] = reinterpret_cast<unsigned long long*>(base + mail_bytes);
+        recv[q] = reinterpret_cast<double*>(base + recv_off);
+    }
+    char* own = static_cast<char*>(c->peer_buf);
+    PeerView& P = c->red.peer;
+    P.rank = c->rank; P.nranks = nr;
+    P.mail = c->dupload(mail);
+    P.flag = c->dupload(flag);
+    P.recv = c->dupload(recv);
+    P.recv_stride = stride;
+    P.rseq = reinterpret_cast<unsigned long long*>(own + mail_bytes + flag_bytes);
+    P.xseq = P.rseq + 1;
+    P.xticket = reinterpret_cast<unsigned int*>(P.rseq + 2);
+    std::vector<int32_t> nbr(c->neighbors.begin(), c->neighbors.end());
+    const int32_t* d_nbr = c->dupload(nbr);
+    c->cut_peer.resize(nl);
+    for (int l = 0; l < nl; ++l) {
+        // where section `kind` of MY message starts inside the receive area of rank q: q's own table entry for me
+        std::vector<int64_t> rb((size_t)nr * 3, 0);
+        for (int q = 0; q < nr; ++q)
+            for (int kind = 0; kind < 3; ++kind)
+                rb[(size_t)q * 3 + kind] = all[(size_t)q * mine.size() + 1 + ((size_t)l * nr + c->rank) * 3 + kind];
+        c->cut_peer[l].rbase = c->dupload(rb);
+        c->cut_peer[l].nbr = d_nbr;
+        c->cut_peer[l].nnbr = (int)nbr.size();
+    }
+    c->peer_on = true;
+    if (getenv("HMG_DEBUG_CFG")) fprintf(stderr, "hmg: rank %d: peer memory on (%d neighbours, receive areas 2 x %lld doubles)\n", c->rank, (int)nbr.size(), (long long)stride);
 }
 
 hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const double* base_nodes,
@@ -287,6 +429,7 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const 
     c->ne_global = ne_global;
     c->nn = nn;
     c->lambda = lambda;
+    if (const char* v = getenv("HMG_CG_PAIRS")) c->cg_pairs = atoi(v) != 0;
     CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreate(&c->ev0));
     CUDA_OK(cudaEventCreate(&c->ev1));
@@ -333,6 +476,15 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const 
         V.boundary = c->dupload(R.boundary);
         V.G = c->dupload(R.G);
         V.iface_idx = c->dupload(R.iface_idx);
+        {
+            // inverse of the two-owner part of iface_idx (3D: the 4 faces, 2D: the 3 edges): node -> (local cell, position)
+            const int ncell = dim == 3 ? 4 : 3, npc = dim == 3 ? V.npf : V.npe;
+            std::vector<uint16_t> pi((size_t)R.nf, 0xFFFFu);
+            HMG_CHECK(npc < (1 << 14), "too many nodes per two-owner cell for the pair table");
+            for (int f = 0; f < ncell; ++f)
+                for (int k = 0; k < npc; ++k) pi[R.iface_idx[(size_t)f * npc + k]] = (uint16_t)((f << 14) | k);
+            V.pairinfo = c->dupload(pi);
+        }
         V.interp_tab = c->dupload(R.interp_tab);
         V.restrict_tab = c->dupload(R.restrict_tab);
         for (int v = 0; v < 4; ++v) V.vpos[v] = v < nv ? R.hier2lat[v] : 0;
@@ -416,6 +568,7 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const 
         }
         c->p2p_send = c->dalloc<double>((size_t)max_msg);
         c->p2p_recv = c->dalloc<double>((size_t)max_msg);
+        peer_setup(c.get(), max_msg);
     }
     {
         std::vector<uint16_t> cm((size_t)c->nunits * c->W, 0);
@@ -473,8 +626,16 @@ void do_apply(hmg_ctx* c, int l, int mode, double alpha, const double* x, double
 // cut cells: only interface partial sums move (NCCL over NVLink).  Every rank sends the partial sum of a cut node to
 // the ranks that share it (grouped ncclSend / ncclRecv with its <= 7 neighbours in a block partition) and adds the
 // partial sums in ascending rank order.  sq: also add owners x total^2 to S_TMP.
-void do_cut_exchange_impl(hmg_ctx* c, int l, double* x, bool sq) {
+void do_cut_exchange_impl(hmg_ctx* c, int l, double* x, bool sq, int sq_post = POST_ADD) {
     const LevelView& V = c->level(l).view;
+    if (c->peer_on) {
+        // peer memory: the pack kernel stores into the neighbours' receive areas and raises their flags, the unpack
+        // kernel waits for the neighbours' flags -- two launches, no collective call
+        const CutPeer* cp = &c->cut_peer[l - 1];
+        check_launch(c, launch_cut_p2p(c->dim, CUT_PACK, V, c->cutv, c->kbase[l - 1], x, nullptr, false, c->red, c->stream, cp));
+        check_launch(c, launch_cut_p2p(c->dim, CUT_UNPACK, V, c->cutv, c->kbase[l - 1], x, nullptr, sq, c->red, c->stream, cp, sq_post));
+        return;
+    }
     const std::vector<int64_t>& off = c->msg_off[l - 1];
     const std::vector<int64_t>& len = c->msg_len[l - 1];
     check_launch(c, launch_cut_p2p(c->dim, CUT_PACK, V, c->cutv, c->kbase[l - 1], x, c->p2p_send, false, c->red, c->stream));
@@ -485,15 +646,17 @@ void do_cut_exchange_impl(hmg_ctx* c, int l, double* x, bool sq) {
         NCCL_OK(nccl().Recv(c->p2p_recv + off[q], (size_t)len[q], ncclDouble, c->neighbors[q], c->comm, c->stream));
     }
     NCCL_OK(nccl().GroupEnd());
-    check_launch(c, launch_cut_p2p(c->dim, CUT_UNPACK, V, c->cutv, c->kbase[l - 1], x, c->p2p_recv, sq, c->red, c->stream));
+    check_launch(c, launch_cut_p2p(c->dim, CUT_UNPACK, V, c->cutv, c->kbase[l - 1], x, c->p2p_recv, sq, c->red, c->stream, nullptr, sq_post));
 }
 void do_cut_exchange(hmg_ctx* c, int l, double* x) {
     const int64_t slots = c->cut_slots(l);
     if (c->nranks == 1 || slots == 0) return;
     do_cut_exchange_impl(c, l, x, false);
 }
-void do_broadcast(hmg_ctx* c, int l, double* x) {
-    check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->stream));
+// part: 3 = every shared cell; 2 = only the cells with more than two owners (the two-owner cells are summed on the fly
+// by the CG update that follows) -- the cut cells are exchanged either way
+void do_broadcast(hmg_ctx* c, int l, double* x, int part = 3) {
+    check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->stream, part));
     do_cut_exchange(c, l, x);
 }
 void do_zero_all_but_one(hmg_ctx* c, int l, double* x) {
@@ -506,9 +669,19 @@ void do_zero_all_but_one(hmg_ctx* c, int l, double* x) {
 // post-op of a reduction kernel: on one GPU the kernel's last block derives the CG scalars itself; with
 // several ranks the kernel stores the local sum in S_TMP, the sums are all-reduced and a one-thread
 // kernel derives the scalars
-int kernel_post(hmg_ctx* c, int post) { return c->nranks > 1 ? (int)POST_STORE : post; }
-void finish_reduction(hmg_ctx* c, int post, int slot) {
+// Several ranks: with peer memory the kernel itself sums over the ranks (POST_GLOBAL) and nothing is left to do; on the
+// NCCL path the kernel stores the local sum in S_TMP, the sums are all-reduced and a one-thread kernel derives the scalars
+int kernel_post(hmg_ctx* c, int post) {
+    if (c->nranks == 1) return post;
+    return c->peer_on ? (post | POST_GLOBAL) : (int)POST_STORE;
+}
+// in_kernel = false: the reduction kernel does not know about ranks (it stored its local sum in S_TMP)
+void finish_reduction(hmg_ctx* c, int post, int slot, bool in_kernel = true) {
     if (c->nranks == 1) return;
+    if (c->peer_on) {
+        if (!in_kernel) check_launch(c, launch_scalar_post(c->red, post | POST_GLOBAL, slot, c->stream));
+        return;
+    }
     NCCL_OK(nccl().AllReduce(c->red.scalars + S_TMP, c->red.scalars + S_TMP, 1, ncclDouble, ncclSum, c->comm, c->stream));
     check_launch(c, launch_scalar_post(c->red, post, slot, c->stream));
 }
@@ -518,7 +691,7 @@ void do_local_residual(hmg_ctx* c, int l) {
 // y = broadcast(constraint(A x)); with dot_post >= 0 the apply kernel also reduces
 // sum_entries owners(entry) * x * y_local = dot(x, y) over all stored entries (x consistent across owners).
 // dot_only: nothing but that reduction is wanted -- y is neither stored nor interface-summed.
-void do_global_product(hmg_ctx* c, int l, const double* x, double* y, int dot_post = -1, bool dot_only = false) {
+void do_global_product(hmg_ctx* c, int l, const double* x, double* y, int dot_post = -1, bool dot_only = false, int part = 3) {
     LevelDev& L = c->level(l);
     ApplyArgs a;
     a.L = L.view; a.cfg = L.cfg; a.cfg_fused = L.cfg_fused; a.cfg_rhs = L.cfg_rhs;
@@ -532,7 +705,7 @@ void do_global_product(hmg_ctx* c, int l, const double* x, double* y, int dot_po
     HMG_CHECK(n >= 0, "apply kernel refused the launch configuration");
     check_launch(c, n);
     if (dot_post >= 0) finish_reduction(c, dot_post, S_TMP);
-    if (!dot_only) do_broadcast(c, l, y);                            // interface sums
+    if (!dot_only) do_broadcast(c, l, y, part);                      // interface sums
 }
 // r = broadcast(r) and rho = dot(r, r) over all stored entries without a pass over r: the residual apply
 // left the interior part in S_TMP; the interface kernels add (owners x sum^2) of every shared node
@@ -546,13 +719,19 @@ void do_broadcast_rho(hmg_ctx* c, int l, double* r) {
     }
     check_launch(c, launch_interface_sum_sq(c->dim, V, c->tview, r, c->red, POST_ADD, c->stream));
     const int64_t slots = c->cut_slots(l);
+    if (c->peer_on) {
+        // the last kernel of the chain adds its part to S_TMP, sums over the ranks and sets rho
+        if (slots > 0) do_cut_exchange_impl(c, l, r, true, POST_RHO_ADD | POST_GLOBAL);
+        else check_launch(c, launch_scalar_post(c->red, POST_RHO | POST_GLOBAL, 0, c->stream));
+        return;
+    }
     if (slots > 0) do_cut_exchange_impl(c, l, r, true);
     finish_reduction(c, POST_RHO, S_TMP);
 }
 // p' = r + beta p and Ap = broadcast(constraint(A p')) with p' applied straight out of shared memory: the new
 // direction goes to the level's second p buffer (other CTAs still read the old one), then the buffers swap.
 // dot_only: p' and p'.Ap only (Ap is neither stored nor summed).
-void do_fused_direction_product(hmg_ctx* c, int l, bool dot_only = false) {
+void do_fused_direction_product(hmg_ctx* c, int l, bool dot_only = false, int part = 3) {
     LevelDev& L = c->level(l);
     if (!L.p2) L.p2 = c->dalloc<double>((size_t)c->nstored(l));
     ApplyArgs a;
@@ -569,7 +748,7 @@ void do_fused_direction_product(hmg_ctx* c, int l, bool dot_only = false) {
     check_launch(c, n);
     std::swap(L.vec[HMG_P], L.p2);
     finish_reduction(c, POST_PAP, S_TMP);
-    if (!dot_only) do_broadcast(c, l, c->vecp(l, HMG_AP));
+    if (!dot_only) do_broadcast(c, l, c->vecp(l, HMG_AP), part);
 }
 // smoothing_steps! (src/multigrid.jl:46-71).  need_r = false (inside a V-cycle, wherever nothing reads the residual of
 // the last step: before the restriction -- local_residual! recomputes r -- and after the correction on every level
@@ -589,18 +768,25 @@ void do_smoothing(hmg_ctx* c, int l, int steps, bool need_r = true) {
         const bool x_only = !need_r && i == steps - 1;
         // Ap = broadcast(constraint(A p)), alpha = rho / p.Ap; after the first step the direction update
         // p = r + beta p (src/multigrid.jl:68) happens inside the product
+        // (Ap is only read by the update below: with cg_pairs its two-owner cells stay un-summed in memory and the
+        // update adds the partner's copy on the fly)
         const double* dir = p;
-        if (i == 0) { do_global_product(c, l, r, Ap, POST_PAP, x_only); dir = r; }
-        else if (fuse) { do_fused_direction_product(c, l, x_only); p = c->vecp(l, HMG_P); dir = p; }
+        const int part = c->cg_pairs ? 2 : 3;
+        if (i == 0) { do_global_product(c, l, r, Ap, POST_PAP, x_only, part); dir = r; }
+        else if (fuse) { do_fused_direction_product(c, l, x_only, part); p = c->vecp(l, HMG_P); dir = p; }
         else {
             check_launch(c, launch_p_update(c->red, p, r, n, c->stream));
-            do_global_product(c, l, p, Ap, POST_PAP, x_only);
+            do_global_product(c, l, p, Ap, POST_PAP, x_only, part);
         }
         if (x_only) {
             check_launch(c, launch_x_update(c->red, x, dir, n, c->stream));
             break;
         }
-        check_launch(c, launch_cg_update(c->red, x, p, r, Ap, n, kernel_post(c, POST_RSQR), i == 0, c->stream));
+        if (c->cg_pairs)
+            check_launch(c, launch_cg_update_pairs(c->dim, c->red, c->level(l).view, c->tview, c->nunits, x, p, r, Ap,
+                                                   kernel_post(c, POST_RSQR), i == 0, c->stream));
+        else
+            check_launch(c, launch_cg_update(c->red, x, p, r, Ap, n, kernel_post(c, POST_RSQR), i == 0, c->stream));
         finish_reduction(c, POST_RSQR, S_TMP);
         // the reference also updates p after the last step, but that value is never used
         // (the next smoothing call starts from a fresh residual)
@@ -826,6 +1012,8 @@ void assemble_coarse_impl(hmg_ctx* c) {
 
 }  // namespace
 
+namespace hmg { void set_last_error(const std::string& msg) { g_err = msg; } }   // field.cu
+
 #define HMG_API_BEGIN try {
 #define HMG_API_END                                  \
     return 0;                                        \
@@ -889,6 +1077,7 @@ int64_t hmg_ld(const hmg_ctx* c, int level) {
     return c->lv[level - 1].view.nf;
 }
 int hmg_group_width(const hmg_ctx* c) { return c ? c->W : -1; }
+int hmg_comm_mode(const hmg_ctx* c) { return !c ? -1 : (c->nranks == 1 ? 0 : (c->peer_on ? 2 : 1)); }
 int hmg_local_elements(const hmg_ctx* c, int64_t* out) {
     HMG_API_BEGIN
     NEED_CTX(c);
@@ -1049,7 +1238,7 @@ int hmg_dot(hmg_ctx* c, int level, int a, int b, double* out) {
     HMG_API_BEGIN
     NEED_CTX(c);
     CUDA_OK(cudaSetDevice(c->device));
-    check_launch(c, launch_dot(c->red, c->vecp(level, a), c->vecp(level, b), c->nstored(level), POST_STORE, S_TMP, c->stream));
+    check_launch(c, launch_dot(c->red, c->vecp(level, a), c->vecp(level, b), c->nstored(level), kernel_post(c, POST_STORE), S_TMP, c->stream));
     finish_reduction(c, POST_STORE, S_TMP);
     *out = read_scalar(c, S_TMP);
     HMG_API_END
@@ -1183,7 +1372,7 @@ static void vcycle_with_norm(hmg_ctx* c, int top, int steps, bool want_norm, int
     if (want_norm) {
         double* r = c->vecp(top, HMG_R);
         do_zero_all_but_one(c, top, r);
-        check_launch(c, launch_dot(c->red, r, r, c->nstored(top), POST_STORE, S_TMP, c->stream));
+        check_launch(c, launch_dot(c->red, r, r, c->nstored(top), kernel_post(c, POST_STORE), S_TMP, c->stream));
         finish_reduction(c, POST_STORE, S_TMP);
         CUDA_OK(cudaMemcpyAsync(c->red.scalars + slot, c->red.scalars + S_TMP, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     }
@@ -1273,7 +1462,7 @@ double integrate(hmg_ctx* c, const double* v, const double* v2, const double* fl
     mass_apply(c, c->coef_mass1, 1.0, v, Mv);
     check_launch(c, launch_integrate(c->dim, c->red, c->level(l).view, c->nunits, nsubset, c->gidx, c->elem_coef, c->dphi,
                                      flux, v, v2, Mv, c->stream));
-    finish_reduction(c, POST_STORE, S_TMP);
+    finish_reduction(c, POST_STORE, S_TMP, false);
     return read_scalar(c, S_TMP);
 }
 }  // namespace
@@ -1379,6 +1568,12 @@ int hmg_time_op(hmg_ctx* c, int op, int level, int steps, int reps, float* ms_ou
         } else if (op == 12) {
             HMG_CHECK(c->level(level).cfg_fused.ring_rows > 0, "the fused p-update does not fit this level");
             do_fused_direction_product(c, level);
+        } else if (op == 15) {
+            check_launch(c, launch_cg_update_pairs(c->dim, c->red, c->level(level).view, c->tview, c->nunits, c->vecp(level, HMG_X),
+                                                   c->vecp(level, HMG_P), c->vecp(level, HMG_R), c->vecp(level, HMG_AP), POST_RSQR,
+                                                   false, c->stream));
+        } else if (op == 16) {
+            check_launch(c, launch_x_update(c->red, c->vecp(level, HMG_X), c->vecp(level, HMG_P), c->nstored(level), c->stream));
         } else if (op == 11) {
             do_apply(c, level, APPLY_AX, 1.0, c->vecp(level, HMG_P), c->vecp(level, HMG_AP), nullptr, POST_STORE);
         } else {

@@ -64,16 +64,75 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 __device__ __forceinline__ void scalar_post(double* S, int post, int slot, double tot) {
     if (post == POST_STORE) S[slot] = tot;
-    else if (post == POST_RHO) S[S_RHO] = tot;
+    else if (post == POST_RHO || post == POST_RHO_ADD) S[S_RHO] = tot;
     else if (post == POST_PAP) { S[S_PAP] = tot; S[S_ALPHA] = S[S_RHO] / tot; }
     else if (post == POST_RSQR) { S[S_RSQR] = tot; S[S_BETA] = tot / S[S_RHO]; S[S_RHO] = tot; }
     else if (post == POST_ADD) S[slot] += tot;
-    else if (post == POST_RHO_ADD) S[S_RHO] = S[S_TMP] + tot;
+}
+// what a reduction kernel contributes to the post-op: its own total, plus what earlier kernels of the chain left in S_TMP
+__device__ __forceinline__ double scalar_pre(const double* S, int post, double tot) {
+    return post == POST_RHO_ADD ? S[S_TMP] + tot : tot;
 }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// ---- peer memory (NVLink): system-scope stores / loads and the in-kernel all-reduce of one double --------------------
+__device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// a peer that never answers (a rank that died) must not hang the GPU: ~10 s of spinning, then the kernel traps and the
+// host sees a launch failure
+constexpr long long PEER_TIMEOUT_CYCLES = 20000000000ll;
+__device__ __forceinline__ void peer_wait_ge(const unsigned long long* p, unsigned long long want) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) < want) {
+        if (clock64() - t0 > PEER_TIMEOUT_CYCLES) {
+            printf("hmg: rank timed out waiting for a peer (sequence %llu)\n", want);
+            __trap();
+        }
+        __nanosleep(20);
+    }
+}
+// Sum of `local` over all ranks, added in rank order (every rank gets the same bits).  Called by ALL threads of one
+// block per rank (the last block of a reduction kernel), which needs at least nranks threads.  Thread q stores the
+// rank's value into the mailbox of rank q (value, then the sequence number with release semantics) and waits for
+// rank q's value in its own mailbox; mailboxes are a ring of PEER_SLOTS sequence numbers (a rank is never more than
+// one reduction ahead of a peer: it needs the peer's value of reduction s to finish s).
+__device__ __forceinline__ double peer_allreduce(const PeerView& P, double local) {
+    __shared__ double vals[32];
+    const unsigned long long s = *P.rseq + 1;
+    const int slot = (int)(s & (PEER_SLOTS - 1));
+    const int t = threadIdx.x;
+    if (t < P.nranks) {
+        PeerMail* dst = P.mail[t] + slot * P.nranks + P.rank;
+        st_relaxed_sys(&dst->value, local);
+        st_release_sys(&dst->seq, s);
+        const PeerMail* src = P.mail[P.rank] + slot * P.nranks + t;
+        peer_wait_ge(&src->seq, s);
+        vals[t] = ld_relaxed_sys(&src->value);
+    }
+    __syncthreads();
+    double g = 0.0;
+    for (int q = 0; q < P.nranks; ++q) g += vals[q];
+    __syncthreads();
+    if (t == 0) *P.rseq = s;
+    return g;
 }
 
 // deterministic: fixed grid, fixed per-block tree, partials summed in block order by the last block
@@ -101,10 +160,27 @@ __device__ __forceinline__ void block_reduce_finish(double v, const Reducer& R, 
     __syncthreads();
     if (lane == 0) wsum[wid] = s;
     __syncthreads();
+    const int op = post & 0xff;
+    if (post & POST_GLOBAL) {
+        // the sum over all ranks, inside this kernel (peer memory)
+        __shared__ double mine;
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += wsum[w];
+            mine = scalar_pre(R.scalars, op, tot);
+        }
+        __syncthreads();
+        const double g = peer_allreduce(R.peer, mine);
+        if (threadIdx.x == 0) {
+            scalar_post(R.scalars, op, slot, g);
+            *R.ticket = 0u;
+        }
+        return;
+    }
     if (threadIdx.x == 0) {
         double tot = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += wsum[w];
-        scalar_post(R.scalars, post, slot, tot);
+        scalar_post(R.scalars, op, slot, scalar_pre(R.scalars, op, tot));
         *R.ticket = 0u;
     }
 }
@@ -704,15 +780,15 @@ int launch_apply(int dim, const ApplyArgs& a, cudaStream_t st) {
 // Codimension-1 cells (3D faces, 2D edges) have exactly two owners: lanes are the elements of a
 // unit, the lower owner of a pair reads both copies, adds them in ascending owner order
 // (src/implicit_fine_grid.jl:219-244) and writes both.  Cells with more owners (3D edges, vertices):
-// a group of 8 threads per shared fine node, one owner per thread -- all owner copies are loaded at
-// once, every thread of the group adds them in ascending owner order (the same bits as the serial loop
-// of src/implicit_fine_grid.jl:262-283) and writes the sum to its own owner's copy.  OP 0: sum +
+// a group of 8 threads per cell, one owner per thread, walking the cell's shared nodes four at a time -- the owner
+// copies of a node are loaded at once, every thread of the group adds them in ascending owner order (the same bits
+// as the serial loop of src/implicit_fine_grid.jl:262-283) and writes the sum to its own owner's copy.  OP 0: sum +
 // broadcast; OP 1: zero all but the first owner (src/implicit_fine_grid.jl:334-386).
 // SQ: additionally reduce sum over the touched entries of value^2 ( = owners * sum^2 per shared node) and add it
 // to S_TMP -- the part of rho = dot(r, r) that lives on interfaces; the apply kernel reduces the interior part
 // (src/multigrid.jl:54 without a pass over r).  With SQ the grid is bounded and blocks loop over virtual blocks.
-constexpr int MULTI_G = 8;                      // threads per shared node of a multi-owner cell
-constexpr int MULTI_ITEMS = 256 / MULTI_G;      // shared nodes per virtual block
+constexpr int MULTI_G = 8;                      // threads per multi-owner cell (one owner each)
+constexpr int MULTI_ITEMS = 256 / MULTI_G;      // cells per virtual block
 template <int DIM, int OP, bool SQ>
 __global__ void __launch_bounds__(256) interface_kernel(const LevelView L, const TopoView T, int64_t npair_blocks,
                                                         int64_t vb_begin, int64_t nvirtual, double* __restrict__ x, const Reducer R,
@@ -767,10 +843,11 @@ __global__ void __launch_bounds__(256) interface_kernel(const LevelView L, const
             }
             continue;
         }
-        // multi-owner cells: MULTI_ITEMS (cell, node) items per virtual block, MULTI_G threads each
+        // multi-owner cells: MULTI_ITEMS cells per virtual block, MULTI_G threads each (thread j <-> owner j); the
+        // owner list is read once per cell, the shared nodes of the cell are walked four at a time
         const int nel = DIM == 3 ? 6 : 3, nfl = DIM == 3 ? 4 : 0;
-        const int64_t nedge_items = DIM == 3 ? T.nedges * L.npe : 0;
-        const int64_t total = nedge_items + T.nverts;
+        const int64_t nedge_cells = DIM == 3 && L.npe > 0 ? T.nedges : 0;
+        const int64_t total = nedge_cells + T.nverts;
         const int sub = threadIdx.x & (MULTI_G - 1);
         const int lane0 = (threadIdx.x & 31) & ~(MULTI_G - 1);         // first lane of the group
         const unsigned gmask = ((1u << MULTI_G) - 1u) << lane0;
@@ -780,42 +857,77 @@ __global__ void __launch_bounds__(256) interface_kernel(const LevelView L, const
         const int32_t* own;
         const uint16_t* tab;
         int64_t cell;
-        int k, npc;
-        if (t < nedge_items) {
-            cell = t / L.npe;
-            k = (int)(t - cell * L.npe);
+        int npc;
+        if (t < nedge_cells) {
+            cell = t;
             npc = L.npe;
             off = T.edge_off; own = T.edge_own;
             tab = L.iface_idx + nfl * L.npf;
         } else {
-            cell = t - nedge_items;
-            k = 0; npc = 1;
+            cell = t - nedge_cells;
+            npc = 1;
             off = T.vert_off; own = T.vert_own;
             tab = L.iface_idx + nfl * L.npf + nel * L.npe;
         }
         const int64_t b = off[cell], en = off[cell + 1];
-        auto entry = [&](int64_t o) -> double* {
+        const int n = (int)(en - b);
+        // column of owner o and its row table
+        auto column = [&](int64_t o, const uint16_t*& rows) -> double* {
             const int32_t id = __ldg(own + o);
             const int64_t el = id >> 3;
-            return x + ((el >> ws) * (int64_t)nf + __ldg(tab + (id & 7) * npc + k)) * W + (el & (W - 1));
+            rows = tab + (id & 7) * npc;
+            return x + (el >> ws) * (int64_t)nf * W + (el & (W - 1));
         };
         if (OP == 1) {
-            for (int64_t o = b + 1 + sub; o < en; o += MULTI_G) *entry(o) = 0.0;
+            for (int64_t o = b + 1 + sub; o < en; o += MULTI_G) {
+                const uint16_t* rows;
+                double* col = column(o, rows);
+                for (int k = 0; k < npc; ++k) col[(int64_t)__ldg(rows + k) * W] = 0.0;
+            }
             continue;
         }
-        double s = 0.0;
-        double* mine = nullptr;                                        // this thread's owner copy of the first round
-        for (int64_t o0 = b; o0 < en; o0 += MULTI_G) {
-            const bool have = o0 + sub < en;
-            double* ptr = have ? entry(o0 + sub) : nullptr;
-            const double v = have ? *ptr : 0.0;
-            if (o0 == b) mine = ptr;
-            const int cnt = (int)min((int64_t)MULTI_G, en - o0);       // uniform within the group
-            for (int j = 0; j < cnt; ++j) s += __shfl_sync(gmask, v, lane0 + j);
+        if (n <= MULTI_G) {
+            const bool have = sub < n;
+            const uint16_t* rows;
+            double* col = column(b + (have ? sub : 0), rows);
+            constexpr int U = 4;
+            for (int k0 = 0; k0 < npc; k0 += U) {
+                int64_t at[U];
+                double v[U];
+#pragma unroll
+                for (int q = 0; q < U; ++q) at[q] = (int64_t)__ldg(rows + min(k0 + q, npc - 1)) * W;
+#pragma unroll
+                for (int q = 0; q < U; ++q) v[q] = have ? col[at[q]] : 0.0;
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    double sum = 0.0;
+                    for (int j = 0; j < n; ++j) sum += __shfl_sync(gmask, v[q], lane0 + j);      // ascending owner order
+                    if (k0 + q < npc) {
+                        if (have) col[at[q]] = sum;
+                        if (SQ && sub == 0) sq = fma((double)n * sum, sum, sq);
+                    }
+                }
+            }
+            continue;
         }
-        if (mine) *mine = s;
-        for (int64_t o = b + MULTI_G + sub; o < en; o += MULTI_G) *entry(o) = s;      // more than MULTI_G owners: rare
-        if (SQ && sub == 0) sq = fma((double)(en - b) * s, s, sq);
+        // more owners than threads in the group (vertices of dense meshes): rounds of MULTI_G owners per node
+        for (int k = 0; k < npc; ++k) {
+            double sum = 0.0;
+            for (int64_t o0 = b; o0 < en; o0 += MULTI_G) {
+                const bool have = o0 + sub < en;
+                const uint16_t* rows;
+                double* col = column(have ? o0 + sub : b, rows);
+                const double v = have ? col[(int64_t)__ldg(rows + k) * W] : 0.0;
+                const int cnt = (int)min((int64_t)MULTI_G, en - o0);
+                for (int j = 0; j < cnt; ++j) sum += __shfl_sync(gmask, v, lane0 + j);
+            }
+            for (int64_t o = b + sub; o < en; o += MULTI_G) {
+                const uint16_t* rows;
+                double* col = column(o, rows);
+                col[(int64_t)__ldg(rows + k) * W] = sum;
+            }
+            if (SQ && sub == 0) sq = fma((double)n * sum, sum, sq);
+        }
     }
     if (SQ) block_reduce_finish(sq, R, post, S_TMP);
 }
@@ -835,7 +947,7 @@ static int launch_interface(int dim, const LevelView& L, const TopoView& T, doub
     const int npc = dim == 3 ? L.npf : L.npe;
     const int64_t nunits = (T.ne + L.W - 1) / L.W;
     const int64_t npair_blocks = npc > 0 ? nunits * (dim == 3 ? 4 : 3) : 0;
-    const int64_t multi = (dim == 3 ? T.nedges * L.npe : 0) + T.nverts;
+    const int64_t multi = (dim == 3 && L.npe > 0 ? T.nedges : 0) + T.nverts;       // cells
     const int64_t nmulti_blocks = (multi + MULTI_ITEMS - 1) / MULTI_ITEMS;
     const int64_t vb_begin = (part & 1) ? 0 : npair_blocks;
     const int64_t nvirtual = (part & 2) ? npair_blocks + nmulti_blocks : npair_blocks;
@@ -915,10 +1027,28 @@ int launch_cut(int dim, int op, const LevelView& L, const CutView* C, const int6
     return 1;
 }
 
-template <int OP, bool SQ>
+// PEER: the messages travel through peer memory instead of ncclSend / ncclRecv.  CUT_PACK stores every partial sum
+// straight into the receive area (even / odd exchange) of the rank it is meant for; when the last block is done
+// (system-scope fences, a ticket) it raises this rank's flag on every neighbour to the exchange number.  CUT_UNPACK
+// first waits until every neighbour's flag has reached the exchange number, then reads its own receive area.  Two
+// receive areas suffice: a rank packs exchange j + 2 only after it unpacked j + 1, which needed every neighbour's
+// message j + 1, which the neighbour sent after it had unpacked j.
+template <int OP, bool SQ, bool PEER>
 __global__ void __launch_bounds__(256) cut_p2p_kernel(const LevelView L, const CutAll A, const int64_t* __restrict__ kbase,
-                                                      double* __restrict__ x, double* __restrict__ msg, const Reducer R) {
+                                                      double* __restrict__ x, double* __restrict__ msg, const Reducer R,
+                                                      const CutPeer CP, int sq_post) {
     double sq = 0.0;
+    const PeerView& P = R.peer;
+    unsigned long long xs = 0;
+    const double* inbox = msg;
+    if (PEER) {
+        xs = *P.xseq + 1;
+        if (OP == CUT_UNPACK) {
+            if ((int)threadIdx.x < CP.nnbr) peer_wait_ge(P.flag[P.rank] + CP.nbr[threadIdx.x], xs);
+            __syncthreads();
+            inbox = P.recv[P.rank] + (xs & 1ull) * P.recv_stride;
+        }
+    }
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < A.items[3]; t += (int64_t)gridDim.x * blockDim.x) {
         const int kd = t < A.items[1] ? 0 : (t < A.items[2] ? 1 : 2);
         const CutView& C = A.kind[kd];
@@ -935,14 +1065,19 @@ __global__ void __launch_bounds__(256) cut_p2p_kernel(const LevelView L, const C
         }
         const int64_t pb = C.peer_off[cell], pe = C.peer_off[cell + 1];
         if (OP == CUT_PACK) {
-            for (int64_t j = pb; j < pe; ++j) msg[kbase[C.peer_rank[j] * 3 + kd] + (int64_t)C.peer_idx[j] * npc + k] = part;
+            for (int64_t j = pb; j < pe; ++j) {
+                const int pr = C.peer_rank[j];
+                if (PEER) P.recv[pr][(xs & 1ull) * P.recv_stride + CP.rbase[pr * 3 + kd] + (int64_t)C.peer_idx[j] * npc + k] = part;
+                else msg[kbase[pr * 3 + kd] + (int64_t)C.peer_idx[j] * npc + k] = part;
+            }
             continue;
         }
         const int mine = C.my_pos[cell];
         double tot = 0.0;
         for (int64_t j = pb; j < pe; ++j) {
             if ((int)(j - pb) == mine) tot += part;
-            tot += msg[kbase[C.peer_rank[j] * 3 + kd] + (int64_t)C.peer_idx[j] * npc + k];
+            const int64_t at = kbase[C.peer_rank[j] * 3 + kd] + (int64_t)C.peer_idx[j] * npc + k;
+            tot += PEER ? __ldcg(inbox + at) : inbox[at];      // peers wrote it: never from a stale L1 line
         }
         if ((int)(pe - pb) == mine) tot += part;
         for (int64_t o = b; o < en; ++o) {
@@ -952,10 +1087,30 @@ __global__ void __launch_bounds__(256) cut_p2p_kernel(const LevelView L, const C
         }
         if (SQ) sq = fma((double)(en - b) * tot, tot, sq);
     }
-    if (SQ) block_reduce_finish(sq, R, POST_ADD, S_TMP);
+    if (PEER) {
+        // the last block to finish publishes: PACK -> the flags on the neighbours, UNPACK -> the exchange counter
+        __shared__ bool last_x;
+        if (OP == CUT_PACK) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned t = atomicAdd(P.xticket, 1u);
+            last_x = (t == gridDim.x - 1);
+            if (last_x) *P.xticket = 0u;
+        }
+        __syncthreads();
+        if (last_x) {
+            if (OP == CUT_PACK) {
+                __threadfence_system();
+                if ((int)threadIdx.x < CP.nnbr) st_release_sys(P.flag[CP.nbr[threadIdx.x]] + P.rank, xs);
+            } else if (threadIdx.x == 0) {
+                *P.xseq = xs;
+            }
+        }
+    }
+    if (SQ) block_reduce_finish(sq, R, sq_post, S_TMP);
 }
 int launch_cut_p2p(int dim, int op, const LevelView& L, const CutView* C, const int64_t* kbase, double* x, double* msg, bool sq,
-                   const Reducer& R, cudaStream_t st) {
+                   const Reducer& R, cudaStream_t st, const CutPeer* peer, int sq_post) {
     const int nfl = dim == 3 ? 4 : 0, nel = dim == 3 ? 6 : 3;
     CutAll A;
     A.items[0] = 0;
@@ -967,11 +1122,19 @@ int launch_cut_p2p(int dim, int op, const LevelView& L, const CutView* C, const 
         A.items[kd + 1] = A.items[kd] + C[kd].ncells * A.npc[kd];
         if (A.npc[kd] == 0) A.npc[kd] = 1;
     }
-    if (A.items[3] == 0 && !sq) return 0;
+    // (with peer memory the kernels also run for a rank without items: the exchange is collective)
+    if (A.items[3] == 0 && !sq && !peer) return 0;
     const unsigned grid = grid_for(std::max<int64_t>(A.items[3], 1), 256, sq ? R.max_blocks : 148 * 16);
-    if (op == CUT_PACK) cut_p2p_kernel<CUT_PACK, false><<<grid, 256, 0, st>>>(L, A, kbase, x, msg, R);
-    else if (sq) cut_p2p_kernel<CUT_UNPACK, true><<<grid, 256, 0, st>>>(L, A, kbase, x, msg, R);
-    else cut_p2p_kernel<CUT_UNPACK, false><<<grid, 256, 0, st>>>(L, A, kbase, x, msg, R);
+    const CutPeer cp = peer ? *peer : CutPeer{};
+    if (peer) {
+        if (op == CUT_PACK) cut_p2p_kernel<CUT_PACK, false, true><<<grid, 256, 0, st>>>(L, A, kbase, x, msg, R, cp, sq_post);
+        else if (sq) cut_p2p_kernel<CUT_UNPACK, true, true><<<grid, 256, 0, st>>>(L, A, kbase, x, msg, R, cp, sq_post);
+        else cut_p2p_kernel<CUT_UNPACK, false, true><<<grid, 256, 0, st>>>(L, A, kbase, x, msg, R, cp, sq_post);
+        return 1;
+    }
+    if (op == CUT_PACK) cut_p2p_kernel<CUT_PACK, false, false><<<grid, 256, 0, st>>>(L, A, kbase, x, msg, R, cp, sq_post);
+    else if (sq) cut_p2p_kernel<CUT_UNPACK, true, false><<<grid, 256, 0, st>>>(L, A, kbase, x, msg, R, cp, sq_post);
+    else cut_p2p_kernel<CUT_UNPACK, false, false><<<grid, 256, 0, st>>>(L, A, kbase, x, msg, R, cp, sq_post);
     return 1;
 }
 
@@ -1051,9 +1214,16 @@ int launch_interp_add(int, const LevelView& Lf, const LevelView& Lc, int64_t nun
 // ------------------------------------------------------------------------------------------
 // K3: reductions and fused CG vector updates (scalars stay on the device)
 // ------------------------------------------------------------------------------------------
-__global__ void scalar_post_kernel(double* S, int post, int slot) { scalar_post(S, post, slot, S[S_TMP]); }
+// the post-op of a reduction whose total earlier kernels left in S_TMP; with POST_GLOBAL that total is first summed over
+// all ranks (peer memory)
+__global__ void __launch_bounds__(32) scalar_post_kernel(const Reducer R, int post, int slot) {
+    double* S = R.scalars;
+    double tot = S[S_TMP];
+    if (post & POST_GLOBAL) tot = peer_allreduce(R.peer, tot);
+    if (threadIdx.x == 0) scalar_post(S, post & 0xff, slot, tot);
+}
 int launch_scalar_post(const Reducer& R, int post, int slot, cudaStream_t st) {
-    scalar_post_kernel<<<1, 1, 0, st>>>(R.scalars, post, slot);
+    scalar_post_kernel<<<1, 32, 0, st>>>(R, post, slot);
     return 1;
 }
 
@@ -1111,6 +1281,78 @@ __global__ void __launch_bounds__(256) cg_update_kernel(const Reducer R, double*
         s = fma(rv.x, rv.x, s); s = fma(rv.y, rv.y, s);
     }
     block_reduce_finish(s, R, post, S_TMP);
+}
+
+// The same update with the pair part of the interface sum of Ap folded in (the V-cycle never needs the summed Ap as
+// a stored vector: alpha comes from the owner-weighted dot of the apply kernel, and only r -= alpha Ap reads it).
+// Lanes are the elements of a unit, a warp takes rows; on a row of a two-owner cell (3D face, 2D edge interior) every
+// lane adds its partner's local copy, ascending owner order being irrelevant for two addends (a + b == b + a bit for
+// bit, so both owners compute the same r).  Cells with more owners and cut cells were summed in place before.
+template <int DIM, bool FIRST>
+__global__ void __launch_bounds__(256) cg_update_pairs_kernel(const Reducer R, const LevelView L, const TopoView T, int64_t nunits,
+                                                              double* __restrict__ x, double* __restrict__ p, double* __restrict__ r,
+                                                              const double* __restrict__ Ap, int post) {
+    constexpr int ROWS = 32, U = 4;                     // rows per block step, rows per warp step (8 warps)
+    const double alpha = R.scalars[S_ALPHA];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nf = L.nf;
+    const int npc = DIM == 3 ? L.npf : L.npe;
+    const uint16_t* tab = L.iface_idx;
+    const int nrb = (nf + ROWS - 1) / ROWS;
+    const int64_t total = nunits * nrb;
+    double s = 0.0;
+    for (int64_t it = blockIdx.x; it < total; it += gridDim.x) {
+        const int64_t u = it / nrb;
+        const int rb = (int)(it - u * nrb);
+        const int64_t e = u * 32 + lane;
+        int4 pr = make_int4(-1, -1, -1, -1);
+        if (e < T.ne) pr = __ldg(reinterpret_cast<const int4*>(T.partner) + e);
+        const int64_t base = u * (int64_t)nf * 32 + lane;
+        int row[U];
+        double xv[U], rv[U], pv[U], qv[U], bv[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            row[q] = rb * ROWS + q * 8 + warp;
+            const bool in = row[q] < nf;
+            const int64_t at = base + (int64_t)(in ? row[q] : 0) * 32;
+            xv[q] = x[at]; rv[q] = r[at]; qv[q] = Ap[at];
+            pv[q] = FIRST ? rv[q] : p[at];
+            bv[q] = 0.0;
+            const unsigned info = in ? __ldg(L.pairinfo + row[q]) : 0xFFFFu;
+            if (info != 0xFFFFu) {
+                const int f = info >> 14, kk = info & 0x3FFF;
+                const int prt = f == 0 ? pr.x : (f == 1 ? pr.y : (f == 2 ? pr.z : pr.w));
+                if (prt >= 0) {
+                    const int64_t pe = prt >> 3;
+                    bv[q] = Ap[((pe >> 5) * (int64_t)nf + __ldg(tab + (prt & 7) * npc + kk)) * 32 + (pe & 31)];
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            if (row[q] >= nf) continue;
+            const int64_t at = base + (int64_t)row[q] * 32;
+            const double ap = qv[q] + bv[q];
+            const double xn = fma(alpha, pv[q], xv[q]);
+            const double rn = fma(-alpha, ap, rv[q]);
+            x[at] = xn; r[at] = rn;
+            if (FIRST) p[at] = rv[q];
+            s = fma(rn, rn, s);
+        }
+    }
+    block_reduce_finish(s, R, post, S_TMP);
+}
+int launch_cg_update_pairs(int dim, const Reducer& R, const LevelView& L, const TopoView& T, int64_t nunits, double* x, double* p,
+                           double* r, const double* Ap, int post, bool first, cudaStream_t st) {
+    const int nrb = (L.nf + 31) / 32;
+    const unsigned grid = (unsigned)std::min<int64_t>(nunits * nrb, R.max_blocks);
+    if (dim == 3) {
+        if (first) cg_update_pairs_kernel<3, true><<<grid, 256, 0, st>>>(R, L, T, nunits, x, p, r, Ap, post);
+        else cg_update_pairs_kernel<3, false><<<grid, 256, 0, st>>>(R, L, T, nunits, x, p, r, Ap, post);
+    } else {
+        if (first) cg_update_pairs_kernel<2, true><<<grid, 256, 0, st>>>(R, L, T, nunits, x, p, r, Ap, post);
+        else cg_update_pairs_kernel<2, false><<<grid, 256, 0, st>>>(R, L, T, nunits, x, p, r, Ap, post);
+    }
+    return 1;
 }
 
 // p = r + beta p   (src/multigrid.jl:68)

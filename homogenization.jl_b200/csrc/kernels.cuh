@@ -21,6 +21,7 @@ struct LevelView {
     const uint32_t* boundary;   // [n_boundary] p | class<<14   (sorted by class)
     const double* G;            // [ncls][ndir][nc]
     const uint16_t* iface_idx;  // paired-node packed indices: faces [4][npf], edges [6|3][npe], vertices
+    const uint16_t* pairinfo;   // [nf] two-owner cell of a node: local cell id << 14 | position in the cell's list; 0xFFFF none
     const uint32_t* interp_tab; // [nf] coarse parents pa | pb<<16 (levels >= 2)
     const uint16_t* restrict_tab; // [nf(level-1)][ndir] fine indices, 0xFFFF = outside
     int vpos[4];                // packed lattice index of the reference vertices
@@ -38,11 +39,33 @@ struct TopoView {
 enum Scalar { S_RHO = 0, S_PAP = 1, S_ALPHA = 2, S_RSQR = 3, S_BETA = 4, S_TMP = 5, S_NRM = 6, S_COUNT = 16 };
 enum PostOp { POST_STORE = 0, POST_RHO = 1, POST_PAP = 2, POST_RSQR = 3, POST_ADD = 4, POST_RHO_ADD = 5 };
 
+// ---- multi-GPU: peer memory over NVLink (one process per GPU, buffers mapped with CUDA IPC) -------------------------
+// A rank's communication buffer holds, in this order: scalar mailboxes [PEER_SLOTS][nranks] (value + sequence number),
+// exchange flags [nranks], and two receive areas (even / odd exchange) for the messages of the cut-cell exchange.
+// Every rank maps the buffers of all others; kernels store straight into a peer's buffer and spin on their own.
+struct PeerMail { double value; unsigned long long seq; };
+constexpr int PEER_SLOTS = 4;
+struct PeerView {
+    int rank = 0, nranks = 1;                 // nranks <= 1: off (single GPU, or the NCCL path)
+    PeerMail* const* mail = nullptr;          // [nranks] device pointers (peer-mapped; [rank] = the own buffer)
+    unsigned long long* const* flag = nullptr;   // [nranks] exchange flags of every rank (peer-mapped)
+    double* const* recv = nullptr;            // [nranks] receive areas of every rank (peer-mapped)
+    int64_t recv_stride = 0;                  // doubles per receive area (the same on every rank)
+    unsigned long long* rseq = nullptr;       // reductions completed on this rank (device counter)
+    unsigned long long* xseq = nullptr;       // cut-cell exchanges completed on this rank
+    unsigned int* xticket = nullptr;          // last-block-done counter of the exchange kernels
+};
+// a reduction whose post-op carries POST_GLOBAL is summed over all ranks INSIDE the kernel: the last block of every rank
+// stores its total into the mailbox of every peer, waits for the others' totals and adds them in rank order (the same
+// bits everywhere) before the post-op runs -- no collective call, no extra launch
+constexpr int POST_GLOBAL = 0x100;
+
 struct Reducer {
     double* partials;     // [max_blocks]
     double* scalars;      // [S_COUNT]
     unsigned int* ticket; // last-block-done counter (self-resetting)
     int max_blocks;
+    PeerView peer;
 };
 
 // cut cells of one kind (faces / edges / vertices) this rank takes part in (multi-GPU, hmg_host.hpp)
@@ -57,6 +80,13 @@ struct CutView {
     const int32_t* peer_rank;
     const int32_t* peer_idx;
     const int32_t* my_pos;      // peers with a smaller rank: where the own partial sum enters the ordered total
+};
+// peer-memory form of the exchange: rbase[rank * 3 + kind] = first entry of the kind's section of MY message inside the
+// receive area of `rank`; nbr[0 .. nnbr) = the ranks this rank exchanges with at all
+struct CutPeer {
+    const int64_t* rbase = nullptr;
+    const int32_t* nbr = nullptr;
+    int nnbr = 0;
 };
 enum CutOp { CUT_PACK = 0, CUT_UNPACK = 1, CUT_ZERO_BUT_FIRST = 2 };
 
@@ -116,7 +146,7 @@ int launch_cut(int dim, int op, const LevelView& L, const CutView* C, const int6
 // rank that shares it, CUT_UNPACK adds the partial sums of all sharing ranks in ascending rank order (every rank gets
 // the same bits).  kbase[rank * 3 + kind] = first entry of the kind's section in the message to / from `rank`.
 int launch_cut_p2p(int dim, int op, const LevelView& L, const CutView* C, const int64_t* kbase, double* x, double* msg, bool sq,
-                   const Reducer& R, cudaStream_t st);
+                   const Reducer& R, cudaStream_t st, const CutPeer* peer = nullptr, int sq_post = POST_ADD);
 // derived CG scalars after a cross-rank all-reduce of the raw dot product in S_TMP
 int launch_scalar_post(const Reducer& R, int post, int slot, cudaStream_t st);
 int launch_masked_copy_to_base(const LevelView& L1, int64_t nn, const int32_t* node_first, const uint8_t* contrib, const double* v,
@@ -132,6 +162,10 @@ int launch_interp_add(int dim, const LevelView& Lf, const LevelView& Lc, int64_t
 int launch_dot(const Reducer& R, const double* a, const double* b, int64_t n, int post, int slot, cudaStream_t st);
 int launch_copy_dot(const Reducer& R, const double* r, double* p, int64_t n, int post, cudaStream_t st);
 int launch_cg_update(const Reducer& R, double* x, double* p, double* r, const double* Ap, int64_t n, int post, bool first, cudaStream_t st);
+// the same update with the interface sum of the two-owner cells (3D faces, 2D edges) of Ap taken on the fly: every owner
+// adds its partner's local copy while it streams -- Ap's copies on those cells stay UN-summed in memory
+int launch_cg_update_pairs(int dim, const Reducer& R, const LevelView& L, const TopoView& T, int64_t nunits, double* x, double* p,
+                           double* r, const double* Ap, int post, bool first, cudaStream_t st);
 int launch_p_update(const Reducer& R, double* p, const double* r, int64_t n, cudaStream_t st);
 int launch_x_update(const Reducer& R, double* x, const double* p, int64_t n, cudaStream_t st);   // x += S_ALPHA * p
 int launch_axpy(double alpha, const double* x, double* y, int64_t n, cudaStream_t st);

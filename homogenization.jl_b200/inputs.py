@@ -80,6 +80,42 @@ def random_field_cells(dim, n, seed=2, alpha=1.0, p=1.5):
     return np.repeat(g[..., None], dim, axis=-1)
 
 
+def philox_normal(n, seed):
+    """The standard-normal stream of the device generator (csrc/field.cu: Philox4x32-10, key = seed, counter = cell
+    index, Box-Muller on two 53-bit uniforms), restated with numpy integer arithmetic."""
+    i = np.arange(n, dtype=np.uint64)
+    c = [(i & np.uint64(0xFFFFFFFF)), (i >> np.uint64(32)), np.zeros(n, np.uint64), np.zeros(n, np.uint64)]
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    M = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c[0]
+        p1 = np.uint64(0xCD9E8D57) * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k0, p1 & M, (p0 >> np.uint64(32)) ^ c[3] ^ k1, p0 & M]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & M
+        k1 = (k1 + np.uint64(0xBB67AE85)) & M
+    u1 = ((((c[0] << np.uint64(32)) | c[1]) >> np.uint64(11)).astype(np.float64) + 0.5) * 2.0 ** -53
+    u2 = ((((c[2] << np.uint64(32)) | c[3]) >> np.uint64(11)).astype(np.float64) + 0.5) * 2.0 ** -53
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+
+
+def random_field_cells_device(dim, n, seed=2, alpha=1.0, p=1.5, normalize=True, noise=None, device=0):
+    """The same field through the library's cuFFT generator (hmg_generate_field; tools/generate_st1_field.jl:86-120).
+    ``noise`` (shape (n,)*dim): the caller's white noise; None: drawn on the device (``philox_normal`` restates it)."""
+    import ctypes as C
+    from ._lib import load, check
+    lib = load()
+    ns = (C.c_int * 3)(*([n] * dim + [1] * (3 - dim)))
+    out = np.empty((n,) * dim, dtype=np.float64)
+    nz = None
+    if noise is not None:
+        nz = np.ascontiguousarray(noise, dtype=np.float64)
+        assert nz.shape == (n,) * dim
+    check(lib.hmg_generate_field(dim, ns, int(seed), float(alpha), float(p), int(bool(normalize)),
+                                 nz.ctypes.data_as(C.c_void_p) if nz is not None else None,
+                                 out.ctypes.data_as(C.c_void_p), int(device)))
+    return np.repeat(out[..., None], dim, axis=-1)
+
+
 def conductivity_per_element(mesh, cells, offset):
     """conductivity_per_element (src/examples/homogenized_coefficients.jl:494-503):
     the cell of an element is trunc(centroid + offset), 1-based."""

@@ -64,6 +64,11 @@ int64_t hmg_nf(const hmg_ctx* ctx, int level);
 int64_t hmg_ne_local(const hmg_ctx* ctx);
 int64_t hmg_ld(const hmg_ctx* ctx, int level);
 int hmg_group_width(const hmg_ctx* ctx);
+/* how the ranks of a partitioned context talk: 0 = one rank, 1 = NCCL (all-reduce of the CG scalars, grouped send/recv
+ * of the cut cells), 2 = peer memory over NVLink (CUDA IPC: the reduction kernels sum over the ranks themselves, the
+ * pack kernel stores into the neighbours' buffers).  2 is the default where every rank can map every other's buffer;
+ * HMG_PEER=0 forces 1.  The coarse-level reduce / broadcast is NCCL in both. */
+int hmg_comm_mode(const hmg_ctx* ctx);
 /* global element index (1-based) of local column j (1-based) */
 int hmg_local_elements(const hmg_ctx* ctx, int64_t* out);
 
@@ -154,6 +159,16 @@ int hmg_integrate_terms(hmg_ctx* ctx, int which_vk, int which_vkm1, int64_t nsub
 int hmg_integrate_area(hmg_ctx* ctx, int64_t nsubset, double* out);
 int hmg_next_rhs(hmg_ctx* ctx, int which_b, int which_x);
 
+/* generate_field(ns, T, threads, alpha, p) (tools/generate_st1_field.jl:86-120): white Gaussian
+ * noise -> real FFT -> division by (1 + |k|)^p (:41-84) -> inverse real FFT -> exp(alpha |G|), on the device with cuFFT.
+ * n[dim] even extents; the field comes back as n[0] x n[1] (x n[2]) doubles, last index fastest (the transpose of the
+ * Julia array).  normalize != 0: G is scaled to unit (population) standard deviation before the exponential (the inputs
+ * of BASELINE.json configs[4]; 0 = the tool as written).  noise_or_null: the caller's standard-normal samples in the same
+ * layout, or NULL to draw them on the device (Philox4x32-10, key = seed, counter = cell index, Box-Muller).  No context
+ * is needed. */
+int hmg_generate_field(int dim, const int* n, uint64_t seed, double alpha, double p, int normalize,
+                       const double* noise_or_null, double* out_host, int device);
+
 /* refined_mesh(implicit, level) (src/implicit_fine_grid.jl:24): the refined reference element that construct_full_grid
  * (src/implicit_fine_grid.jl:41-78) maps into every coarse element for the VTK export.  nodes[dim x Nf(level)] reference
  * coordinates in hierarchical row order, elems1[(dim+1) x nel] 1-based, index-sorted per element; arrays may be NULL,
@@ -169,7 +184,8 @@ int hmg_synchronize(hmg_ctx* ctx);
  * rho), 9 = restriction level -> level-1, 10 = interpolation level-1 -> level, 11 = local apply with
  * the fused owner-weighted dot, 12 = the fused direction update + product of a CG step (p' = R + beta P
  * formed inside the apply kernel, AP = broadcast(constraint(A p'))), 13 / 14 = the interface kernel restricted to the
- * two-owner cells (faces in 3D, edges in 2D) / to the cells with more owners (local cells only).  The operation is
+ * two-owner cells (faces in 3D, edges in 2D) / to the cells with more owners (local cells only), 15 = the CG update with
+ * the two-owner interface sums of AP taken on the fly, 16 = x += alpha P.  The operation is
  * launched `reps` times back to back. */
 int hmg_time_op(hmg_ctx* ctx, int op, int level, int steps, int reps, float* ms_out);
 /* number of kernel launches issued on the context's stream since creation */

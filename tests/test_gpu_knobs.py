@@ -11,6 +11,7 @@ from oracle import implicit as oi, operators as oo, multigrid as om
 pytestmark = pytest.mark.gpu
 
 KNOBS = [
+    {"HMG_CG_PAIRS": "0"},                                 # interface sums of Ap as their own pass before the CG update
     {"HMG_FUSE_P": "0"},                                   # direction update as its own kernel (p_update + product)
     {"HMG_APPLY_WARPS": "8"},
     {"HMG_APPLY_RUN": "1", "HMG_APPLY_CHUNK_SHIFT": "5"},

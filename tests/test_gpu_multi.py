@@ -21,7 +21,9 @@ def _ngpus():
         return 0
 
 
-def _worker(rank, world, nccl_id, case, results):
+def _worker(rank, world, nccl_id, case, results, peer="1"):
+    import os
+    os.environ["HMG_PEER"] = peer          # "1": peer memory over NVLink (default), "0": the NCCL path
     from parity_common import relerr
     from oracle.mesh import Mesh as OMesh
     from oracle.fem import build_local_diffusion_operators, build_local_mass_matrices, assemble_matrix
@@ -39,6 +41,7 @@ def _worker(rank, world, nccl_id, case, results):
                              nccl_id=nccl_id)
     l2g = g.local_elements()
     assert np.array_equal(l2g, np.nonzero(owner == rank)[0])
+    assert g.comm_mode() == ("peer" if peer == "1" else "nccl")      # no silent fall-back to the other path
     obase = OMesh(mesh.nodes, mesh.elements)
     oimp = OImplicit(obase, levels)
     z = ZeroDirichletConstraint(*list_boundary_nodes_edges_faces(obase))
@@ -109,6 +112,22 @@ def test_two_gpus_match_the_oracle_on_the_whole_mesh(case):
     mp.spawn(_worker, args=(2, bytes(raw), case, results), nprocs=2, join=True)
     got = dict(results.get() for _ in range(2))
     assert got[0] == got[1]          # every rank sees the same residual history
+
+
+def test_two_gpus_nccl_path_matches_the_oracle():
+    """HMG_PEER=0: scalar sums by ncclAllReduce, cut cells by grouped ncclSend / ncclRecv (what a box without peer
+    mapping falls back to)."""
+    if _ngpus() < 2:
+        pytest.skip("needs two GPUs")
+    import torch
+    import torch.multiprocessing as mp
+    raw = (C.c_ubyte * 128)()
+    hmg._lib.check(hmg.load().hmg_nccl_unique_id(raw))
+    ctx = mp.get_context("spawn")
+    results = ctx.SimpleQueue()
+    mp.spawn(_worker, args=(2, bytes(raw), (3, 3, 4), results, "0"), nprocs=2, join=True)
+    got = dict(results.get() for _ in range(2))
+    assert got[0] == got[1]
 
 
 @pytest.mark.parametrize("case", [(3, 4, 4), (2, 6, 5)], ids=["tet-c4-L4", "tri-c6-L5"])
