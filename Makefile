@@ -11,7 +11,7 @@ SRCS      := $(CSRC)/api.cu $(CSRC)/kernels.cu $(CSRC)/field.cu $(CSRC)/referenc
 HDRS      := include/hmg.h $(CSRC)/hmg_host.hpp $(CSRC)/kernels.cuh $(CSRC)/lattice.hpp $(CSRC)/apply_core.cuh
 OBJS      := $(patsubst $(CSRC)/%,$(BUILD)/%.o,$(SRCS))
 
-all: $(LIB) oracle
+all: $(LIB) oracle checked
 
 $(LIB): $(OBJS)
 	$(NVCC) -shared -o $@ $(OBJS) -L$(CUDA_LIB) -lcusolver -lcublas -ldl \
@@ -25,10 +25,14 @@ $(BUILD)/%.cpp.o: $(CSRC)/%.cpp $(HDRS)
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@
 
+# the library with device-side bounds assertions (this pool has no compute-sanitizer): variants/libhmg_checked.so
+checked:
+	$(MAKE) BUILD=build/checked LIB=variants/libhmg_checked.so HMG_EXTRA="-DHMG_BOUNDS" variants/libhmg_checked.so
+
 oracle:
 	@if [ -f oracle/c/Makefile ]; then $(MAKE) -C oracle/c; fi
 
 clean:
 	rm -rf build $(LIB)
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean checked

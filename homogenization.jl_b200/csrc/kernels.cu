@@ -22,6 +22,16 @@
 #include "lattice.hpp"
 #include "apply_core.cuh"
 
+// HMG_BOUNDS (build variant, `make checked`): the pool has no compute-sanitizer, so the checked library asserts every
+// ring read, every output store of the apply kernel and every entry the interface / CG kernels touch against its bounds
+// (tests run the parity suite through it with HMG_LIB=variants/libhmg_checked.so)
+#ifdef HMG_BOUNDS
+#include <cassert>
+#define HMG_DEV_ASSERT(c) assert(c)
+#else
+#define HMG_DEV_ASSERT(c) ((void)0)
+#endif
+
 namespace hmg {
 
 // ------------------------------------------------------------------------------------------
@@ -243,6 +253,7 @@ template <int DIM> __device__ __forceinline__ int64_t plane_at_or_after(int64_t 
 // nobody reads: alpha = rho / p.Ap needs the dot, x += alpha p needs p -- the vector Ap itself is dead)
 template <int DIM, int W, int MODE, bool DOT, bool STORE = true> struct OutDev {
     static constexpr int APPLY_W = W;
+    double *ylo, *yhi;     // bounds of the output vector (read by the checked build only)
     double* yl;            // output row of node 0 of the current line (lane included)
     const double* tl;
     double sa;
@@ -283,6 +294,7 @@ template <int DIM, int W, int MODE, bool DOT, bool STORE = true> struct OutDev {
             tq[TD - 1] = __ldcs(tl + min(k + TD, klast) * APPLY_W);
             v = MODE == APPLY_RESIDUAL ? (fixed ? 0.0 : tv - acc) : fma(sa, acc, tv);
         }
+        HMG_DEV_ASSERT(!STORE || (yl + k * APPLY_W >= ylo && yl + k * APPLY_W < yhi));
         if (STORE) yl[k * APPLY_W] = v;
         if (DOT) {
             if (MODE == APPLY_AX) dsum = fma(weight<CLS>() * x0, v, dsum);
@@ -293,7 +305,11 @@ template <int DIM, int W, int MODE, bool DOT, bool STORE = true> struct OutDev {
 
 struct SmemLoad {
     const double* sm;
-    __device__ __forceinline__ double operator()(int addr) const { return sm[addr]; }
+    int limit;             // doubles in the ring + mirror rows
+    __device__ __forceinline__ double operator()(int addr) const {
+        HMG_DEV_ASSERT(addr >= 0 && addr < limit);
+        return sm[addr];
+    }
 };
 
 // FUSEP (with MODE = AX): the input is not a stored vector but the new search direction p' = r + beta p of
@@ -452,8 +468,9 @@ __global__ void __launch_bounds__(DIM == 3 ? HMG_MAXT3 : APPLY_MAXT, 1) apply_ke
         }
     } else if (nchunks > 0) {
         // ---------------- consumers ----------------
-        SmemLoad mem{sm};
+        SmemLoad mem{sm, (R + SP) * APPLY_W};
         OutDev<DIM, W, MODE, DOT, STORE> out;
+        out.ylo = a.y; out.yhi = a.y + a.nunits * (int64_t)nf * APPLY_W;
         out.sa = a.sa;
         out.dsum = 0.0;
         out.cm = 0; out.ml = out.mh = 0ull;
@@ -826,7 +843,10 @@ __global__ void __launch_bounds__(256) interface_kernel(const LevelView L, const
                 }
                 if (OP == 0) {
 #pragma unroll
-                    for (int q = 0; q < U; ++q) { va[q] = A[oa[q]]; vb_[q] = B[ob[q]]; }
+                    for (int q = 0; q < U; ++q) {
+                        HMG_DEV_ASSERT(oa[q] >= 0 && oa[q] < (int64_t)nf * W && ob[q] >= 0 && ob[q] < (int64_t)nf * W && pe < T.ne);
+                        va[q] = A[oa[q]]; vb_[q] = B[ob[q]];
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < U; ++q) {
@@ -876,6 +896,7 @@ __global__ void __launch_bounds__(256) interface_kernel(const LevelView L, const
             const int32_t id = __ldg(own + o);
             const int64_t el = id >> 3;
             rows = tab + (id & 7) * npc;
+            HMG_DEV_ASSERT(o >= b && o < en && el >= 0 && el < T.ne && (id & 7) < (npc == 1 ? DIM + 1 : nel));
             return x + (el >> ws) * (int64_t)nf * W + (el & (W - 1));
         };
         if (OP == 1) {
@@ -1323,6 +1344,7 @@ __global__ void __launch_bounds__(256) cg_update_pairs_kernel(const Reducer R, c
                 const int prt = f == 0 ? pr.x : (f == 1 ? pr.y : (f == 2 ? pr.z : pr.w));
                 if (prt >= 0) {
                     const int64_t pe = prt >> 3;
+                    HMG_DEV_ASSERT(pe >= 0 && pe < T.ne && kk < npc && (prt & 7) < (DIM == 3 ? 4 : 3));
                     bv[q] = Ap[((pe >> 5) * (int64_t)nf + __ldg(tab + (prt & 7) * npc + kk)) * 32 + (pe & 31)];
                 }
             }
