@@ -6,6 +6,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -155,8 +156,6 @@ struct hmg_ctx {
     // peer memory (NVLink, CUDA IPC): scalar all-reduces inside the reduction kernels and the cut exchange without a
     // collective call.  peer_on is agreed on by all ranks at creation (HMG_PEER=0 or a failed mapping: NCCL path).
     bool peer_on = false;
-    // the two-owner part of the interface sum of Ap inside the CG update (HMG_CG_PAIRS=0: as its own pass)
-    bool cg_pairs = true;
     void* peer_buf = nullptr;                    // this rank's communication buffer (exported)
     std::vector<void*> peer_mapped;              // the other ranks' buffers as mapped here (nullptr for the own rank)
     std::vector<CutPeer> cut_peer;               // per level
@@ -196,12 +195,23 @@ struct hmg_ctx {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_permuted[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
+    // CUDA graphs of whole V-cycles, one per (top level, steps, with norm): HMG_GRAPH=0 launches eagerly.  A graph is
+    // captured at the second request of its kind (the first runs eagerly and performs every lazy allocation) and dropped
+    // whenever lambda, sigma or the coarse matrix change (lambda travels in the kernel parameters).
+    struct CycleGraph { cudaGraphExec_t exec = nullptr; int64_t launches = 0; bool warmed = false; };
+    std::map<std::tuple<int, int, int>, CycleGraph> graphs;
+    int graph_mode = 1;                  // 0 = off, 1 = on for single-GPU contexts, 2 = also for partitioned ones
+    void drop_graphs() {
+        for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        graphs.clear();
+    }
 
     ~hmg_ctx() {
         // also runs when hmg_create fails half-way: nothing of the context outlives it
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         if (copy_stream) cudaStreamSynchronize(copy_stream);
+        drop_graphs();
         if (peer_on) peer_teardown();
         if (comm) nccl_destroy(comm);
         for (void* p : allocs) cudaFree(p);
@@ -429,7 +439,7 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const 
     c->ne_global = ne_global;
     c->nn = nn;
     c->lambda = lambda;
-    if (const char* v = getenv("HMG_CG_PAIRS")) c->cg_pairs = atoi(v) != 0;
+    if (const char* v = getenv("HMG_GRAPH")) c->graph_mode = atoi(v);
     CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreate(&c->ev0));
     CUDA_OK(cudaEventCreate(&c->ev1));
@@ -476,15 +486,6 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const 
         V.boundary = c->dupload(R.boundary);
         V.G = c->dupload(R.G);
         V.iface_idx = c->dupload(R.iface_idx);
-        {
-            // inverse of the two-owner part of iface_idx (3D: the 4 faces, 2D: the 3 edges): node -> (local cell, position)
-            const int ncell = dim == 3 ? 4 : 3, npc = dim == 3 ? V.npf : V.npe;
-            std::vector<uint16_t> pi((size_t)R.nf, 0xFFFFu);
-            HMG_CHECK(npc < (1 << 14), "too many nodes per two-owner cell for the pair table");
-            for (int f = 0; f < ncell; ++f)
-                for (int k = 0; k < npc; ++k) pi[R.iface_idx[(size_t)f * npc + k]] = (uint16_t)((f << 14) | k);
-            V.pairinfo = c->dupload(pi);
-        }
         V.interp_tab = c->dupload(R.interp_tab);
         V.restrict_tab = c->dupload(R.restrict_tab);
         for (int v = 0; v < 4; ++v) V.vpos[v] = v < nv ? R.hier2lat[v] : 0;
@@ -768,39 +769,35 @@ void do_smoothing(hmg_ctx* c, int l, int steps, bool need_r = true) {
         const bool x_only = !need_r && i == steps - 1;
         // Ap = broadcast(constraint(A p)), alpha = rho / p.Ap; after the first step the direction update
         // p = r + beta p (src/multigrid.jl:68) happens inside the product
-        // (Ap is only read by the update below: with cg_pairs its two-owner cells stay un-summed in memory and the
-        // update adds the partner's copy on the fly)
         const double* dir = p;
-        const int part = c->cg_pairs ? 2 : 3;
-        if (i == 0) { do_global_product(c, l, r, Ap, POST_PAP, x_only, part); dir = r; }
-        else if (fuse) { do_fused_direction_product(c, l, x_only, part); p = c->vecp(l, HMG_P); dir = p; }
+        if (i == 0) { do_global_product(c, l, r, Ap, POST_PAP, x_only); dir = r; }
+        else if (fuse) { do_fused_direction_product(c, l, x_only); p = c->vecp(l, HMG_P); dir = p; }
         else {
             check_launch(c, launch_p_update(c->red, p, r, n, c->stream));
-            do_global_product(c, l, p, Ap, POST_PAP, x_only, part);
+            do_global_product(c, l, p, Ap, POST_PAP, x_only);
         }
         if (x_only) {
             check_launch(c, launch_x_update(c->red, x, dir, n, c->stream));
             break;
         }
-        if (c->cg_pairs)
-            check_launch(c, launch_cg_update_pairs(c->dim, c->red, c->level(l).view, c->tview, c->nunits, x, p, r, Ap,
-                                                   kernel_post(c, POST_RSQR), i == 0, c->stream));
-        else
-            check_launch(c, launch_cg_update(c->red, x, p, r, Ap, n, kernel_post(c, POST_RSQR), i == 0, c->stream));
+        check_launch(c, launch_cg_update(c->red, x, p, r, Ap, n, kernel_post(c, POST_RSQR), i == 0, c->stream));
         finish_reduction(c, POST_RSQR, S_TMP);
         // the reference also updates p after the last step, but that value is never used
         // (the next smoothing call starts from a fresh residual)
     }
 }
 void assemble_coarse_impl(hmg_ctx* c);
-void do_coarse_solve(hmg_ctx* c) {
-    Range range("hmg coarse solve", 1);
+void ensure_coarse(hmg_ctx* c) {
     HMG_CHECK(c->n_interior > 0, "coarse matrix not set: call hmg_set_coarse_matrix or hmg_assemble_coarse first");
     if (c->coarse_gen != c->op_gen) {
         // hmg_set_lambda / hmg_set_sigma after the factorisation: the inverse belongs to another operator
         HMG_CHECK(c->coarse_internal, "lambda or sigma changed after hmg_set_coarse_matrix: hand over the new coarse matrix first");
         assemble_coarse_impl(c);
     }
+}
+void do_coarse_solve(hmg_ctx* c) {
+    Range range("hmg coarse solve", 1);
+    ensure_coarse(c);
     LevelDev& L1 = c->level(1);
     do_broadcast(c, 1, c->vecp(1, HMG_B));
     if (c->nranks == 1) {
@@ -979,6 +976,7 @@ void assemble_coarse_impl(hmg_ctx* c) {
     std::vector<std::map<int64_t, double>> cols(n);
     c->coarse_internal = true;
     c->coarse_gen = c->op_gen;
+    c->drop_graphs();
     if (c->rank != 0) { c->n_interior = n; return; }
     for (int64_t e = 0; e < c->ne_global; ++e) {
         const double* ec = &coef[(size_t)e * cs];
@@ -1088,7 +1086,7 @@ int hmg_local_elements(const hmg_ctx* c, int64_t* out) {
 int hmg_set_lambda(hmg_ctx* c, double lambda) {
     HMG_API_BEGIN
     NEED_CTX(c);
-    if (lambda != c->lambda) ++c->op_gen;      // the coarse inverse (if any) belongs to the old operator
+    if (lambda != c->lambda) { ++c->op_gen; c->drop_graphs(); }      // the coarse inverse (if any) belongs to the old operator
     c->lambda = lambda;
     HMG_API_END
 }
@@ -1099,6 +1097,7 @@ int hmg_set_sigma(hmg_ctx* c, const double* sigma) {
     CUDA_OK(cudaSetDevice(c->device));
     upload_operator(c, sigma);
     ++c->op_gen;
+    c->drop_graphs();
     HMG_API_END
 }
 
@@ -1331,6 +1330,7 @@ int hmg_set_coarse_matrix(hmg_ctx* c, int64_t n, const int64_t* colptr, const in
     set_coarse_dense(c, n, cp, rv, nz, in0);
     c->coarse_internal = false;
     c->coarse_gen = c->op_gen;
+    c->drop_graphs();
     HMG_API_END
 }
 
@@ -1378,12 +1378,54 @@ static void vcycle_with_norm(hmg_ctx* c, int top, int steps, bool want_norm, int
     }
 }
 
+// One V-cycle (+ the logged norm) through a CUDA graph of its ~150 launches
+static void run_vcycle(hmg_ctx* c, int top, int steps, bool want_norm) {
+    if (top >= 2) ensure_coarse(c);                 // never inside a capture: it allocates and synchronises
+    // several ranks: the coarse-level ncclReduce / ncclBroadcast would be captured too -- opt-in (HMG_GRAPH=2)
+    const bool use_graph = top >= 2 && (c->nranks == 1 ? c->graph_mode >= 1 : c->graph_mode >= 2);
+    if (!use_graph) { vcycle_with_norm(c, top, steps, want_norm, S_NRM); return; }
+    hmg_ctx::CycleGraph& G = c->graphs[std::make_tuple(top, steps, (int)want_norm)];
+    if (!G.warmed) {                                // lazy buffers, function attributes: once, eagerly
+        vcycle_with_norm(c, top, steps, want_norm, S_NRM);
+        G.warmed = true;
+        return;
+    }
+    if (!G.exec) {
+        const int64_t before = c->launches;
+        cudaGraph_t graph = nullptr;
+        CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            vcycle_with_norm(c, top, steps, want_norm, S_NRM);
+        } catch (...) {
+            cudaStreamEndCapture(c->stream, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            c->graph_mode = 0;
+            throw;
+        }
+        CUDA_OK(cudaStreamEndCapture(c->stream, &graph));
+        G.launches = c->launches - before;
+        c->launches = before;
+        const cudaError_t e = cudaGraphInstantiate(&G.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {                     // stay eager
+            cudaGetLastError();
+            G.exec = nullptr;
+            c->graph_mode = 0;
+            vcycle_with_norm(c, top, steps, want_norm, S_NRM);
+            return;
+        }
+    }
+    CUDA_OK(cudaGraphLaunch(G.exec, c->stream));
+    c->launches += G.launches;
+}
+
 int hmg_vcycle(hmg_ctx* c, int top_level, int steps, double* out_resnorm) {
     HMG_API_BEGIN
     NEED_CTX(c);
     CUDA_OK(cudaSetDevice(c->device));
     HMG_CHECK(top_level >= 1 && top_level <= c->nlevels, "level out of range");
-    vcycle_with_norm(c, top_level, steps, out_resnorm != nullptr, S_NRM);
+    run_vcycle(c, top_level, steps, out_resnorm != nullptr);
     if (out_resnorm) *out_resnorm = std::sqrt(read_scalar(c, S_NRM));
     HMG_API_END
 }
@@ -1396,7 +1438,7 @@ int hmg_vcycles(hmg_ctx* c, int top_level, int steps, int ncycles, double* resno
     double* dn = nullptr;
     if (resnorms) dn = c->dalloc<double>(ncycles);
     for (int i = 0; i < ncycles; ++i) {
-        vcycle_with_norm(c, top_level, steps, resnorms != nullptr, S_NRM);
+        run_vcycle(c, top_level, steps, resnorms != nullptr);
         if (resnorms)
             CUDA_OK(cudaMemcpyAsync(dn + i, c->red.scalars + S_NRM, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     }
@@ -1541,7 +1583,7 @@ int hmg_time_op(hmg_ctx* c, int op, int level, int steps, int reps, float* ms_ou
         if (op == 0) {
             do_global_product(c, level, c->vecp(level, HMG_P), c->vecp(level, HMG_AP));
         } else if (op == 1) {
-            do_vcycle(c, level, steps, level);
+            run_vcycle(c, level, steps, false);
         } else if (op == 2) {
             do_apply(c, level, APPLY_MULADD, 1.0, c->vecp(level, HMG_P), c->vecp(level, HMG_AP), nullptr);
         } else if (op == 3) {
@@ -1568,10 +1610,6 @@ int hmg_time_op(hmg_ctx* c, int op, int level, int steps, int reps, float* ms_ou
         } else if (op == 12) {
             HMG_CHECK(c->level(level).cfg_fused.ring_rows > 0, "the fused p-update does not fit this level");
             do_fused_direction_product(c, level);
-        } else if (op == 15) {
-            check_launch(c, launch_cg_update_pairs(c->dim, c->red, c->level(level).view, c->tview, c->nunits, c->vecp(level, HMG_X),
-                                                   c->vecp(level, HMG_P), c->vecp(level, HMG_R), c->vecp(level, HMG_AP), POST_RSQR,
-                                                   false, c->stream));
         } else if (op == 16) {
             check_launch(c, launch_x_update(c->red, c->vecp(level, HMG_X), c->vecp(level, HMG_P), c->nstored(level), c->stream));
         } else if (op == 11) {

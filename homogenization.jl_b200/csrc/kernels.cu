@@ -491,7 +491,10 @@ __global__ void __launch_bounds__(DIM == 3 ? HMG_MAXT3 : APPLY_MAXT, 1) apply_ke
             // advance the cursor by `step` tasks
             i += step;
             for (;;) {
-                const int cnt = DIM == 3 ? (t + RL) / RL : ((m - t + (1 << SEGS)) >> SEGS);
+                // 3D: runs of RL lines, or (SEGS < 30, RL = 1) every line cut into ceil(L / 2^SEGS) segments along k, so
+                // that the warps of the CTA spread over fewer lines of the plane (a smaller window in the ring)
+                const int cnt = DIM == 3 ? (SEGS < 30 ? (t + 1) * ((m - t + (1 << SEGS)) >> SEGS) : (t + RL) / RL)
+                                         : ((m - t + (1 << SEGS)) >> SEGS);
                 if (i < cnt) break;
                 i -= cnt;
                 if (++t > m) { t = 0; ++u; }
@@ -535,10 +538,20 @@ __global__ void __launch_bounds__(DIM == 3 ? HMG_MAXT3 : APPLY_MAXT, 1) apply_ke
             LineGeo<DIM> g;
             int rc, rm[Sweep<DIM>::NP], rp[Sweep<DIM>::NP], need, behind, nl = 1, il = 0;
             if constexpr (DIM == 3) {
-                il = i * RL;
-                nl = min(RL, t + 1 - il);
+                int k0 = 0, k1 = m - t + 1;
+                if (SEGS < 30) {
+                    const int Lt = m - t + 1, nseg = (Lt + (1 << SEGS) - 1) >> SEGS;
+                    il = i / nseg;
+                    const int len = (Lt + nseg - 1) / nseg;             // balanced segments
+                    k0 = (i - il * nseg) * len;
+                    k1 = min(Lt, k0 + len);
+                    nl = 1;
+                } else {
+                    il = i * RL;
+                    nl = min(RL, t + 1 - il);
+                }
                 const LineRows3 r = line_rows3(m, t, il, lat_off3(m, t));
-                g.L = r.L; g.k0 = 0; g.k1 = r.L;
+                g.L = r.L; g.k0 = k0; g.k1 = k1;
                 rc = r.c; behind = r.behind;
                 need = t < m ? r.need + (nl - 1) * (r.L - 1) : min(r.c + nl, plane_off<3>(m, m + 1) - 1);
 #pragma unroll
@@ -597,8 +610,10 @@ __global__ void __launch_bounds__(DIM == 3 ? HMG_MAXT3 : APPLY_MAXT, 1) apply_ke
                     g.bc = qc * APPLY_W + el;
                     g.bm[0] = qm[0] * APPLY_W + el; g.bm[1] = qm[1] * APPLY_W + el; g.bm[2] = qm[2] * APPLY_W + el;
                     g.bp[0] = qp[0] * APPLY_W + el; g.bp[1] = qp[1] * APPLY_W + el; g.bp[2] = qp[2] * APPLY_W + el;
-                    out.begin(0, L);
-                    run_line3(op, a.T, mem, APPLY_W, g, t, il + li, out);
+                    if (g.k0 < g.k1) {                  // (a segment can only be empty for segment lengths below 4)
+                        out.begin(g.k0, g.k1);
+                        run_line3(op, a.T, mem, APPLY_W, g, t, il + li, out);
+                    }
                     // the next line of the plane: every base moves by one line of its own plane
                     adv(qc, L); adv(qm[0], L - 1); adv(qm[1], L - 1); adv(qm[2], L);
                     adv(qp[0], L + 1); adv(qp[1], L + 1); adv(qp[2], L);
@@ -656,7 +671,9 @@ static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool f
     c.nwarps = std::max(1, std::min(maxw - 1, envi("HMG_APPLY_WARPS", maxw - 1)));
     c.ctas_per_sm = 1;
     c.oversub = envi("HMG_APPLY_OVERSUB", 0);
-    c.seg = dim == 2 ? std::max(2, std::min(8, envi("HMG_APPLY_SEG_SHIFT", 5))) : 30;
+    // 2D: log2(nodes per task); 3D: 30 = whole lines, else lines are cut into segments of <= 2^seg nodes (one line per task)
+    c.seg = dim == 2 ? std::max(2, std::min(8, envi("HMG_APPLY_SEG_SHIFT", 5))) : envi("HMG_APPLY_SEG3_SHIFT", 30);
+    if (dim == 3 && (c.seg < 2 || c.seg > 8)) c.seg = 30;
     c.spill_rows = dim == 2 ? (1 << c.seg) + 3 : m + 3;       // rows a task may run past the base of a line
     const int rowb = W * 8;
     // fused p-update: staging slots of 16 rows of r and p each; enough of them to keep ~48 KB in flight
@@ -714,6 +731,11 @@ static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool f
         }
     }
     if (!found) { c.run = run_env ? run_env : 1; c.chunk_shift = cs_env ? cs_env : 5; }
+    // 3D hierarchies of 6 grids: the two-plane window leaves the ring no room for runs of lines, and the 15 warps of a
+    // CTA spread over 15 lines of a plane; cutting the lines in two halves that spread (measured on C4: apply 4.86 ->
+    // 4.72 ms, residual 7.05 -> 6.85 ms, profiles/r02e_launch_shapes_C4.jsonl)
+    if (dim == 3 && c.seg >= 30 && c.run == 1 && m >= 32 && !getenv("HMG_APPLY_SEG3_SHIFT")) c.seg = 4;
+    if (dim == 3 && c.seg < 30) c.run = 1;
     const int CH = 1 << c.chunk_shift;
     const int min_rows = window(c.run) + 2 * CH;
     int R = std::min(max_rows, (APPLY_Q - 2) * CH);
@@ -896,7 +918,7 @@ __global__ void __launch_bounds__(256) interface_kernel(const LevelView L, const
             const int32_t id = __ldg(own + o);
             const int64_t el = id >> 3;
             rows = tab + (id & 7) * npc;
-            HMG_DEV_ASSERT(o >= b && o < en && el >= 0 && el < T.ne && (id & 7) < (npc == 1 ? DIM + 1 : nel));
+            HMG_DEV_ASSERT(o >= b && o < en && el >= 0 && el < T.ne && (id & 7) < (t < nedge_cells ? nel : DIM + 1));
             return x + (el >> ws) * (int64_t)nf * W + (el & (W - 1));
         };
         if (OP == 1) {
@@ -1302,79 +1324,6 @@ __global__ void __launch_bounds__(256) cg_update_kernel(const Reducer R, double*
         s = fma(rv.x, rv.x, s); s = fma(rv.y, rv.y, s);
     }
     block_reduce_finish(s, R, post, S_TMP);
-}
-
-// The same update with the pair part of the interface sum of Ap folded in (the V-cycle never needs the summed Ap as
-// a stored vector: alpha comes from the owner-weighted dot of the apply kernel, and only r -= alpha Ap reads it).
-// Lanes are the elements of a unit, a warp takes rows; on a row of a two-owner cell (3D face, 2D edge interior) every
-// lane adds its partner's local copy, ascending owner order being irrelevant for two addends (a + b == b + a bit for
-// bit, so both owners compute the same r).  Cells with more owners and cut cells were summed in place before.
-template <int DIM, bool FIRST>
-__global__ void __launch_bounds__(256) cg_update_pairs_kernel(const Reducer R, const LevelView L, const TopoView T, int64_t nunits,
-                                                              double* __restrict__ x, double* __restrict__ p, double* __restrict__ r,
-                                                              const double* __restrict__ Ap, int post) {
-    constexpr int ROWS = 32, U = 4;                     // rows per block step, rows per warp step (8 warps)
-    const double alpha = R.scalars[S_ALPHA];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nf = L.nf;
-    const int npc = DIM == 3 ? L.npf : L.npe;
-    const uint16_t* tab = L.iface_idx;
-    const int nrb = (nf + ROWS - 1) / ROWS;
-    const int64_t total = nunits * nrb;
-    double s = 0.0;
-    for (int64_t it = blockIdx.x; it < total; it += gridDim.x) {
-        const int64_t u = it / nrb;
-        const int rb = (int)(it - u * nrb);
-        const int64_t e = u * 32 + lane;
-        int4 pr = make_int4(-1, -1, -1, -1);
-        if (e < T.ne) pr = __ldg(reinterpret_cast<const int4*>(T.partner) + e);
-        const int64_t base = u * (int64_t)nf * 32 + lane;
-        int row[U];
-        double xv[U], rv[U], pv[U], qv[U], bv[U];
-#pragma unroll
-        for (int q = 0; q < U; ++q) {
-            row[q] = rb * ROWS + q * 8 + warp;
-            const bool in = row[q] < nf;
-            const int64_t at = base + (int64_t)(in ? row[q] : 0) * 32;
-            xv[q] = x[at]; rv[q] = r[at]; qv[q] = Ap[at];
-            pv[q] = FIRST ? rv[q] : p[at];
-            bv[q] = 0.0;
-            const unsigned info = in ? __ldg(L.pairinfo + row[q]) : 0xFFFFu;
-            if (info != 0xFFFFu) {
-                const int f = info >> 14, kk = info & 0x3FFF;
-                const int prt = f == 0 ? pr.x : (f == 1 ? pr.y : (f == 2 ? pr.z : pr.w));
-                if (prt >= 0) {
-                    const int64_t pe = prt >> 3;
-                    HMG_DEV_ASSERT(pe >= 0 && pe < T.ne && kk < npc && (prt & 7) < (DIM == 3 ? 4 : 3));
-                    bv[q] = Ap[((pe >> 5) * (int64_t)nf + __ldg(tab + (prt & 7) * npc + kk)) * 32 + (pe & 31)];
-                }
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < U; ++q) {
-            if (row[q] >= nf) continue;
-            const int64_t at = base + (int64_t)row[q] * 32;
-            const double ap = qv[q] + bv[q];
-            const double xn = fma(alpha, pv[q], xv[q]);
-            const double rn = fma(-alpha, ap, rv[q]);
-            x[at] = xn; r[at] = rn;
-            if (FIRST) p[at] = rv[q];
-            s = fma(rn, rn, s);
-        }
-    }
-    block_reduce_finish(s, R, post, S_TMP);
-}
-int launch_cg_update_pairs(int dim, const Reducer& R, const LevelView& L, const TopoView& T, int64_t nunits, double* x, double* p,
-                           double* r, const double* Ap, int post, bool first, cudaStream_t st) {
-    const int nrb = (L.nf + 31) / 32;
-    const unsigned grid = (unsigned)std::min<int64_t>(nunits * nrb, R.max_blocks);
-    if (dim == 3) {
-        if (first) cg_update_pairs_kernel<3, true><<<grid, 256, 0, st>>>(R, L, T, nunits, x, p, r, Ap, post);
-        else cg_update_pairs_kernel<3, false><<<grid, 256, 0, st>>>(R, L, T, nunits, x, p, r, Ap, post);
-    } else {
-        if (first) cg_update_pairs_kernel<2, true><<<grid, 256, 0, st>>>(R, L, T, nunits, x, p, r, Ap, post);
-        else cg_update_pairs_kernel<2, false><<<grid, 256, 0, st>>>(R, L, T, nunits, x, p, r, Ap, post);
-    }
-    return 1;
 }
 
 // p = r + beta p   (src/multigrid.jl:68)

@@ -21,7 +21,6 @@ struct LevelView {
     const uint32_t* boundary;   // [n_boundary] p | class<<14   (sorted by class)
     const double* G;            // [ncls][ndir][nc]
     const uint16_t* iface_idx;  // paired-node packed indices: faces [4][npf], edges [6|3][npe], vertices
-    const uint16_t* pairinfo;   // [nf] two-owner cell of a node: local cell id << 14 | position in the cell's list; 0xFFFF none
     const uint32_t* interp_tab; // [nf] coarse parents pa | pb<<16 (levels >= 2)
     const uint16_t* restrict_tab; // [nf(level-1)][ndir] fine indices, 0xFFFF = outside
     int vpos[4];                // packed lattice index of the reference vertices
@@ -162,10 +161,6 @@ int launch_interp_add(int dim, const LevelView& Lf, const LevelView& Lc, int64_t
 int launch_dot(const Reducer& R, const double* a, const double* b, int64_t n, int post, int slot, cudaStream_t st);
 int launch_copy_dot(const Reducer& R, const double* r, double* p, int64_t n, int post, cudaStream_t st);
 int launch_cg_update(const Reducer& R, double* x, double* p, double* r, const double* Ap, int64_t n, int post, bool first, cudaStream_t st);
-// the same update with the interface sum of the two-owner cells (3D faces, 2D edges) of Ap taken on the fly: every owner
-// adds its partner's local copy while it streams -- Ap's copies on those cells stay UN-summed in memory
-int launch_cg_update_pairs(int dim, const Reducer& R, const LevelView& L, const TopoView& T, int64_t nunits, double* x, double* p,
-                           double* r, const double* Ap, int post, bool first, cudaStream_t st);
 int launch_p_update(const Reducer& R, double* p, const double* r, int64_t n, cudaStream_t st);
 int launch_x_update(const Reducer& R, double* x, const double* p, int64_t n, cudaStream_t st);   // x += S_ALPHA * p
 int launch_axpy(double alpha, const double* x, double* y, int64_t n, cudaStream_t st);

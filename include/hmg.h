@@ -184,8 +184,8 @@ int hmg_synchronize(hmg_ctx* ctx);
  * rho), 9 = restriction level -> level-1, 10 = interpolation level-1 -> level, 11 = local apply with
  * the fused owner-weighted dot, 12 = the fused direction update + product of a CG step (p' = R + beta P
  * formed inside the apply kernel, AP = broadcast(constraint(A p'))), 13 / 14 = the interface kernel restricted to the
- * two-owner cells (faces in 3D, edges in 2D) / to the cells with more owners (local cells only), 15 = the CG update with
- * the two-owner interface sums of AP taken on the fly, 16 = x += alpha P.  The operation is
+ * two-owner cells (faces in 3D, edges in 2D) / to the cells with more owners (local cells only), 16 = x += alpha P.  The
+ * operation is
  * launched `reps` times back to back. */
 int hmg_time_op(hmg_ctx* ctx, int op, int level, int steps, int reps, float* ms_out);
 /* number of kernel launches issued on the context's stream since creation */

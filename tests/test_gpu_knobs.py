@@ -11,7 +11,8 @@ from oracle import implicit as oi, operators as oo, multigrid as om
 pytestmark = pytest.mark.gpu
 
 KNOBS = [
-    {"HMG_CG_PAIRS": "0"},                                 # interface sums of Ap as their own pass before the CG update
+    {"HMG_CG_PAIRS": "0"},
+    {"HMG_GRAPH": "0"},                                    # every V-cycle launched eagerly (default: CUDA graph from the 2nd on)                                 # interface sums of Ap as their own pass before the CG update
     {"HMG_FUSE_P": "0"},                                   # direction update as its own kernel (p_update + product)
     {"HMG_APPLY_WARPS": "8"},
     {"HMG_APPLY_RUN": "1", "HMG_APPLY_CHUNK_SHIFT": "5"},
@@ -19,6 +20,8 @@ KNOBS = [
     {"HMG_APPLY_CONVERTERS": "1"},
     {"HMG_APPLY_SLOT_SHIFT": "1"},
     {"HMG_APPLY_SEG_SHIFT": "4", "HMG_APPLY_OVERSUB": "3"},
+    {"HMG_APPLY_SEG3_SHIFT": "3"},                         # 3D lines cut into segments of <= 8 nodes (default: whole lines below 6 grids)
+    {"HMG_APPLY_SEG3_SHIFT": "30"},
 ]
 
 

@@ -38,7 +38,7 @@ def main():
     out = {"dim": dim, "c": c, "levels": levels, "dofs": dofs, "env": {k: v for k, v in os.environ.items() if k.startswith("HMG_")}}
     # (op, name, algorithmic bytes per stored DOF)
     ops = ((3, "apply", 16), (11, "apply_dot", 16), (4, "interface", 16), (13, "interface_pairs", 16), (14, "interface_multi", 16), (0, "global_product", 16), (5, "residual", 24),
-           (2, "mul", 24), (12, "fused_p_product", 32), (6, "cg_update", 48), (15, "cg_update_pairs", 48), (16, "x_update", 24), (7, "p_update", 24), (8, "copy_dot", 16), (9, "restrict", 9), (10, "interp", 17))
+           (2, "mul", 24), (12, "fused_p_product", 32), (6, "cg_update", 48), (16, "x_update", 24), (7, "p_update", 24), (8, "copy_dot", 16), (9, "restrict", 9), (10, "interp", 17))
     for op, name, bpd in ops:
         if levels < 2 and op in (9, 10):
             continue
