@@ -60,6 +60,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// non-blocking probe of a phase: several of them issue back to back, their latencies overlap
+__device__ __forceinline__ unsigned mbar_test(uint64_t* bar, uint32_t parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -576,6 +587,11 @@ __global__ void __launch_bounds__(DIM == 3 ? HMG_MAXT3 : APPLY_MAXT, 1) apply_ke
                         for (int c = released; c < r0; ++c) mbar_arrive(&empty_bar[c & (APPLY_Q - 1)]);
                     released = r0;
                 }
+                // A warp sees every chunk (a line of its own every NW lines: ~8 chunks per task at 3D level 6).  Probing
+                // them one blocking wait after the other costs the latency of a barrier probe per chunk even when the data
+                // has long arrived (ncu, round 2: 38 % of the kernel's stall samples sat on these branches); four probes
+                // issued back to back cost one.  Only when a probe fails does the warp block, on the oldest chunk.
+#ifdef HMG_SERIAL_PROBES          // (A/B build of round 2: one blocking wait per chunk, as in round 1)
                 while (waited <= qn) {
                     mbar_wait(&full_bar[waited & (APPLY_Q - 1)], (waited >> APPLY_QS) & 1u);
                     ++waited;
@@ -585,6 +601,29 @@ __global__ void __launch_bounds__(DIM == 3 ? HMG_MAXT3 : APPLY_MAXT, 1) apply_ke
                         ++released;
                     }
                 }
+#else
+                while (waited <= qn) {
+                    const int n = min(qn - waited + 1, 4);
+                    unsigned ok = 1u;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int cq = waited + min(j, n - 1);
+                        ok &= mbar_test(&full_bar[cq & (APPLY_Q - 1)], (cq >> APPLY_QS) & 1u);
+                    }
+                    if (ok) waited += n;
+                    else {
+                        mbar_wait(&full_bar[waited & (APPLY_Q - 1)], (waited >> APPLY_QS) & 1u);
+                        ++waited;
+                    }
+                    const int r1 = min(qb, waited);
+                    if (released < r1) {
+                        __syncwarp();
+                        if (lane == 0)
+                            for (int c = released; c < r1; ++c) mbar_arrive(&empty_bar[c & (APPLY_Q - 1)]);
+                        released = r1;
+                    }
+                }
+#endif
             }
             // ring rows: the window start moves monotonically, every line starts less than R rows after it
             pb += su + behind - sb;
@@ -734,7 +773,7 @@ static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool f
     // 3D hierarchies of 6 grids: the two-plane window leaves the ring no room for runs of lines, and the 15 warps of a
     // CTA spread over 15 lines of a plane; cutting the lines in two halves that spread (measured on C4: apply 4.86 ->
     // 4.72 ms, residual 7.05 -> 6.85 ms, profiles/r02e_launch_shapes_C4.jsonl)
-    if (dim == 3 && c.seg >= 30 && c.run == 1 && m >= 32 && !getenv("HMG_APPLY_SEG3_SHIFT")) c.seg = 4;
+    if (dim == 3 && c.seg >= 30 && m >= 32 && !run_env && !getenv("HMG_APPLY_SEG3_SHIFT")) c.seg = 4;
     if (dim == 3 && c.seg < 30) c.run = 1;
     const int CH = 1 << c.chunk_shift;
     const int min_rows = window(c.run) + 2 * CH;
