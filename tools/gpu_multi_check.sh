@@ -1,7 +1,7 @@
 #!/bin/bash
 # Multi-GPU check (run through `gpurun --gpus N -- bash tools/gpu_multi_check.sh N TAG`): the partitioned-context tests
 # against the oracle, then bench.py at N ranks -- peer memory (default), CUDA graphs on top, and the NCCL path.
-N=${1:-2}; TAG=${2:-r02}
+N=${1:-2}; TAG=${2:-r02}; SEL=${3:-gpus}
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 t0=$(date +%s)
@@ -15,10 +15,10 @@ run() { # name, env..., then bench args after --
 }
 el start
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-timeout 1500 python -m pytest tests/test_gpu_multi.py -q -x > gpurun_out/${TAG}_pytest_multi_n${N}.log 2>&1; el "pytest multi rc=$?"; tail -4 gpurun_out/${TAG}_pytest_multi_n${N}.log
+timeout 1500 python -m pytest tests/test_gpu_multi.py -q -x -k "$SEL" > gpurun_out/${TAG}_pytest_multi_n${N}.log 2>&1; el "pytest multi rc=$?"; tail -4 gpurun_out/${TAG}_pytest_multi_n${N}.log
 run peer HMG_DEBUG_CFG=1 -- --steps 5 --warmup 3 --no-e2e --no-cpu-baseline
-run peer_graph HMG_GRAPH=2 -- --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-also
-run nccl HMG_PEER=0 -- --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-also
+run peer_graph HMG_GRAPH=2 -- --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-also
+run nccl HMG_PEER=0 -- --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-also
 python - <<PY
 import json,glob
 for f in sorted(glob.glob('gpurun_out/${TAG}_bench_n${N}_*.log')):

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """BASELINE.json configs[4] (C5): matrix-free A*x and V-cycle throughput on a random piecewise coefficient
 field (recipe of tools/generate_st1_field.jl, alpha = 1, p = 1.5, seed 2) as a function of the number of
-stored DOFs.  One JSON line per problem; device-timed with CUDA events on the library's stream.
+stored DOFs.  The field comes from the library's cuFFT generator (hmg_generate_field, noise drawn on the device); the
+convergence of three V-cycles is recorded beside the timings.  One JSON line per problem; device-timed with CUDA events
+on the library's stream.
 
     python tools/sweep_c5.py [--max-gb 60] > profiles/rNN_c5_sweep.jsonl
 """
@@ -29,7 +31,9 @@ def main():
         ne = 2 * c ** 2 if dim == 2 else 6 * c ** 3
         if 9.5 * 8e-9 * nf * ne > args.max_gb:
             continue
-        mesh, sigma = hmg.inputs.checkerboard_problem(dim, c, field="random", seed=2)
+        mesh, _ = hmg.inputs.checkerboard_problem(dim, c)
+        cells = hmg.inputs.random_field_cells_device(dim, c, seed=2, alpha=1.0, p=1.5)       # cuFFT, on the device
+        sigma = hmg.inputs.conductivity_per_element(mesh, cells, (c / 2.0 + 1.0,) * dim)
         g = hmg.ImplicitFineGrid(mesh, levels, sigma, lam=1.0)
         st = g.state(levels)
         rng = np.random.default_rng(3)
@@ -43,18 +47,19 @@ def main():
         hmg.apply_constraint(st.x, levels, g)
         st.p.copy_from(st.x)
         hmg.rhs_a_xi_grad_v(st.b, g, np.ones(dim) / dim ** 0.5)
-        hmg.BaseLevel(g)
+        bl = hmg.BaseLevel(g)
+        hist = [float(v) for v in hmg.vcycles(g, bl, levels, SMOOTHING_STEPS, 3)]
         dofs = nf * ne
         reps = 20 if dofs < 2e8 else 10
         g.time_op(0, levels, 0, 3)
         ms_ax = g.time_op(0, levels, 0, reps) / reps
         g.time_op(1, levels, SMOOTHING_STEPS, 2)
         ms_v = g.time_op(1, levels, SMOOTHING_STEPS, 5) / 5
-        res = hmg.vcycles(g, None, levels, SMOOTHING_STEPS, 3) if False else None
         bv = vcycle_bytes_per_dof(dim, levels)
         print(json.dumps({
             "dim": dim, "cells_per_side": c, "grids": levels, "coarse_elements": ne, "stored_dofs": dofs,
-            "sigma_min_max": [float(sigma.min()), float(sigma.max())],
+            "sigma_min_max": [float(sigma.min()), float(sigma.max())], "field": "hmg_generate_field (cuFFT), seed 2",
+            "residual_after_vcycles_1_2_3": hist,
             "ax_ms": ms_ax, "ax_gdofs": dofs / ms_ax / 1e6, "ax_hbm_frac": 16.0 * dofs / ms_ax / 1e6 / peak,
             "vcycle_ms": ms_v, "vcycle_gdofs": dofs / ms_v / 1e6, "vcycle_hbm_frac": bv * dofs / ms_v / 1e6 / peak}), flush=True)
         g.close()
