@@ -533,7 +533,6 @@ hmg_ctx* create_impl(int dim, int nlevels, int64_t ne_global, int64_t nn, const 
             const CutCells& C = P.cut[kind];
             c->cut_nglobal[kind] = C.nglobal;
             c->cutv[kind].ncells = C.ncells();
-            c->cutv[kind].slot = c->dupload(C.slot);
             c->cutv[kind].off = c->dupload(C.offset);
             c->cutv[kind].own = c->dupload(C.owner);
             c->cutv[kind].first_local = c->dupload(C.first_local);
@@ -662,14 +661,8 @@ void do_broadcast(hmg_ctx* c, int l, double* x, int part = 3) {
 }
 void do_zero_all_but_one(hmg_ctx* c, int l, double* x) {
     check_launch(c, launch_zero_all_but_one(c->dim, c->level(l).view, c->tview, x, c->stream));
-    if (c->nranks > 1) {
-        const int64_t base[3] = {0, 0, 0};
-        check_launch(c, launch_cut(c->dim, CUT_ZERO_BUT_FIRST, c->level(l).view, c->cutv, base, x, nullptr, false, c->red, c->stream));
-    }
+    if (c->nranks > 1) check_launch(c, launch_cut_zero_but_first(c->dim, c->level(l).view, c->cutv, x, c->stream));
 }
-// post-op of a reduction kernel: on one GPU the kernel's last block derives the CG scalars itself; with
-// several ranks the kernel stores the local sum in S_TMP, the sums are all-reduced and a one-thread
-// kernel derives the scalars
 // Several ranks: with peer memory the kernel itself sums over the ranks (POST_GLOBAL) and nothing is left to do; on the
 // NCCL path the kernel stores the local sum in S_TMP, the sums are all-reduced and a one-thread kernel derives the scalars
 int kernel_post(hmg_ctx* c, int post) {

@@ -1049,20 +1049,29 @@ int launch_zero_all_but_one(int dim, const LevelView& L, const TopoView& T, doub
     return launch_interface<1, false>(dim, L, T, x, Reducer{}, 0, st);
 }
 
-// Cut cells (owners on several ranks): pack the partial sum over the local owners into the level's
-// packed buffer / write the all-reduced total back to the local owners / zero all but the globally
-// first owner.  One thread per (cell, paired node); faces, edges and vertices in ONE launch.
+// Cut cells (owners on several ranks).  One thread per (cell, paired node); faces, edges and vertices in ONE launch.
 struct CutAll {
     CutView kind[3];
     int npc[3];               // paired nodes per cell
-    int64_t base[3];          // first slot of the kind in the packed buffer
     const uint16_t* tab[3];   // packed node index of the t-th paired node of every local cell
     int64_t items[4];         // prefix sums of ncells * npc
 };
-template <int OP, bool SQ>
-__global__ void __launch_bounds__(256) cut_kernel(const LevelView L, const CutAll A, double* __restrict__ x, double* __restrict__ buf,
-                                                  const Reducer R) {
-    double sq = 0.0;
+static CutAll make_cut_all(int dim, const LevelView& L, const CutView* C) {
+    const int nfl = dim == 3 ? 4 : 0, nel = dim == 3 ? 6 : 3;
+    CutAll A;
+    A.items[0] = 0;
+    for (int kd = 0; kd < 3; ++kd) {
+        A.kind[kd] = C[kd];
+        A.npc[kd] = kd == 0 ? L.npf : (kd == 1 ? L.npe : 1);
+        A.tab[kd] = L.iface_idx + (kd == 0 ? 0 : (kd == 1 ? nfl * L.npf : nfl * L.npf + nel * L.npe));
+        A.items[kd + 1] = A.items[kd] + C[kd].ncells * A.npc[kd];
+        if (A.npc[kd] == 0) A.npc[kd] = 1;      // never divided by: the kind has no item
+    }
+    return A;
+}
+// zero_out_all_but_one! across ranks: every local copy of a cut node but the one of the GLOBALLY first owner
+// (src/implicit_fine_grid.jl:334-386; first_local says whether that owner lives here)
+__global__ void __launch_bounds__(256) cut_zero_kernel(const LevelView L, const CutAll A, double* __restrict__ x) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < A.items[3]; t += (int64_t)gridDim.x * blockDim.x) {
         const int kd = t < A.items[1] ? 0 : (t < A.items[2] ? 1 : 2);
         const CutView& C = A.kind[kd];
@@ -1071,41 +1080,18 @@ __global__ void __launch_bounds__(256) cut_kernel(const LevelView L, const CutAl
         const int64_t cell = q / npc;
         const int k = (int)(q - cell * npc);
         const int64_t b = C.off[cell], en = C.off[cell + 1];
-        const int64_t s = A.base[kd] + C.slot[cell] * npc + k;
-        double acc = OP == CUT_UNPACK ? buf[s] : 0.0;
         for (int64_t o = b; o < en; ++o) {
+            if (o == b && C.first_local[cell]) continue;
             const int32_t id = C.own[o];
             const int64_t el = id >> 3;
-            double* ptr = x + ((el >> L.wshift) * (int64_t)L.nf + __ldg(A.tab[kd] + (id & 7) * npc + k)) * L.W + (el & (L.W - 1));
-            if (OP == CUT_PACK) acc += *ptr;
-            else if (OP == CUT_UNPACK) *ptr = acc;
-            else if (!(o == b && C.first_local[cell])) *ptr = 0.0;
+            x[((el >> L.wshift) * (int64_t)L.nf + __ldg(A.tab[kd] + (id & 7) * npc + k)) * L.W + (el & (L.W - 1))] = 0.0;
         }
-        if (OP == CUT_PACK) buf[s] = acc;
-        if (SQ) sq = fma((double)(en - b) * acc, acc, sq);     // every local copy of the node holds the total
     }
-    if (SQ) block_reduce_finish(sq, R, POST_ADD, S_TMP);
 }
-// op: CUT_PACK / CUT_UNPACK / CUT_ZERO_BUT_FIRST; sq (with CUT_UNPACK): add (local copies) * total^2 to S_TMP
-int launch_cut(int dim, int op, const LevelView& L, const CutView* C, const int64_t* base, double* x, double* buf, bool sq,
-               const Reducer& R, cudaStream_t st) {
-    const int nfl = dim == 3 ? 4 : 0, nel = dim == 3 ? 6 : 3;
-    CutAll A;
-    A.items[0] = 0;
-    for (int kd = 0; kd < 3; ++kd) {
-        A.kind[kd] = C[kd];
-        A.npc[kd] = kd == 0 ? L.npf : (kd == 1 ? L.npe : 1);
-        A.base[kd] = base[kd];
-        A.tab[kd] = L.iface_idx + (kd == 0 ? 0 : (kd == 1 ? nfl * L.npf : nfl * L.npf + nel * L.npe));
-        A.items[kd + 1] = A.items[kd] + C[kd].ncells * A.npc[kd];
-        if (A.npc[kd] == 0) A.npc[kd] = 1;      // never divided by: the kind has no item
-    }
-    if (A.items[3] == 0 && !sq) return 0;
-    const unsigned grid = grid_for(std::max<int64_t>(A.items[3], 1), 256, sq ? R.max_blocks : 148 * 16);
-    if (op == CUT_PACK) cut_kernel<CUT_PACK, false><<<grid, 256, 0, st>>>(L, A, x, buf, R);
-    else if (op == CUT_UNPACK && sq) cut_kernel<CUT_UNPACK, true><<<grid, 256, 0, st>>>(L, A, x, buf, R);
-    else if (op == CUT_UNPACK) cut_kernel<CUT_UNPACK, false><<<grid, 256, 0, st>>>(L, A, x, buf, R);
-    else cut_kernel<CUT_ZERO_BUT_FIRST, false><<<grid, 256, 0, st>>>(L, A, x, buf, R);
+int launch_cut_zero_but_first(int dim, const LevelView& L, const CutView* C, double* x, cudaStream_t st) {
+    const CutAll A = make_cut_all(dim, L, C);
+    if (A.items[3] == 0) return 0;
+    cut_zero_kernel<<<grid_for(A.items[3], 256), 256, 0, st>>>(L, A, x);
     return 1;
 }
 
@@ -1193,17 +1179,7 @@ __global__ void __launch_bounds__(256) cut_p2p_kernel(const LevelView L, const C
 }
 int launch_cut_p2p(int dim, int op, const LevelView& L, const CutView* C, const int64_t* kbase, double* x, double* msg, bool sq,
                    const Reducer& R, cudaStream_t st, const CutPeer* peer, int sq_post) {
-    const int nfl = dim == 3 ? 4 : 0, nel = dim == 3 ? 6 : 3;
-    CutAll A;
-    A.items[0] = 0;
-    for (int kd = 0; kd < 3; ++kd) {
-        A.kind[kd] = C[kd];
-        A.npc[kd] = kd == 0 ? L.npf : (kd == 1 ? L.npe : 1);
-        A.base[kd] = 0;
-        A.tab[kd] = L.iface_idx + (kd == 0 ? 0 : (kd == 1 ? nfl * L.npf : nfl * L.npf + nel * L.npe));
-        A.items[kd + 1] = A.items[kd] + C[kd].ncells * A.npc[kd];
-        if (A.npc[kd] == 0) A.npc[kd] = 1;
-    }
+    const CutAll A = make_cut_all(dim, L, C);
     // (with peer memory the kernels also run for a rank without items: the exchange is collective)
     if (A.items[3] == 0 && !sq && !peer) return 0;
     const unsigned grid = grid_for(std::max<int64_t>(A.items[3], 1), 256, sq ? R.max_blocks : 148 * 16);

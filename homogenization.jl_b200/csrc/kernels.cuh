@@ -70,7 +70,6 @@ struct Reducer {
 // cut cells of one kind (faces / edges / vertices) this rank takes part in (multi-GPU, hmg_host.hpp)
 struct CutView {
     int64_t ncells;
-    const int64_t* slot;        // ordinal of the cell among the global cut cells of the kind
     const int64_t* off;         // CSR over the local owners
     const int32_t* own;         // local element * 8 + local id
     const uint8_t* first_local; // the globally first owner is own[off[c]]
@@ -87,7 +86,7 @@ struct CutPeer {
     const int32_t* nbr = nullptr;
     int nnbr = 0;
 };
-enum CutOp { CUT_PACK = 0, CUT_UNPACK = 1, CUT_ZERO_BUT_FIRST = 2 };
+enum CutOp { CUT_PACK = 0, CUT_UNPACK = 1 };
 
 enum ApplyMode { APPLY_AX = 0, APPLY_RESIDUAL = 1, APPLY_MULADD = 2 };
 
@@ -137,10 +136,8 @@ ApplyConfig make_apply_config(int dim, int m, int nf, int W, bool fused = false,
 int launch_interface_sum(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st, int part = 3);
 int launch_interface_sum_sq(int dim, const LevelView& L, const TopoView& T, double* x, const Reducer& R, int post, cudaStream_t st);
 int launch_zero_all_but_one(int dim, const LevelView& L, const TopoView& T, double* x, cudaStream_t st);
-// all three kinds (faces / edges / vertices) in one launch; base[kind] = first slot of the kind in the level's
-// packed buffer; sq (with CUT_UNPACK): add (local copies) * total^2 of every cut node to S_TMP
-int launch_cut(int dim, int op, const LevelView& L, const CutView* C, const int64_t* base, double* x, double* buf, bool sq,
-               const Reducer& R, cudaStream_t st);
+// zero every local copy of a cut node except the globally first owner's (all three kinds in one launch)
+int launch_cut_zero_but_first(int dim, const LevelView& L, const CutView* C, double* x, cudaStream_t st);
 // neighbour exchange of the cut cells: CUT_PACK writes the partial sum of every cut node into the message of every
 // rank that shares it, CUT_UNPACK adds the partial sums of all sharing ranks in ascending rank order (every rank gets
 // the same bits).  kbase[rank * 3 + kind] = first entry of the kind's section in the message to / from `rank`.
