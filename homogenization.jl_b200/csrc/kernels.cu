@@ -123,10 +123,7 @@ constexpr long long PEER_TIMEOUT_CYCLES = 20000000000ll;
 __device__ __forceinline__ void peer_wait_ge(const unsigned long long* p, unsigned long long want) {
     const long long t0 = clock64();
     while (ld_acquire_sys(p) < want) {
-        if (clock64() - t0 > PEER_TIMEOUT_CYCLES) {
-            printf("hmg: rank timed out waiting for a peer (sequence %llu)\n", want);
-            __trap();
-        }
+        if (clock64() - t0 > PEER_TIMEOUT_CYCLES) __trap();     // (no printf: a call in here costs every reduction kernel registers)
         __nanosleep(20);
     }
 }
@@ -225,6 +222,9 @@ constexpr int APPLY_MAXT = 16 * 32;    // 15 consumer warps + the producer warp:
 #ifndef HMG_TD2
 #define HMG_TD2 4
 #endif
+#ifndef HMG_TD3_DOT
+#define HMG_TD3_DOT 3      // values of b in flight per lane in the 3D residual with the fused reduction (2: 24 instead of 48 bytes of spills, but 0.6 % slower V-cycles)
+#endif
 #ifndef HMG_MAXT3
 #define HMG_MAXT3 512
 #endif
@@ -270,20 +270,16 @@ template <int DIM, int W, int MODE, bool DOT, bool STORE = true> struct OutDev {
     double sa;
     unsigned cm;
     double dsum;
-    double mw[4];          // owners of the cells of the single-face classes
-    unsigned long long ml, mh;   // owners of every class, one byte each
+    unsigned long long ml, mh;   // owners of every class, one byte each (converted where a boundary node needs it:
+                                 // keeping the four face weights as doubles cost the dot variants 8 registers and spills)
     template <int CLS> __device__ __forceinline__ double weight() const {
         if (CLS == 0) return 1.0;
-        if (CLS == 1) return mw[0];
-        if (CLS == 2) return mw[1];
-        if (CLS == 4) return mw[2];
-        if (CLS == 8) return mw[3];
         return (double)(unsigned)((CLS < 8 ? (ml >> (8 * (CLS & 7))) : (mh >> (8 * (CLS & 7)))) & 255ull);
     }
     // b / y of the next TD nodes travel in registers (they come from L2, where the producer's bulk prefetch
     // put them): the load of node k + TD is issued before node k is finished, which keeps
     // warps x TD x 256 bytes in flight per SM
-    static constexpr int TD = DIM == 2 ? HMG_TD2 : 3;
+    static constexpr int TD = DIM == 2 ? HMG_TD2 : (DOT ? HMG_TD3_DOT : 3);
     double tq[TD];
     int klast;
     __device__ __forceinline__ void begin(int k0, int k1) {
@@ -536,10 +532,6 @@ __global__ void __launch_bounds__(DIM == 3 ? HMG_MAXT3 : APPLY_MAXT, 1) apply_ke
                         hi |= (unsigned long long)__ldg(mp + (c + 8) * APPLY_W) << (8 * c);
                     }
                     out.ml = lo; out.mh = hi;
-                    out.mw[0] = (double)(unsigned)((lo >> 8) & 255ull);
-                    out.mw[1] = (double)(unsigned)((lo >> 16) & 255ull);
-                    out.mw[2] = (double)(unsigned)((lo >> 32) & 255ull);
-                    out.mw[3] = (double)(unsigned)(hi & 255ull);
                 }
                 su = (int)(u * nf - g0);
                 ybase = a.y + u * (int64_t)nf * APPLY_W + el;
