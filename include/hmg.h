@@ -16,6 +16,8 @@
  *     the library permutes to its lattice order and interleaves groups of columns internally.
  *   - a context is owned by the caller (hmg_destroy), is not thread-safe, and all calls are
  *     stream-ordered on the context's CUDA stream; calls that return host data synchronise.
+ *     The library keeps per-device launch attributes in process-wide tables without a lock: make the calls
+ *     of one process from one host thread at a time (one process per GPU is the multi-GPU model).
  *   - there is no CPU fallback: without a CUDA device hmg_create fails.
  */
 #ifndef HMG_B200_H
