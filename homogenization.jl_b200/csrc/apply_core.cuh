@@ -219,17 +219,25 @@ HMG_HD void sweep_line(const Op& op, const StencilTab<DIM>& T, const Mem& mem, i
         }
     }
     const int kend = g.k1 < g.L - 1 ? g.k1 : g.L - 1;
+    // running pointers to what node k loads next -- xp on the centre line, the minus lines at k, the plus lines at
+    // k + 1: one add per line and TWO nodes (the second node of the unrolled pair is an immediate offset) instead of
+    // a multiply-add from k per load (15 integer instructions per two nodes in the 3D loop of round 1)
+    const double* ac = mem.ptr(g.bc + (k + 1) * RS);
+    const double *am[NP], *ap[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) { am[q] = mem.ptr(g.bm[q] + k * RS); ap[q] = mem.ptr(g.bp[q] + (k + 1) * RS); }
     auto node = [&](int kk) {
-        xp = mem(g.bc + (kk + 1) * RS);
+        xp = mem.ld(ac);
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
-            if (uses_minus_k<DIM, MID>(q) || uses_minus_km<DIM, MID>(q) || uses_minus_km<DIM, LAST>(q)) Mk[q] = mem(g.bm[q] + kk * RS);
-            if (uses_plus_kp<DIM, MID>(q) || uses_plus_k<DIM, MID>(q) || uses_plus_k<DIM, LAST>(q)) Pp[q] = mem(g.bp[q] + (kk + 1) * RS);
+            if (uses_minus_k<DIM, MID>(q) || uses_minus_km<DIM, MID>(q) || uses_minus_km<DIM, LAST>(q)) Mk[q] = mem.ld(am[q]);
+            if (uses_plus_kp<DIM, MID>(q) || uses_plus_k<DIM, MID>(q) || uses_plus_k<DIM, LAST>(q)) Pp[q] = mem.ld(ap[q]);
         }
         out.template put<MID>(kk, eval_node<DIM, MID>(op, T, xm, x0, xp, Mm, Mk, Pk, Pp), x0);
         xm = x0; x0 = xp;
+        ac += RS;
 #pragma unroll
-        for (int q = 0; q < NP; ++q) { Mm[q] = Mk[q]; Pk[q] = Pp[q]; }
+        for (int q = 0; q < NP; ++q) { Mm[q] = Mk[q]; Pk[q] = Pp[q]; am[q] += RS; ap[q] += RS; }
     };
 #pragma unroll 1
     for (; k + 1 < kend; k += 2) { node(k); node(k + 1); }
@@ -237,8 +245,8 @@ HMG_HD void sweep_line(const Op& op, const StencilTab<DIM>& T, const Mem& mem, i
     if (g.k1 == g.L) {     // k == L - 1
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
-            if (uses_minus_k<DIM, LAST>(q)) Mk[q] = mem(g.bm[q] + k * RS);
-            if (uses_plus_kp<DIM, LAST>(q)) Pp[q] = mem(g.bp[q] + (k + 1) * RS);
+            if (uses_minus_k<DIM, LAST>(q)) Mk[q] = mem.ld(am[q]);
+            if (uses_plus_kp<DIM, LAST>(q)) Pp[q] = mem.ld(ap[q]);
         }
         out.template put<LAST>(k, eval_node<DIM, LAST>(op, T, xm, x0, 0.0, Mm, Mk, Pk, Pp), x0);
     }

@@ -75,6 +75,11 @@ struct HostMem {
         HMG_CHECK(addr >= 0 && addr < nf, "sweep reads a row outside the element");
         return x[addr];
     }
+    const double* ptr(int addr) const { return x + addr; }       // (may point past the element until it is read)
+    double ld(const double* p) const {
+        HMG_CHECK(p >= x && p < x + nf, "sweep reads a row outside the element");
+        return *p;
+    }
 };
 struct HostOut {
     double* y;

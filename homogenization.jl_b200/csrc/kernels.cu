@@ -317,6 +317,11 @@ struct SmemLoad {
         HMG_DEV_ASSERT(addr >= 0 && addr < limit);
         return sm[addr];
     }
+    __device__ __forceinline__ const double* ptr(int addr) const { return sm + addr; }
+    __device__ __forceinline__ double ld(const double* p) const {
+        HMG_DEV_ASSERT(p >= sm && p < sm + limit);
+        return *p;
+    }
 };
 
 // FUSEP (with MODE = AX): the input is not a stored vector but the new search direction p' = r + beta p of
