@@ -14,6 +14,7 @@ OBJS      := $(patsubst $(CSRC)/%,$(BUILD)/%.o,$(SRCS))
 all: $(LIB) oracle checked
 
 $(LIB): $(OBJS)
+	@mkdir -p $(dir $@)
 	$(NVCC) -shared -o $@ $(OBJS) -L$(CUDA_LIB) -lcusolver -lcublas -ldl \
 	    -Xlinker -rpath=$(CUDA_LIB)
 
