@@ -109,3 +109,34 @@ def test_coarse_inverse_follows_lambda():
             hmg.vcycle(pair.g, bl2, L, 3)
     finally:
         pair.close()
+
+
+def test_graph_replay_is_bit_identical_to_eager_launches(monkeypatch):
+    """From the second V-cycle of a kind on the launches are replayed from a CUDA graph (HMG_GRAPH, default on): the
+    residual history and the solution must equal the eager run bit for bit (deterministic reductions, the same kernels
+    with the same arguments), also across a change of lambda, which drops the captured graphs."""
+    def run(graph):
+        monkeypatch.setenv("HMG_GRAPH", graph)
+        pair = Pair(3, 2, 4, lam=0.7)
+        try:
+            assert pair.g.comm_mode() == "single"
+            L = pair.levels
+            x = pair.rand(L)
+            oi.broadcast_interfaces(x, pair.oimp, L)
+            oi.apply_constraint(x, L, pair.constraint, pair.oimp)
+            b = pair.rand(L)
+            st = pair.g.state(L)
+            st.x.set(x)
+            st.b.set(b)
+            bl = hmg.BaseLevel(pair.g)
+            hist = [hmg.vcycle(pair.g, bl, L, 3, resnorm=True) for _ in range(4)]
+            pair.g.set_lambda(0.35)
+            hist += [hmg.vcycle(pair.g, bl, L, 3, resnorm=True) for _ in range(3)]
+            hist += list(hmg.vcycles(pair.g, bl, L, 3, 3))
+            return np.array(hist), st.x.get()
+        finally:
+            pair.close()
+    h1, x1 = run("1")
+    h0, x0 = run("0")
+    assert np.array_equal(h1, h0)
+    assert np.array_equal(x1, x0)
