@@ -52,7 +52,11 @@ int hmg_destroy(hmg_ctx* ctx);
 
 /* multi-GPU: one process per GPU; coarse elements are partitioned by `owner_rank[ne]`; this
  * process keeps the columns with owner_rank == rank (global order preserved).  nccl_id is the
- * 128-byte ncclUniqueId produced by rank 0.  Only interface partial sums and scalars move. */
+ * 128-byte ncclUniqueId produced by rank 0.  Only interface partial sums and scalars move.
+ * Creation and hmg_destroy of a partitioned context are COLLECTIVE (every rank maps the communication buffers of all
+ * others and nobody may free one a peer still has mapped): call them on all ranks, in the same order; so is every
+ * operation that sums over interfaces or reduces a scalar (broadcast_interfaces, zero_out_all_but_one, dot, apply_global,
+ * smoothing_steps, vcycle(s), the integrals).  A rank that stops answering makes the others' kernels trap after ~10 s. */
 int hmg_create_partitioned(int dim, int nlevels, int64_t ne, int64_t nn, const double* base_nodes,
                            const int64_t* base_elems, const double* sigma, double lambda,
                            int device, int rank, int nranks, const int32_t* owner_rank,
