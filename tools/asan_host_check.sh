@@ -1,6 +1,6 @@
 #!/bin/bash
 # Host-side setup code under AddressSanitizer + UBSan (no GPU needed): builds the three host sources with g++ into
-# /tmp/hmg_asan and runs tools/asan_host_check.py against them.  Last run (round 1): clean.
+# /tmp/hmg_asan and runs tools/asan_host_check.py against them.  Last run (round 2, final code): clean.
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 OUT=/tmp/hmg_asan
