@@ -150,17 +150,6 @@ HMG_HD double eval_node(const Op& op, const StencilTab<DIM>& T, double xm, doubl
                         const double* Mm, const double* Mk, const double* Pk, const double* Pp) {
     using S = Sweep<DIM>;
     if (CLS == 0) {
-#ifdef HMG_FOUR_CHAINS
-        // four accumulation chains of depth <= 3 instead of two of depth 4-5 (the kernel stalls on fp64 latency)
-        double a = op.c0 * x0, b = op.cz * (xm + xp);
-        double c = op.ca[0] * (Mk[0] + Pk[0]), d = op.cb[0] * (Mm[0] + Pp[0]);
-#pragma unroll
-        for (int q = 1; q < S::NP; ++q) {
-            if (q & 1) { a = fma(op.ca[q], Mk[q] + Pk[q], a); b = fma(op.cb[q], Mm[q] + Pp[q], b); }
-            else { c = fma(op.ca[q], Mk[q] + Pk[q], c); d = fma(op.cb[q], Mm[q] + Pp[q], d); }
-        }
-        return (a + c) + (b + d);
-#else
         double a = op.c0 * x0, b = op.cz * (xm + xp);      // two chains for latency
 #pragma unroll
         for (int q = 0; q < S::NP; ++q) {
@@ -168,7 +157,6 @@ HMG_HD double eval_node(const Op& op, const StencilTab<DIM>& T, double xm, doubl
             b = fma(op.cb[q], Mm[q] + Pp[q], b);
         }
         return a + b;
-#endif
     }
     double a1 = 0.0, ah = 0.0;
     constexpr int wc = wcode<DIM>(CLS, 0);
@@ -251,10 +239,13 @@ HMG_HD void sweep_line(const Op& op, const StencilTab<DIM>& T, const Mem& mem, i
 #pragma unroll
         for (int q = 0; q < NP; ++q) { Mm[q] = Mk[q]; Pk[q] = Pp[q]; am[q] += RS; ap[q] += RS; }
     };
-#ifdef HMG_UNROLL4
+    // four nodes per trip where the registers allow it (Out::UNROLL4): one pointer add per line and four nodes, more
+    // loads in flight.  Measured on C4 / C2 (profiles/r02t_unroll_AB.jsonl): product 4.54 -> 4.38 ms, residual 6.74 ->
+    // 6.33 ms, 2D residual 2.84 -> 2.43 ms; the 3D variants with the fused reduction lose 2 % (registers) and keep two.
+    if constexpr (Out::UNROLL4) {
 #pragma unroll 1
-    for (; k + 3 < kend; k += 4) { node(k); node(k + 1); node(k + 2); node(k + 3); }
-#endif
+        for (; k + 3 < kend; k += 4) { node(k); node(k + 1); node(k + 2); node(k + 3); }
+    }
 #pragma unroll 1
     for (; k + 1 < kend; k += 2) { node(k); node(k + 1); }
     if (k < kend) { node(k); ++k; }

@@ -82,6 +82,7 @@ struct HostMem {
     }
 };
 struct HostOut {
+    static constexpr bool UNROLL4 = true;
     double* y;
     int* written;
     const uint32_t* nodeinfo;

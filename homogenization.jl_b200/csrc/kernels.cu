@@ -264,6 +264,7 @@ template <int DIM> __device__ __forceinline__ int64_t plane_at_or_after(int64_t 
 // nobody reads: alpha = rho / p.Ap needs the dot, x += alpha p needs p -- the vector Ap itself is dead)
 template <int DIM, int W, int MODE, bool DOT, bool STORE = true> struct OutDev {
     static constexpr int APPLY_W = W;
+    static constexpr bool UNROLL4 = DIM == 2 || !DOT;      // interior loop of the line sweep: 4 nodes per trip
     double *ylo, *yhi;     // bounds of the output vector (read by the checked build only)
     double* yl;            // output row of node 0 of the current line (lane included)
     const double* tl;
