@@ -653,11 +653,27 @@ void do_cut_exchange(hmg_ctx* c, int l, double* x) {
     if (c->nranks == 1 || slots == 0) return;
     do_cut_exchange_impl(c, l, x, false);
 }
-// part: 3 = every shared cell; 2 = only the cells with more than two owners (the two-owner cells are summed on the fly
-// by the CG update that follows) -- the cut cells are exchanged either way
+// The two halves of the peer-memory exchange.  Cut cells and rank-local cells touch disjoint entries, so the pack can
+// run BEFORE the local interface kernel: the messages cross NVLink (and the neighbours get to their own pack) while that
+// kernel sums the local cells, and the unpack finds the flags raised.  Measured on 8 ranks (tools/comm_bench.py, C4):
+// an exchange on its own costs 71 us at level 6 and 27 us on the small levels.
+bool peer_exchange(hmg_ctx* c, int l) { return c->nranks > 1 && c->peer_on && c->cut_slots(l) > 0; }
+void cut_pack_peer(hmg_ctx* c, int l, double* x) {
+    check_launch(c, launch_cut_p2p(c->dim, CUT_PACK, c->level(l).view, c->cutv, c->kbase[l - 1], x, nullptr, false, c->red, c->stream,
+                                   &c->cut_peer[l - 1]));
+}
+void cut_unpack_peer(hmg_ctx* c, int l, double* x, bool sq = false, int sq_post = POST_ADD) {
+    check_launch(c, launch_cut_p2p(c->dim, CUT_UNPACK, c->level(l).view, c->cutv, c->kbase[l - 1], x, nullptr, sq, c->red, c->stream,
+                                   &c->cut_peer[l - 1], sq_post));
+}
+// part: 3 = every shared cell; 1 / 2 = only the two-owner cells / the cells with more owners (measurement) -- the cut
+// cells are exchanged either way
 void do_broadcast(hmg_ctx* c, int l, double* x, int part = 3) {
+    const bool px = peer_exchange(c, l);
+    if (px) cut_pack_peer(c, l, x);
     check_launch(c, launch_interface_sum(c->dim, c->level(l).view, c->tview, x, c->stream, part));
-    do_cut_exchange(c, l, x);
+    if (px) cut_unpack_peer(c, l, x);
+    else do_cut_exchange(c, l, x);
 }
 void do_zero_all_but_one(hmg_ctx* c, int l, double* x) {
     check_launch(c, launch_zero_all_but_one(c->dim, c->level(l).view, c->tview, x, c->stream));
@@ -711,14 +727,17 @@ void do_broadcast_rho(hmg_ctx* c, int l, double* r) {
         if (n == 0) check_launch(c, launch_scalar_post(c->red, POST_RHO, 0, c->stream));     // no shared cell at all
         return;
     }
-    check_launch(c, launch_interface_sum_sq(c->dim, V, c->tview, r, c->red, POST_ADD, c->stream));
     const int64_t slots = c->cut_slots(l);
     if (c->peer_on) {
-        // the last kernel of the chain adds its part to S_TMP, sums over the ranks and sets rho
-        if (slots > 0) do_cut_exchange_impl(c, l, r, true, POST_RHO_ADD | POST_GLOBAL);
+        // pack first (see do_broadcast); the last kernel of the chain adds its part to S_TMP, sums over the ranks and
+        // sets rho
+        if (slots > 0) cut_pack_peer(c, l, r);
+        check_launch(c, launch_interface_sum_sq(c->dim, V, c->tview, r, c->red, POST_ADD, c->stream));
+        if (slots > 0) cut_unpack_peer(c, l, r, true, POST_RHO_ADD | POST_GLOBAL);
         else check_launch(c, launch_scalar_post(c->red, POST_RHO | POST_GLOBAL, 0, c->stream));
         return;
     }
+    check_launch(c, launch_interface_sum_sq(c->dim, V, c->tview, r, c->red, POST_ADD, c->stream));
     if (slots > 0) do_cut_exchange_impl(c, l, r, true);
     finish_reduction(c, POST_RHO, S_TMP);
 }
@@ -1605,6 +1624,13 @@ int hmg_time_op(hmg_ctx* c, int op, int level, int steps, int reps, float* ms_ou
         } else if (op == 12) {
             HMG_CHECK(c->level(level).cfg_fused.ring_rows > 0, "the fused p-update does not fit this level");
             do_fused_direction_product(c, level);
+        } else if (op == 17) {
+            // one scalar sum over all stored entries AND all ranks (the reduction pattern of every CG scalar)
+            check_launch(c, launch_dot(c->red, c->vecp(level, HMG_P), c->vecp(level, HMG_AP), c->nstored(level),
+                                       kernel_post(c, POST_STORE), S_TMP, c->stream));
+            finish_reduction(c, POST_STORE, S_TMP);
+        } else if (op == 18) {
+            do_cut_exchange(c, level, c->vecp(level, HMG_AP));       // pack, exchange with the neighbours, unpack
         } else if (op == 16) {
             check_launch(c, launch_x_update(c->red, c->vecp(level, HMG_X), c->vecp(level, HMG_P), c->nstored(level), c->stream));
         } else if (op == 11) {

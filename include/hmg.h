@@ -190,7 +190,8 @@ int hmg_synchronize(hmg_ctx* ctx);
  * rho), 9 = restriction level -> level-1, 10 = interpolation level-1 -> level, 11 = local apply with
  * the fused owner-weighted dot, 12 = the fused direction update + product of a CG step (p' = R + beta P
  * formed inside the apply kernel, AP = broadcast(constraint(A p'))), 13 / 14 = the interface kernel restricted to the
- * two-owner cells (faces in 3D, edges in 2D) / to the cells with more owners (local cells only), 16 = x += alpha P.  The
+ * two-owner cells (faces in 3D, edges in 2D) / to the cells with more owners (local cells only), 16 = x += alpha P, 17 = dot(P, AP) summed over
+ * the ranks (the pattern of every CG scalar), 18 = the cut-cell exchange of AP alone (partitioned contexts).  The
  * operation is
  * launched `reps` times back to back. */
 int hmg_time_op(hmg_ctx* ctx, int op, int level, int steps, int reps, float* ms_out);
