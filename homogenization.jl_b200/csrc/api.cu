@@ -877,6 +877,15 @@ int64_t staging_chunk(hmg_ctx* c, int nf) {
     return std::min<int64_t>(chunk, (c->ne + c->W - 1) / c->W * c->W);
 }
 
+// all ranks of a partitioned context meet here (collective): used where one rank does seconds of work the others do
+// not -- a kernel of theirs would otherwise spin on its peer mailbox for that long
+void rank_barrier(hmg_ctx* c) {
+    if (c->nranks == 1) return;
+    int* d = c->dalloc<int>(1);
+    NCCL_OK(nccl().AllReduce(d, d, 1, ncclInt, ncclSum, c->comm, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->dfree(d);
+}
 void set_coarse_dense(hmg_ctx* c, int64_t n, const std::vector<int64_t>& colptr, const std::vector<int64_t>& rowval,
                       const std::vector<double>& nzval, const std::vector<int64_t>& interior0) {
     // dense Cholesky inverse on the device: A^-1 is formed once, every V-cycle applies it with one
@@ -989,7 +998,7 @@ void assemble_coarse_impl(hmg_ctx* c) {
     c->coarse_internal = true;
     c->coarse_gen = c->op_gen;
     c->drop_graphs();
-    if (c->rank != 0) { c->n_interior = n; return; }
+    if (c->rank != 0) { c->n_interior = n; rank_barrier(c); return; }      // wait for rank 0's factorisation
     for (int64_t e = 0; e < c->ne_global; ++e) {
         const double* ec = &coef[(size_t)e * cs];
         double P[3][3];
@@ -1018,6 +1027,7 @@ void assemble_coarse_impl(hmg_ctx* c) {
         cp[j + 1] = (int64_t)rv.size();
     }
     set_coarse_dense(c, n, cp, rv, nz, interior);
+    rank_barrier(c);
 }
 
 }  // namespace
@@ -1343,6 +1353,7 @@ int hmg_set_coarse_matrix(hmg_ctx* c, int64_t n, const int64_t* colptr, const in
     c->coarse_internal = false;
     c->coarse_gen = c->op_gen;
     c->drop_graphs();
+    rank_barrier(c);                       // (collective on a partitioned context: rank 0 factorises, the others wait)
     HMG_API_END
 }
 

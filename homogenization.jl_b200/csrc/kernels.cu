@@ -117,9 +117,10 @@ __device__ __forceinline__ double ld_relaxed_sys(const double* p) {
     asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
-// a peer that never answers (a rank that died) must not hang the GPU: ~10 s of spinning, then the kernel traps and the
-// host sees a launch failure
-constexpr long long PEER_TIMEOUT_CYCLES = 20000000000ll;
+// a peer that never answers (a rank that died) must not hang the GPU: ~60 s of spinning, then the kernel traps and the
+// host sees a launch failure.  (Ranks legitimately wait for each other for seconds where one of them does more host-side
+// work; the coarse factorisation on rank 0, the longest such wait, ends in a barrier of its own, api.cu.)
+constexpr long long PEER_TIMEOUT_CYCLES = 120000000000ll;
 __device__ __forceinline__ void peer_wait_ge(const unsigned long long* p, unsigned long long want) {
     const long long t0 = clock64();
     while (ld_acquire_sys(p) < want) {

@@ -56,7 +56,9 @@ int hmg_destroy(hmg_ctx* ctx);
  * Creation and hmg_destroy of a partitioned context are COLLECTIVE (every rank maps the communication buffers of all
  * others and nobody may free one a peer still has mapped): call them on all ranks, in the same order; so is every
  * operation that sums over interfaces or reduces a scalar (broadcast_interfaces, zero_out_all_but_one, dot, apply_global,
- * smoothing_steps, vcycle(s), the integrals).  A rank that stops answering makes the others' kernels trap after ~10 s. */
+ * smoothing_steps, vcycle(s), the integrals) and the coarse-matrix setup (hmg_assemble_coarse / hmg_set_coarse_matrix:
+ * rank 0 factorises, the others wait in a barrier).  A rank that stops answering makes the others' kernels trap after
+ * about a minute. */
 int hmg_create_partitioned(int dim, int nlevels, int64_t ne, int64_t nn, const double* base_nodes,
                            const int64_t* base_elems, const double* sigma, double lambda,
                            int device, int rank, int nranks, const int32_t* owner_rank,
