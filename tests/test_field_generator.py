@@ -69,3 +69,23 @@ def test_generator_rejects_odd_extents_without_touching_the_gpu_path():
     out = np.zeros(20)
     assert lib.hmg_generate_field(2, ns, 1, 1.0, 1.5, 1, None, out.ctypes.data_as(C.c_void_p), 0) != 0
     assert b"even" in lib.hmg_last_error() or b"CUDA" in lib.hmg_last_error()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(8, 12), (6, 4, 10)])
+def test_device_field_with_different_extents(shape):
+    """The C entry point takes one extent per axis (tools/generate_st1_field.jl:86-90 does too): the wrapped frequency
+    index of every axis uses that axis' own half length."""
+    import ctypes as C
+    dim = len(shape)
+    noise = np.random.default_rng(9).standard_normal(shape)
+    lib = hmg.load()
+    ns = (C.c_int * 3)(*(list(shape) + [1] * (3 - dim)))
+    out = np.empty(shape)
+    hmg._lib.check(lib.hmg_generate_field(dim, ns, 0, 0.5, 1.5, 1, noise.ctypes.data_as(C.c_void_p),
+                                          out.ctypes.data_as(C.c_void_p), 0))
+    k = np.meshgrid(*[np.fft.fftfreq(n) * n for n in shape], indexing="ij")
+    kn = np.sqrt(sum(q * q for q in k))
+    G = np.real(np.fft.ifftn(np.fft.fftn(noise) * (1.0 + kn) ** (-1.5)))
+    expect = np.exp(0.5 * np.abs(G / G.std()))
+    assert np.max(np.abs(out - expect) / expect) <= 1e-12

@@ -140,3 +140,33 @@ def test_graph_replay_is_bit_identical_to_eager_launches(monkeypatch):
     h0, x0 = run("0")
     assert np.array_equal(h1, h0)
     assert np.array_equal(x1, x0)
+
+
+@pytest.mark.parametrize("steps", [0, 1, 2, 4])
+def test_vcycle_with_other_step_counts(steps):
+    """The last CG step of a smoothing call is cut down to alpha and x += alpha p where nobody reads its residual
+    (DESIGN.md section 4): with 1 step that is also the FIRST step (direction = r), with 0 steps there is none.  The
+    top level's step count varies, the levels below always take 2 (src/multigrid.jl:109)."""
+    pair = Pair(3, 2, 4, lam=0.7)
+    try:
+        L = pair.levels
+        top = pair.ostates[-1]
+        x = pair.rand(L)
+        oi.broadcast_interfaces(x, pair.oimp, L)
+        oi.apply_constraint(x, L, pair.constraint, pair.oimp)
+        top.x[:, :] = x
+        oi.local_rhs(top.b, pair.oimp)
+        st = pair.g.state(L)
+        st.x.set(top.x)
+        st.b.set(top.b)
+        obl, _, _ = pair.obase_level()
+        bl = hmg.BaseLevel(pair.g)
+        for _ in range(3):
+            om.vcycle(pair.oimp, obl, pair.oops, pair.ostates, L, steps)
+            oi.zero_out_all_but_one(top.r, pair.oimp, L)
+            ro = float(np.linalg.norm(top.r.ravel(order="K")))
+            rg = hmg.vcycle(pair.g, bl, L, steps, resnorm=True)
+            assert abs(rg - ro) <= 1e-10 * ro, (steps, rg, ro)
+        assert relerr(st.x.get(), top.x) <= 1e-10
+    finally:
+        pair.close()
