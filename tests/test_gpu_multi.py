@@ -33,10 +33,15 @@ def _worker(rank, world, nccl_id, case, results, peer="1"):
     from oracle.multigrid import LevelState as OLevelState, BaseLevel as OBaseLevel
     from oracle import implicit as oi, operators as oo, multigrid as om
 
-    dim, c, levels = case
+    dim, c, levels = case[:3]
     lam = 0.7
     mesh, sigma = hmg.inputs.checkerboard_problem(dim, c)
-    owner = hmg.inputs.spatial_partition(mesh, world)
+    if len(case) > 3 and case[3] == "random":
+        # every element on a random rank: cut cells everywhere, most shared cells have owners on both sides
+        owner = np.random.default_rng(23).integers(0, world, mesh.nelements).astype(np.int32)
+        owner[:world] = np.arange(world)
+    else:
+        owner = hmg.inputs.spatial_partition(mesh, world)
     g = hmg.ImplicitFineGrid(mesh, levels, sigma, lam=lam, device=rank, owner_rank=owner, rank=rank, nranks=world,
                              nccl_id=nccl_id)
     l2g = g.local_elements()
@@ -112,6 +117,23 @@ def test_two_gpus_match_the_oracle_on_the_whole_mesh(case):
     mp.spawn(_worker, args=(2, bytes(raw), case, results), nprocs=2, join=True)
     got = dict(results.get() for _ in range(2))
     assert got[0] == got[1]          # every rank sees the same residual history
+
+
+def test_two_gpus_random_ownership_matches_the_oracle():
+    """No spatial structure: every coarse element on a random one of the two ranks, so nearly every shared face, edge
+    and vertex is a cut cell with several local owners on both sides -- the peer-memory exchange carries almost the
+    whole interface sum."""
+    if _ngpus() < 2:
+        pytest.skip("needs two GPUs")
+    import torch
+    import torch.multiprocessing as mp
+    raw = (C.c_ubyte * 128)()
+    hmg._lib.check(hmg.load().hmg_nccl_unique_id(raw))
+    ctx = mp.get_context("spawn")
+    results = ctx.SimpleQueue()
+    mp.spawn(_worker, args=(2, bytes(raw), (3, 3, 4, "random"), results), nprocs=2, join=True)
+    got = dict(results.get() for _ in range(2))
+    assert got[0] == got[1]
 
 
 def test_two_gpus_nccl_path_matches_the_oracle():
