@@ -505,9 +505,9 @@ __global__ void __launch_bounds__(DIM == 3 ? HMG_MAXT3 : APPLY_MAXT, 1) apply_ke
             // advance the cursor by `step` tasks
             i += step;
             for (;;) {
-                // 3D: runs of RL lines, or (SEGS < 30, RL = 1) every line cut into ceil(L / 2^SEGS) segments along k, so
-                // that the warps of the CTA spread over fewer lines of the plane (a smaller window in the ring)
-                const int cnt = DIM == 3 ? (SEGS < 30 ? (t + 1) * ((m - t + (1 << SEGS)) >> SEGS) : (t + RL) / RL)
+                // 3D: runs of RL lines, or (SEGS < 30, RL = 1) every line longer than 2^SEGS nodes cut into two halves along
+                // k, so that the warps of the CTA spread over fewer lines of the plane (a smaller window in the ring)
+                const int cnt = DIM == 3 ? (SEGS < 30 ? (t + 1) << (m - t + 1 > (1 << SEGS) ? 1 : 0) : (t + RL) / RL)
                                          : ((m - t + (1 << SEGS)) >> SEGS);
                 if (i < cnt) break;
                 i -= cnt;
@@ -550,10 +550,11 @@ __global__ void __launch_bounds__(DIM == 3 ? HMG_MAXT3 : APPLY_MAXT, 1) apply_ke
             if constexpr (DIM == 3) {
                 int k0 = 0, k1 = m - t + 1;
                 if (SEGS < 30) {
-                    const int Lt = m - t + 1, nseg = (Lt + (1 << SEGS) - 1) >> SEGS;
-                    il = i / nseg;
-                    const int len = (Lt + nseg - 1) / nseg;             // balanced segments
-                    k0 = (i - il * nseg) * len;
+                    // (shifts only: the two integer divisions of a general segment count cost ~50 instructions per task)
+                    const int Lt = m - t + 1, two = Lt > (1 << SEGS) ? 1 : 0;
+                    il = i >> two;
+                    const int len = (Lt + two) >> two;                  // balanced halves
+                    k0 = (i & two) * len;
                     k1 = min(Lt, k0 + len);
                     nl = 1;
                 } else {
@@ -648,7 +649,7 @@ __global__ void __launch_bounds__(DIM == 3 ? HMG_MAXT3 : APPLY_MAXT, 1) apply_ke
                     g.bc = qc * APPLY_W + el;
                     g.bm[0] = qm[0] * APPLY_W + el; g.bm[1] = qm[1] * APPLY_W + el; g.bm[2] = qm[2] * APPLY_W + el;
                     g.bp[0] = qp[0] * APPLY_W + el; g.bp[1] = qp[1] * APPLY_W + el; g.bp[2] = qp[2] * APPLY_W + el;
-                    if (g.k0 < g.k1) {                  // (a segment can only be empty for segment lengths below 4)
+                    if (g.k0 < g.k1) {                  // (a half can only be empty for lines of one node, which are never cut)
                         out.begin(g.k0, g.k1);
                         run_line3(op, a.T, mem, APPLY_W, g, t, il + li, out);
                     }
@@ -709,7 +710,7 @@ static ApplyConfig make_apply_config_slots(int dim, int m, int nf, int W, bool f
     c.nwarps = std::max(1, std::min(maxw - 1, envi("HMG_APPLY_WARPS", maxw - 1)));
     c.ctas_per_sm = 1;
     c.oversub = envi("HMG_APPLY_OVERSUB", 0);
-    // 2D: log2(nodes per task); 3D: 30 = whole lines, else lines are cut into segments of <= 2^seg nodes (one line per task)
+    // 2D: log2(nodes per task); 3D: 30 = whole lines, else every line longer than 2^seg nodes is cut into two halves (one line per task)
     c.seg = dim == 2 ? std::max(2, std::min(8, envi("HMG_APPLY_SEG_SHIFT", 5))) : envi("HMG_APPLY_SEG3_SHIFT", 30);
     if (dim == 3 && (c.seg < 2 || c.seg > 8)) c.seg = 30;
     c.spill_rows = dim == 2 ? (1 << c.seg) + 3 : m + 3;       // rows a task may run past the base of a line
